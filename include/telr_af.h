@@ -151,6 +151,8 @@ int telr_af_dp(telr_af_ctx *ctx, int32_t preset, int32_t n_tasks, const telr_dp_
 const char *telr_af_strerror(int code);
 int telr_af_last_cuda(const telr_af_ctx *ctx);      /* last cudaError_t seen by this ctx */
 int telr_af_version(void);
+long long telr_af_launch_count(const telr_af_ctx *ctx);  /* kernels launched by this ctx so far */
+void *telr_af_stream(const telr_af_ctx *ctx);            /* the ctx's cudaStream_t (for event timing by the caller) */
 
 /* Host helper: ASCII -> 2-bit + N mask (one sequence; dst offsets in bases, multiple of 64). */
 int telr_pack_seq(const char *ascii, int32_t len, int64_t dst_off, uint32_t *seq2, uint32_t *nmask);

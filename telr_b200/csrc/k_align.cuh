@@ -1,0 +1,455 @@
+// k_align.cuh — kernel (d): base-level alignment.  One warp owns one (read x contig strand) problem at a
+// time (dynamic queue), runs the alignment coroutine of mm_align.cuh on lane 0 and executes every DP
+// request warp-wide.
+//
+// Replaces ksw_extd2_sse / ksw_ll_i16 (minimap2 ksw2_extd2_sse.c, ksw2_ll_sse.c) and the driver around
+// them (align.c) inside the `minimap2 -a` process the reference spawns at TELR_te.py:503-506.
+// Integer DP on the ALU pipes; no tensor cores (this is not a dense contraction).
+//
+// warp_extd2 (general path): anti-diagonal sweep, 32 cells per step, difference recurrence
+// (u,v,x,y,x2,y2 as int8 in an L1-resident per-warp scratch), direction bytes to the warp's traceback
+// buffer, exact max tracking with the reference's tie order, z-drop, approximate-max mode.
+#pragma once
+#include <cuda_runtime.h>
+#include "mm_align.cuh"
+
+namespace telr {
+
+constexpr int AL_THREADS = 128;
+constexpr int AL_WARPS = AL_THREADS / 32;
+
+struct DpScratch {
+    int8_t *u, *v, *x, *y, *x2, *y2;   // [maxT] each
+    int32_t *H;                        // [maxT]
+    int32_t *ll;                       // [6 * maxT] local-probe rows
+    uint8_t *dir; int64_t dir_cap;
+    uint32_t *ezcig; int32_t ezcap;
+    // shared pool of large traceback buffers for the rare task that does not fit `dir`
+    uint8_t *big; int64_t big_cap; int32_t n_big; int32_t *big_lock;
+};
+
+struct AlignArgs {
+    Opt o;
+    int32_t n_prob, read_base;       // read_base: global index of this chunk's first read
+    const uint32_t *seq2, *nmask;
+    const int64_t *read_off; const int32_t *read_len;
+    const int32_t *contig_len; const int64_t *ctg_boff; const uint8_t *ctg_bytes;
+    const int32_t *prob_read, *prob_ls, *prob_nca;
+    int32_t *prob_nregs;
+    const int64_t *prob_aoff, *prob_roff;
+    Anchor *anchors; Reg *regs;
+    // per-warp scratch
+    uint8_t *warp_scratch; size_t warp_scratch_stride;
+    int32_t max_qlen, max_tlen, max_na, cig_cap, reg_cap_max; int64_t dir_cap;
+    uint8_t *big; int64_t big_cap; int32_t n_big; int32_t *big_lock;
+    // outputs
+    int32_t *work_counter; const int32_t *work_list; int32_t n_work;
+    int32_t *err;
+    unsigned long long *stat_cells, *stat_tasks;
+    // M-blocks for the depth kernel
+    int2 *blocks; unsigned long long *n_blocks; int64_t blocks_cap;
+    int64_t *prob_blk_off; int32_t *prob_blk_cnt;
+    // optional alignment records
+    int32_t *aln_out;   /* 14 ints per record */ unsigned long long *n_aln; int64_t aln_cap;
+    uint32_t *cig_out; unsigned long long *n_cig; int64_t cig_out_cap;
+};
+
+__device__ __forceinline__ int dp_base(const uint8_t *p, int step, int comp, int i)
+{
+    int b = p[(ptrdiff_t)i * step];
+    return comp ? (b >= 4 ? 4 : 3 - b) : b;
+}
+
+struct EzPush {
+    uint32_t *c; int n, cap;
+    __device__ __forceinline__ void push(uint32_t op, int len)
+    {
+        if (n == 0 || op != (c[n - 1] & 0xf)) { if (n < cap) c[n] = (uint32_t)len << 4 | op; ++n; }
+        else c[n - 1] += (uint32_t)len << 4;
+    }
+};
+
+// two-piece affine extension / global DP, warp-wide.  R lives in shared memory.
+__device__ void warp_extd2(const Opt &o, const DpTask &T, DpRes &R, DpScratch &S, unsigned long long *cells_acc, int32_t *err)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    const int qlen = T.qlen, tlen = T.tlen, flag = T.flag;
+    if (lane == 0) { res_reset(R); R.cigar = S.ezcig; }
+    __syncwarp();
+    if (qlen <= 0 || tlen <= 0) return;
+    int q = o.q, e = o.e, q2 = o.q2, e2 = o.e2;
+    if (q2 + e2 < q + e) { int t = q; q = q2; q2 = t; t = e; e = e2; e2 = t; }
+    const int qe = q + e, qe2 = q2 + e2;
+    int w = T.w < 0 ? (tlen > qlen ? tlen : qlen) : T.w;
+    {
+        int min_sc = -o.b < -o.sc_ambi ? -o.b : -o.sc_ambi;
+        if (-min_sc > 2 * (q + e)) return;
+    }
+    int long_thres = e != e2 ? (q2 - q) / (e - e2) - 1 : 0;
+    if (q2 + e2 + long_thres * e2 > q + e + long_thres * e) ++long_thres;
+    const int long_diff = long_thres * (e - e2) - (q2 - q) - e2;
+    int ncol = qlen < tlen ? qlen : tlen;
+    if (ncol > w + 1) ncol = w + 1;
+    uint8_t *p = S.dir;
+    int big_slot = -1;
+    if ((int64_t)(qlen + tlen - 1) * ncol > S.dir_cap) {
+        if ((int64_t)(qlen + tlen - 1) * ncol > S.big_cap || S.n_big <= 0) {
+            if (lane == 0) { atomicOr(err, TELR_ERR_DIRCAP); R.zdropped = 1; }
+            __syncwarp();
+            return;
+        }
+        if (lane == 0) {        // take one of the shared large buffers (holders never wait on anything)
+            unsigned ns = 64;
+            for (int s = (blockIdx.x * AL_WARPS + (threadIdx.x >> 5)) % S.n_big;; s = (s + 1) % S.n_big) {
+                if (atomicCAS(&S.big_lock[s], 0, 1) == 0) { big_slot = s; break; }
+                __nanosleep(ns);
+                if (ns < 4096) ns <<= 1;
+            }
+            __threadfence();
+        }
+        big_slot = __shfl_sync(FULL, big_slot, 0);
+        p = S.big + (int64_t)big_slot * S.big_cap;
+    }
+    const bool approx = flag & KSW_APPROX_MAX, right = flag & KSW_RIGHT;
+    int8_t *u = S.u, *v = S.v, *x = S.x, *y = S.y, *x2 = S.x2, *y2 = S.y2;
+    int32_t *H = S.H;
+    for (int t = lane; t < tlen; t += 32) {
+        u[t] = v[t] = x[t] = y[t] = (int8_t)(-q - e);
+        x2[t] = y2[t] = (int8_t)(-q2 - e2);
+    }
+    __syncwarp();
+    // uniform running state (identical in every lane)
+    int pst = -1, pen = -1;
+    int32_t ez_max = 0, ez_max_t = -1, ez_max_q = -1, ez_mqe = KSW_NEG_INF, ez_mqe_t = -1, ez_mte = KSW_NEG_INF, ez_mte_q = -1;
+    int32_t ez_score = KSW_NEG_INF, zdropped = 0;
+    int32_t H0 = 0, last_H0_t = 0;
+    unsigned long long cells = 0;
+    const int nr = qlen + tlen - 1;
+    for (int r = 0; r < nr; ++r) {
+        int st = 0, en = tlen - 1;
+        if (st < r - qlen + 1) st = r - qlen + 1;
+        if (en > r) en = r;
+        if (st < (r - w + 1) >> 1) st = (r - w + 1) >> 1;
+        if (en > (r + w) >> 1) en = (r + w) >> 1;
+        if (st > en) { zdropped = 1; break; }
+        cells += (unsigned long long)(en - st + 1);
+        const int bnd = r == 0 ? -q - e : r < long_thres ? -e : r == long_thres ? long_diff : -e2;
+        int sx1, sx21, sv1;        // left neighbour of the first cell
+        if (st > 0) {
+            if (st - 1 >= pst && st - 1 <= pen) sx1 = x[st - 1], sx21 = x2[st - 1], sv1 = v[st - 1];
+            else sx1 = -q - e, sx21 = -q2 - e2, sv1 = -q - e;
+        } else sx1 = -q - e, sx21 = -q2 - e2, sv1 = bnd;
+        if (en == r && lane == 0) { y[r] = (int8_t)(-q - e); y2[r] = (int8_t)(-q2 - e2); u[r] = (int8_t)bnd; }
+        __syncwarp();
+        uint8_t *pr = p + (int64_t)r * ncol;
+        for (int c = (en - st) >> 5; c >= 0; --c) {
+            const int t = st + (c << 5) + lane;
+            const bool act = t <= en;
+            int ut = 0, yt = 0, y2t = 0, v1 = sv1, x1 = sx1, x21 = sx21, z = 0;
+            if (act) {
+                ut = u[t], yt = y[t], y2t = y2[t];
+                if (t > st) v1 = v[t - 1], x1 = x[t - 1], x21 = x2[t - 1];
+                int qc = dp_base(T.q, T.qstep, T.qcomp, r - t), tc = dp_base(T.t, T.tstep, 0, t);
+                z = (qc > 3 || tc > 3) ? -o.sc_ambi : qc == tc ? o.a : -o.b;
+            }
+            __syncwarp();
+            if (act) {
+                int a = x1 + v1, b = yt + ut, a2 = x21 + v1, b2 = y2t + ut, d;
+                if (!right) {
+                    d = a > z ? 1 : 0;  z = z > a ? z : a;
+                    d = b > z ? 2 : d;  z = z > b ? z : b;
+                    d = a2 > z ? 3 : d; z = z > a2 ? z : a2;
+                    d = b2 > z ? 4 : d; z = z > b2 ? z : b2;
+                } else {
+                    d = z > a ? 0 : 1;  z = z > a ? z : a;
+                    d = z > b ? d : 2;  z = z > b ? z : b;
+                    d = z > a2 ? d : 3; z = z > a2 ? z : a2;
+                    d = z > b2 ? d : 4; z = z > b2 ? z : b2;
+                }
+                if (z > o.a) z = o.a;
+                u[t] = (int8_t)(z - v1);
+                v[t] = (int8_t)(z - ut);
+                int tmp = z - q;  a -= tmp, b -= tmp;
+                tmp = z - q2;     a2 -= tmp, b2 -= tmp;
+                if (!right) {
+                    x[t] = (int8_t)((a > 0 ? a : 0) - qe);     d |= a > 0 ? 0x08 : 0;
+                    y[t] = (int8_t)((b > 0 ? b : 0) - qe);     d |= b > 0 ? 0x10 : 0;
+                    x2[t] = (int8_t)((a2 > 0 ? a2 : 0) - qe2); d |= a2 > 0 ? 0x20 : 0;
+                    y2[t] = (int8_t)((b2 > 0 ? b2 : 0) - qe2); d |= b2 > 0 ? 0x40 : 0;
+                } else {
+                    x[t] = (int8_t)((a >= 0 ? a : 0) - qe);     d |= a >= 0 ? 0x08 : 0;
+                    y[t] = (int8_t)((b >= 0 ? b : 0) - qe);     d |= b >= 0 ? 0x10 : 0;
+                    x2[t] = (int8_t)((a2 >= 0 ? a2 : 0) - qe2); d |= a2 >= 0 ? 0x20 : 0;
+                    y2[t] = (int8_t)((b2 >= 0 ? b2 : 0) - qe2); d |= b2 >= 0 ? 0x40 : 0;
+                }
+                pr[t - st] = (uint8_t)d;
+            }
+            __syncwarp();
+        }
+        if (!approx) {
+            int32_t max_H, max_t, Hen, Hst;
+            if (r > 0) {
+                Hen = en > 0 ? H[en - 1] + u[en] : H[en] + v[en];     // uniform load, before H[en-1] is advanced
+                __syncwarp();
+                const int en1 = st + (en - st) / 4 * 4;
+                int32_t bh = KSW_NEG_INF * 2; int brank = 0x7fffffff, bt = -1, hst = 0;
+                for (int t = st + lane; t < en; t += 32) {
+                    int32_t h = H[t] + v[t];
+                    H[t] = h;
+                    if (t == st) hst = h;
+                    int rank = t < en1 ? 1 + (((t - st) & 3) << 20) + ((t - st) >> 2) : 1 + (4 << 20) + (t - en1);
+                    if (h > bh || (h == bh && rank < brank)) bh = h, brank = rank, bt = t;
+                }
+                if (lane == 0) { H[en] = Hen; if (Hen > bh || (Hen == bh)) bh = Hen, brank = 0, bt = en; }
+#pragma unroll
+                for (int d = 16; d; d >>= 1) {
+                    int32_t oh = __shfl_xor_sync(FULL, bh, d); int orank = __shfl_xor_sync(FULL, brank, d), ot = __shfl_xor_sync(FULL, bt, d);
+                    if (oh > bh || (oh == bh && orank < brank)) bh = oh, brank = orank, bt = ot;
+                }
+                max_H = bh, max_t = bt;
+                Hst = st == en ? Hen : __shfl_sync(FULL, hst, 0);
+                __syncwarp();
+            } else {
+                Hen = Hst = (int32_t)v[0] - qe;
+                if (lane == 0) H[0] = Hen;
+                max_H = Hen, max_t = 0;
+                __syncwarp();
+            }
+            if (en == tlen - 1 && Hen > ez_mte) ez_mte = Hen, ez_mte_q = r - en;
+            if (r - st == qlen - 1 && Hst > ez_mqe) ez_mqe = Hst, ez_mqe_t = st;
+            // ksw_apply_zdrop
+            bool stop = false;
+            if (max_H > ez_max) ez_max = max_H, ez_max_t = max_t, ez_max_q = r - max_t;
+            else if (max_t >= ez_max_t && r - max_t >= ez_max_q) {
+                int tl = max_t - ez_max_t, ql = (r - max_t) - ez_max_q, l = tl > ql ? tl - ql : ql - tl;
+                if (T.zdrop >= 0 && ez_max - max_H > T.zdrop + l * e2) zdropped = 1, stop = true;
+            }
+            if (stop) break;
+            if (r == nr - 1 && en == tlen - 1) ez_score = Hen;
+        } else {
+            if (r > 0) {
+                if (last_H0_t >= st && last_H0_t <= en && last_H0_t + 1 >= st && last_H0_t + 1 <= en) {
+                    int d0 = v[last_H0_t], d1 = u[last_H0_t + 1];
+                    if (d0 > d1) H0 += d0; else H0 += d1, ++last_H0_t;
+                } else if (last_H0_t >= st && last_H0_t <= en) H0 += v[last_H0_t];
+                else ++last_H0_t, H0 += u[last_H0_t];
+            } else H0 = (int32_t)v[0] - qe, last_H0_t = 0;
+            if (r == nr - 1 && en == tlen - 1) ez_score = H0;
+        }
+        pst = st, pen = en;
+    }
+    if (lane == 0) {
+        atomicAdd(cells_acc, cells);
+        R.max = ez_max; R.max_t = ez_max_t; R.max_q = ez_max_q; R.mqe = ez_mqe; R.mqe_t = ez_mqe_t;
+        R.mte = ez_mte; R.mte_q = ez_mte_q; R.score = ez_score; R.zdropped = zdropped;
+        // ---- traceback (ksw_backtrack) ----
+        int i0 = -1, j0 = -1;
+        if (!zdropped && !(flag & KSW_EXTZ_ONLY)) i0 = tlen - 1, j0 = qlen - 1;
+        else if (!zdropped && (flag & KSW_EXTZ_ONLY) && ez_mqe + T.end_bonus > ez_max) R.reach_end = 1, i0 = ez_mqe_t, j0 = qlen - 1;
+        else if (ez_max_t >= 0 && ez_max_q >= 0) i0 = ez_max_t, j0 = ez_max_q;
+        if (i0 >= 0 && j0 >= 0) {
+            EzPush ep; ep.c = S.ezcig; ep.n = 0; ep.cap = S.ezcap;
+            int i = i0, j = j0, state = 0;
+            while (i >= 0 && j >= 0) {
+                int r = i + j, force_state = -1;
+                int st = 0, en = tlen - 1;
+                if (st < r - qlen + 1) st = r - qlen + 1;
+                if (en > r) en = r;
+                if (st < (r - w + 1) >> 1) st = (r - w + 1) >> 1;
+                if (en > (r + w) >> 1) en = (r + w) >> 1;
+                if (i < st) force_state = 2;
+                if (i > en) force_state = 1;
+                uint32_t tmp = force_state < 0 ? p[(int64_t)r * ncol + (i - st)] : 0;
+                if (state == 0) state = tmp & 7;
+                else if (!(tmp >> (state + 2) & 1)) state = 0;
+                if (state == 0) state = tmp & 7;
+                if (force_state >= 0) state = force_state;
+                if (state == 0) ep.push(0, 1), --i, --j;
+                else if (state == 1 || state == 3) ep.push(2, 1), --i;
+                else ep.push(1, 1), --j;
+            }
+            if (i >= 0) ep.push(2, i + 1);
+            if (j >= 0) ep.push(1, j + 1);
+            if (ep.n > ep.cap) { atomicOr(err, TELR_ERR_CIGCAP); ep.n = 0; }
+            if (!(flag & KSW_REV_CIGAR))
+                for (int k = 0; k < ep.n >> 1; ++k) { uint32_t t = ep.c[k]; ep.c[k] = ep.c[ep.n - 1 - k]; ep.c[ep.n - 1 - k] = t; }
+            R.n_cigar = ep.n;
+        }
+        if (big_slot >= 0) { __threadfence(); atomicExch(&S.big_lock[big_slot], 0); }
+    }
+    __syncwarp();
+}
+
+// local affine Smith-Waterman score probe with end coordinates (first maximum in target-major order)
+__device__ void warp_ll(const Opt &o, const DpTask &T, DpRes &R, DpScratch &S, unsigned long long *cells_acc)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    const int qlen = T.qlen, tlen = T.tlen, gapoe = o.q + o.e, gape = o.e;
+    int32_t *Ha = S.ll, *Hb = Ha + tlen, *Hc = Hb + tlen, *Ea = Hc + tlen, *Eb = Ea + tlen, *F = Eb + tlen;
+    for (int i = lane; i < tlen; i += 32) Ha[i] = Hb[i] = Hc[i] = Ea[i] = Eb[i] = F[i] = 0;
+    __syncwarp();
+    int32_t bh = 0; int bi = 0x7fffffff, bj = 0x7fffffff;
+    for (int d = 0; d < qlen + tlen - 1; ++d) {
+        const int ist = d - qlen + 1 > 0 ? d - qlen + 1 : 0, ien = d < tlen - 1 ? d : tlen - 1;
+        int32_t *Hcur = Ha, *Hp2 = Hb; const int32_t *Eprev = Ea; int32_t *Ecur = Eb;
+        // diagonal d lives in buffer d % 3, so d-2 is in buffer (d+1) % 3
+        switch (d % 3) { case 0: Hcur = Ha; Hp2 = Hb; break; case 1: Hcur = Hb; Hp2 = Hc; break; default: Hcur = Hc; Hp2 = Ha; break; }
+        if (d & 1) Eprev = Eb, Ecur = Ea;
+        for (int i = ist + lane; i <= ien; i += 32) {
+            const int j = d - i;
+            int qc = dp_base(T.q, T.qstep, T.qcomp, j), tc = dp_base(T.t, T.tstep, 0, i);
+            int32_t s = (qc > 3 || tc > 3) ? -o.sc_ambi : qc == tc ? o.a : -o.b;
+            int32_t hd = (i > 0 && j > 0) ? Hp2[i - 1] : 0;
+            int32_t ee = i > 0 ? Eprev[i - 1] : 0, ff = j > 0 ? F[i] : 0;
+            int32_t h = hd + s;
+            if (h < ee) h = ee;
+            if (h < ff) h = ff;
+            if (h < 0) h = 0;
+            Hcur[i] = h;
+            ee -= gape; if (ee < h - gapoe) ee = h - gapoe; if (ee < 0) ee = 0;
+            ff -= gape; if (ff < h - gapoe) ff = h - gapoe; if (ff < 0) ff = 0;
+            Ecur[i] = ee; F[i] = ff;
+            if (h > bh || (h == bh && h > 0 && (i < bi || (i == bi && j < bj)))) bh = h, bi = i, bj = j;
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        int32_t oh = __shfl_xor_sync(FULL, bh, d); int oi = __shfl_xor_sync(FULL, bi, d), oj = __shfl_xor_sync(FULL, bj, d);
+        if (oh > bh || (oh == bh && oh > 0 && (oi < bi || (oi == bi && oj < bj)))) bh = oh, bi = oi, bj = oj;
+    }
+    if (lane == 0) {
+        atomicAdd(cells_acc, (unsigned long long)qlen * (unsigned long long)tlen);
+        R.ll_score = bh; R.ll_qe = bh > 0 ? bj : -1; R.ll_te = bh > 0 ? bi : -1;
+    }
+    __syncwarp();
+}
+
+struct AlWarpSmem { AlnCtx c; DpTask task; DpRes res; int more; };
+
+__global__ void __launch_bounds__(AL_THREADS) k_align(const __grid_constant__ AlignArgs A)
+{
+    __shared__ AlWarpSmem WS[AL_WARPS];
+    const Opt &o = A.o;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned FULL = 0xffffffffu;
+    AlWarpSmem &W = WS[wid];
+    // carve the per-warp scratch
+    uint8_t *base = A.warp_scratch + (size_t)(blockIdx.x * AL_WARPS + wid) * A.warp_scratch_stride;
+    const size_t maxQ = ((size_t)A.max_qlen + 64) & ~(size_t)15, maxT = ((size_t)A.max_tlen + 64) & ~(size_t)15;
+    uint8_t *qfw = base; base += maxQ;
+    uint8_t *qrc = base; base += maxQ;
+    DpScratch S;
+    S.u = (int8_t *)base; base += maxT; S.v = (int8_t *)base; base += maxT; S.x = (int8_t *)base; base += maxT;
+    S.y = (int8_t *)base; base += maxT; S.x2 = (int8_t *)base; base += maxT; S.y2 = (int8_t *)base; base += maxT;
+    S.H = (int32_t *)base; base += maxT * 4;
+    S.ll = (int32_t *)base; base += maxT * 4 * 6;
+    S.ezcap = (int32_t)(maxQ + maxT); S.ezcig = (uint32_t *)base; base += (size_t)S.ezcap * 4;
+    uint32_t *cig = (uint32_t *)base; base += (size_t)A.cig_cap * 4;
+    int32_t *K = (int32_t *)base; base += ((size_t)A.max_na + 8) * 4;
+    uint8_t *hsb = base; base += hit_scratch_bytes((size_t)A.reg_cap_max + 1);
+    base = (uint8_t *)(((uintptr_t)base + 255) & ~(uintptr_t)255);
+    S.dir = base; S.dir_cap = A.dir_cap;
+    S.big = A.big; S.big_cap = A.big_cap; S.n_big = A.n_big; S.big_lock = A.big_lock;
+
+    for (;;) {
+        int wi = 0;
+        if (lane == 0) wi = atomicAdd(A.work_counter, 1);
+        wi = __shfl_sync(FULL, wi, 0);
+        if (wi >= A.n_work) break;
+        const int pidx = A.work_list[wi];
+        const int read = A.prob_read[pidx], ls = A.prob_ls[pidx], l = ls >> 1, strand = ls & 1;
+        const int qlen = A.read_len[read], L = A.contig_len[l];
+        // unpack the read (forward + reverse complement)
+        {
+            const int64_t off = A.read_off[read];
+            for (int i = lane; i < qlen; i += 32) {
+                int64_t pp = off + i;
+                int c = (A.seq2[pp >> 4] >> (2 * (pp & 15))) & 3;
+                if ((A.nmask[pp >> 5] >> (pp & 31)) & 1) c = 4;
+                qfw[i] = (uint8_t)c;
+                qrc[qlen - 1 - i] = (uint8_t)(c < 4 ? 3 - c : 4);
+            }
+        }
+        if (lane == 0) {
+            AlnCtx &c = W.c;
+            c.o = &A.o;
+            c.tseq = A.ctg_bytes + A.ctg_boff[l] + (strand ? L : 0); c.tlen = L;
+            c.qseq[0] = qfw; c.qseq[1] = qrc; c.qlen = qlen;
+            c.a = A.anchors + A.prob_aoff[pidx]; c.n_a = A.prob_nca[pidx];
+            c.regs = A.regs + A.prob_roff[pidx]; c.n_regs = A.prob_nregs[pidx];
+            c.cap_regs = (int)(A.prob_roff[pidx + 1] - A.prob_roff[pidx]);
+            c.cig = cig; c.cig_top = 0; c.cig_cap = (uint32_t)A.cig_cap;
+            hit_scratch_carve(c.hs, hsb, (size_t)A.reg_cap_max + 1);
+            c.K = K; c.capK = A.max_na + 8;
+            c.err = 0; c.n_tasks = 0;
+            c.phase = PH_START;
+            res_reset(W.res);
+        }
+        __syncwarp();
+        for (;;) {
+            if (lane == 0) W.more = aln_next(W.c, W.res, W.task) ? 1 : 0;
+            __syncwarp();
+            if (!W.more) break;
+            if (W.task.kind == 0) warp_extd2(o, W.task, W.res, S, A.stat_cells, A.err);
+            else warp_ll(o, W.task, W.res, S, A.stat_cells);
+            __syncwarp();
+        }
+        if (lane == 0) {
+            AlnCtx &c = W.c;
+            if (c.err) atomicOr(A.err, c.err);
+            atomicAdd(A.stat_tasks, (unsigned long long)c.n_tasks);
+            A.prob_nregs[pidx] = c.n_regs;
+            // M-blocks of every record samtools depth would count (everything but SECONDARY)
+            int nb = 0, ncg = 0;
+            for (int i = 0; i < c.n_regs; ++i) {
+                const Reg &r = c.regs[i];
+                ncg += r.n_cigar;
+                if (r.parent != r.id) continue;
+                const uint32_t *cg = c.cig + r.cig;
+                for (int k = 0; k < r.n_cigar; ++k) nb += (cg[k] & 0xf) == 0;
+            }
+            long long boff = (long long)atomicAdd(A.n_blocks, (unsigned long long)nb);
+            if (boff + nb > A.blocks_cap) { atomicOr(A.err, 32); nb = 0; boff = 0; }
+            A.prob_blk_off[pidx] = boff; A.prob_blk_cnt[pidx] = nb;
+            if (nb) {
+                int w = 0;
+                for (int i = 0; i < c.n_regs; ++i) {
+                    const Reg &r = c.regs[i];
+                    if (r.parent != r.id) continue;
+                    const uint32_t *cg = c.cig + r.cig;
+                    int pos = r.rs;
+                    for (int k = 0; k < r.n_cigar; ++k) {
+                        int op = cg[k] & 0xf, len = (int)(cg[k] >> 4);
+                        if (op == 0) { A.blocks[boff + w++] = make_int2(pos, len); pos += len; }
+                        else if (op == 2) pos += len;
+                    }
+                }
+            }
+            if (A.aln_out && c.n_regs > 0) {
+                long long ao = (long long)atomicAdd(A.n_aln, (unsigned long long)c.n_regs);
+                long long co = (long long)atomicAdd(A.n_cig, (unsigned long long)ncg);
+                if (ao + c.n_regs > A.aln_cap || co + ncg > A.cig_out_cap) atomicOr(A.err, 64);
+                else {
+                    for (int i = 0; i < c.n_regs; ++i) {
+                        const Reg &r = c.regs[i];
+                        int32_t *oo = A.aln_out + (ao + i) * 16;
+                        oo[0] = read + A.read_base; oo[1] = strand; oo[2] = r.rs; oo[3] = r.re; oo[4] = r.qs; oo[5] = r.qe; oo[6] = r.rev;
+                        oo[7] = (r.rev ? 0x10 : 0) | (r.parent != r.id ? 0x100 : !r.sam_pri ? 0x800 : 0);
+                        oo[8] = r.dp_max; oo[9] = r.mlen; oo[10] = r.blen; oo[11] = r.n_cigar;
+                        oo[12] = (int32_t)(co & 0xffffffffLL); oo[13] = (int32_t)(co >> 32);
+                        oo[14] = pidx + 2 * A.read_base; oo[15] = i;
+                        const uint32_t *cg = c.cig + r.cig;
+                        for (int k = 0; k < r.n_cigar; ++k) A.cig_out[co + k] = cg[k];
+                        co += r.n_cigar;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace telr

@@ -1,0 +1,410 @@
+// k_chain.cuh — kernels (b)+(c): per-locus contig minimizer index in shared memory, seed collection,
+// anchor sort, chaining DP with warp-shuffle max-scan, RMQ re-chaining, region generation.
+//
+// Replaces, per (read x contig strand), minimap2's mm_idx_gen/mm_idx_get (index.c), mm_seed_mz_flt /
+// mm_collect_matches (seed.c), collect_seed_hits + radix_sort_128x (map.c), mg_lchain_dp /
+// mg_lchain_rmq (lchain.c), mm_gen_regs / mm_set_parent / mm_select_sub (hit.c) — the work done inside
+// the `minimap2 -a -x <preset>` process the reference spawns at TELR_te.py:503-506.
+//
+// A persistent CTA takes one (locus, strand) at a time: it hashes that contig strand's minimizers into a
+// shared-memory table once, then its 8 warps stream the locus's reads against it.
+#pragma once
+#include <cuda_runtime.h>
+#include "mm_align.cuh"
+
+namespace telr {
+
+constexpr int CH_THREADS = 256;
+constexpr int CH_WARPS = CH_THREADS / 32;
+constexpr int IDX_SLOTS = 8192;          // power of two
+constexpr int IDX_MAXMZ = 4096;          // contig minimizers that fit the shared-memory index
+
+struct IdxSmem {
+    uint64_t keys[IDX_SLOTS];
+    uint32_t cnt[IDX_SLOTS];
+    uint32_t fill[IDX_SLOTS];
+    uint16_t start[IDX_SLOTS];
+    uint32_t occ_y[IDX_MAXMZ];
+    uint16_t slot_of[IDX_MAXMZ];
+    uint8_t occ_span[IDX_MAXMZ];
+    int hist[260];
+    int ws[40];
+    int mid_occ, n_keys, item;
+};
+
+struct ChainArgs {
+    Opt o;
+    int32_t n_loci, n_reads, mode;                 // mode 0: count anchors, 1: fill + chain
+    const int32_t *locus_read_begin;
+    const int64_t *mz_off; const uint64_t *mz_x; const uint32_t *mz_y; const uint16_t *selfcnt;
+    const int32_t *read_len; const uint32_t *read_hash;
+    int32_t *prob_na;                              // [n_prob]
+    int32_t *prob_read, *prob_ls;                  // [n_prob]
+    const int64_t *prob_aoff;                      // [n_prob+1]
+    const int64_t *prob_roff;                      // [n_prob+1]   region capacity offsets
+    Anchor *anchors; Reg *regs;
+    int32_t *prob_nregs, *prob_nca;
+    uint8_t *warp_scratch; size_t warp_scratch_stride; int32_t max_na;
+    int32_t *work_counter; int32_t *err;
+    unsigned long long *stat_anchors;
+};
+
+__device__ __forceinline__ uint32_t idx_hash(uint64_t key) { return (uint32_t)(mix64(key) >> 24); }
+
+// occurrences of a minimizer hash in the contig index
+__device__ __forceinline__ int idx_lookup(const IdxSmem &I, uint64_t key, int *start)
+{
+    uint32_t s = idx_hash(key) & (IDX_SLOTS - 1);
+    for (;;) {
+        uint64_t kk = I.keys[s];
+        if (kk == key) { *start = I.start[s]; return (int)I.cnt[s]; }
+        if (kk == ~0ULL) return 0;
+        s = (s + 1) & (IDX_SLOTS - 1);
+    }
+}
+
+__device__ void idx_build(IdxSmem &I, const Opt &o, int n_c, const uint64_t *cx, const uint32_t *cy)
+{
+    const int tid = threadIdx.x;
+    for (int i = tid; i < IDX_SLOTS; i += CH_THREADS) I.keys[i] = ~0ULL, I.cnt[i] = 0, I.fill[i] = 0;
+    for (int i = tid; i < 260; i += CH_THREADS) I.hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n_c; i += CH_THREADS) {
+        const uint64_t key = cx[i] >> 8;
+        uint32_t s = idx_hash(key) & (IDX_SLOTS - 1);
+        for (;;) {
+            unsigned long long old = atomicCAS((unsigned long long *)&I.keys[s], ~0ULL, (unsigned long long)key);
+            if (old == ~0ULL || old == key) break;
+            s = (s + 1) & (IDX_SLOTS - 1);
+        }
+        atomicAdd(&I.cnt[s], 1u);
+        I.slot_of[i] = (uint16_t)s;
+    }
+    __syncthreads();
+    {   // exclusive scan of cnt over slots -> start; 32 slots per thread
+        int sum = 0;
+        for (int c = 0; c < IDX_SLOTS / CH_THREADS; ++c) sum += (int)I.cnt[tid * (IDX_SLOTS / CH_THREADS) + c];
+        int tot, pre = block_excl_scan(sum, &tot, I.ws);
+        for (int c = 0; c < IDX_SLOTS / CH_THREADS; ++c) {
+            int s = tid * (IDX_SLOTS / CH_THREADS) + c;
+            I.start[s] = (uint16_t)pre;
+            pre += (int)I.cnt[s];
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < n_c; i += CH_THREADS) {
+        int s = I.slot_of[i];
+        int at = I.start[s] + (int)atomicAdd(&I.fill[s], 1u);
+        I.occ_y[at] = cy[i];
+        I.occ_span[at] = (uint8_t)(cx[i] & 0xff);
+    }
+    __syncthreads();
+    // lists in (span, position) order == the order minimap2's per-bucket sort leaves (buckets <= 64 entries)
+    for (int s = tid; s < IDX_SLOTS; s += CH_THREADS) {
+        int c = (int)I.cnt[s];
+        if (c > 0) atomicAdd(&I.hist[c < 255 ? c : 255], 1);
+        if (c > 1) {
+            int b = I.start[s];
+            for (int i = 1; i < c; ++i) {
+                uint32_t y = I.occ_y[b + i]; uint8_t sp = I.occ_span[b + i];
+                uint64_t kk = (uint64_t)sp << 32 | y;
+                int j = i;
+                while (j > 0 && ((uint64_t)I.occ_span[b + j - 1] << 32 | I.occ_y[b + j - 1]) > kk) {
+                    I.occ_y[b + j] = I.occ_y[b + j - 1], I.occ_span[b + j] = I.occ_span[b + j - 1];
+                    --j;
+                }
+                I.occ_y[b + j] = y, I.occ_span[b + j] = sp;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {     // mm_idx_cal_max_occ + mm_mapopt_update
+        int nk = 0;
+        for (int c = 1; c <= 255; ++c) nk += I.hist[c];
+        int mid = 0x7fffffff;
+        if (nk > 0 && o.mid_occ_frac > 0.f) {
+            uint32_t kk = (uint32_t)((1. - (double)o.mid_occ_frac) * nk);
+            int acc = 0, c;
+            for (c = 1; c <= 255; ++c) { acc += I.hist[c]; if ((uint32_t)acc > kk) break; }
+            mid = c + 1;
+        }
+        if (mid < o.min_mid_occ) mid = o.min_mid_occ;
+        if (o.max_mid_occ > o.min_mid_occ && mid > o.max_mid_occ) mid = o.max_mid_occ;
+        I.mid_occ = mid; I.n_keys = nk;
+    }
+    __syncthreads();
+}
+
+// ---- chaining DP: candidates of anchor i are scored 32 at a time; the sequential early-exit rule
+// (skip counter driven by t[] marks) is reproduced with three warp scans ----
+__device__ void chain_dp_warp(const Opt &o, int n, const Anchor *a, ChainScratch &s)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    int32_t *f = s.f, *p = s.p, *v = s.v, *t = s.t;
+    const int max_dist_x = tmax(o.max_gap, o.bw), max_dist_y = max_dist_x;
+    for (int i = lane; i < n; i += 32) t[i] = 0;
+    __syncwarp();
+    int st = 0, max_ii = -1;
+    for (int i = 0; i < n; ++i) {
+        const Anchor ai = a[i];
+        while (st < i && (ai.x >> 32 != a[st].x >> 32 || ai.x > a[st].x + (uint64_t)max_dist_x)) ++st;
+        if (i - st > o.max_chain_iter) st = i - o.max_chain_iter;
+        int32_t max_f = (int32_t)(ai.y >> 32 & 0xff);
+        int max_j = -1, n_skip = 0, end_j = st - 1;
+        for (int jb = i - 1; jb >= st; jb -= 32) {
+            const int j = jb - lane;
+            int32_t sc = INT32_MIN; int pj = -1;
+            if (j >= st) {
+                sc = link_score(ai, a[j], max_dist_x, max_dist_y, o.bw, o.chn_pen_gap, o.chn_pen_skip);
+                if (sc != INT32_MIN) { sc += f[j]; pj = p[j]; }
+            }
+            const bool valid = sc != INT32_MIN;
+            if (valid && pj >= 0) t[pj] = i;
+            __syncwarp();
+            const bool tj = valid && t[j] == i;
+            // exclusive prefix max of candidate scores
+            int32_t inc = valid ? sc : INT32_MIN;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { int32_t y = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc = inc > y ? inc : y; }
+            int32_t exc = __shfl_up_sync(FULL, inc, 1);
+            if (lane == 0) exc = INT32_MIN;
+            const int32_t pm = exc > max_f ? exc : max_f;
+            const bool is_new = valid && sc > pm;
+            const bool is_skip = valid && !is_new && tj;
+            // skip counter: N_k = max(N_{k-1} + d_k, 0)  ==  P_k - min(-N_0, min_{m<=k} P_m)
+            int P = is_skip ? 1 : (is_new ? -1 : 0);
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(FULL, P, d); if (lane >= d) P += y; }
+            int M = P;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(FULL, M, d); if (lane >= d) M = M < y ? M : y; }
+            const int N = P - (M < -n_skip ? M : -n_skip);
+            const unsigned brk = __ballot_sync(FULL, is_skip && N > o.max_chain_skip);
+            const int bl = brk ? __ffs(brk) - 1 : 32;
+            const unsigned newm = __ballot_sync(FULL, is_new) & (bl >= 32 ? FULL : ((1u << bl) - 1));
+            if (newm) {
+                int ln = 31 - __clz(newm);
+                max_f = __shfl_sync(FULL, sc, ln);
+                max_j = jb - ln;
+            }
+            if (brk) { end_j = jb - bl; break; }
+            n_skip = __shfl_sync(FULL, N, 31);
+        }
+        if (max_ii < 0 || ai.x - a[max_ii].x > (uint64_t)(int64_t)max_dist_x) {
+            int32_t bf = INT32_MIN; int bj = -1;       // argmax f over [st, i-1], ties to the largest j
+            for (int j = i - 1 - lane; j >= st; j -= 32) { int32_t fj = f[j]; if (fj > bf) bf = fj, bj = j; }
+#pragma unroll
+            for (int d = 16; d; d >>= 1) {
+                int32_t of = __shfl_xor_sync(FULL, bf, d); int oj = __shfl_xor_sync(FULL, bj, d);
+                if (oj >= 0 && (bj < 0 || of > bf || (of == bf && oj > bj))) bf = of, bj = oj;
+            }
+            max_ii = bj;
+        }
+        if (max_ii >= 0 && max_ii < end_j) {
+            int32_t tmp = link_score(ai, a[max_ii], max_dist_x, max_dist_y, o.bw, o.chn_pen_gap, o.chn_pen_skip);
+            if (tmp != INT32_MIN && max_f < tmp + f[max_ii]) max_f = tmp + f[max_ii], max_j = max_ii;
+        }
+        if (lane == 0) {
+            f[i] = max_f, p[i] = max_j;
+            v[i] = max_j >= 0 && v[max_j] > max_f ? v[max_j] : max_f;
+        }
+        if (max_ii < 0 || (ai.x - a[max_ii].x <= (uint64_t)(int64_t)max_dist_x && f[max_ii] < max_f)) max_ii = i;
+        __syncwarp();
+    }
+}
+
+// re-chaining pass: the range-minimum query over finished anchors is a warp-wide scan
+__device__ void chain_rmq_warp(const Opt &o, int n, const Anchor *a, ChainScratch &s)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    for (int i = lane; i < n; i += 32) s.t[i] = -1, s.v[i] = 0;
+    __syncwarp();
+    RmqWin w;
+    rmq_win_init(w, o);
+    for (int i = 0; i < n; ++i) {
+        rmq_win_advance(w, o, i, a);
+        const int32_t yi = (int32_t)a[i].y;
+        int best = -1; double bp = 0.0; int32_t by = 0;
+        for (int j = (w.st < w.i0 ? w.st : w.i0) + lane; j < w.i0; j += 32) {
+            const Anchor aj = a[j];
+            if (!rmq_in_range(aj, j, yi, w.max_dist)) continue;
+            double pri = rmq_pri(aj, s.f[j], o.chn_pen_gap);
+            if (best < 0 || rmq_better(pri, (int32_t)aj.y, j, bp, by, best)) best = j, bp = pri, by = (int32_t)aj.y;
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+            int ob = __shfl_xor_sync(FULL, best, d); double op = __shfl_xor_sync(FULL, bp, d); int32_t oy = __shfl_xor_sync(FULL, by, d);
+            if (ob >= 0 && (best < 0 || rmq_better(op, oy, ob, bp, by, best))) best = ob, bp = op, by = oy;
+        }
+        if (lane == 0) rmq_step(o, n, i, a, s, best, w.st_inner, w.i0, w.max_dist_inner);
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(CH_THREADS) k_chain(const __grid_constant__ ChainArgs A)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    IdxSmem &I = *reinterpret_cast<IdxSmem *>(smem_raw);
+    const Opt &o = A.o;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned FULL = 0xffffffffu;
+    const int n_items = 2 * A.n_loci;
+    for (;;) {
+        if (tid == 0) I.item = atomicAdd(A.work_counter, 1);
+        __syncthreads();
+        const int item = I.item;
+        __syncthreads();
+        if (item >= n_items) break;
+        const int l = item >> 1, strand = item & 1;
+        const int rb = A.locus_read_begin[l], nr = A.locus_read_begin[l + 1] - rb;
+        const int cseq = A.n_reads + strand * A.n_loci + l;
+        const int64_t cb = A.mz_off[cseq];
+        const int n_c = (int)(A.mz_off[cseq + 1] - cb);
+        if (n_c > IDX_MAXMZ) {
+            if (tid == 0) atomicOr(A.err, 16);
+            for (int r = tid; r < nr; r += CH_THREADS) {
+                int pidx = 2 * rb + strand * nr + r;
+                if (A.mode == 0) A.prob_na[pidx] = 0, A.prob_read[pidx] = rb + r, A.prob_ls[pidx] = item;
+                else A.prob_nregs[pidx] = 0, A.prob_nca[pidx] = 0;
+            }
+            continue;
+        }
+        idx_build(I, o, n_c, A.mz_x + cb, A.mz_y + cb);
+        const int mid_occ = I.mid_occ;
+        for (int r = wid; r < nr; r += CH_WARPS) {
+            const int read = rb + r, pidx = 2 * rb + strand * nr + r;
+            const int64_t qb = A.mz_off[read];
+            const int n = (int)(A.mz_off[read + 1] - qb);
+            const uint64_t *qx = A.mz_x + qb; const uint32_t *qy = A.mz_y + qb; const uint16_t *qc = A.selfcnt + qb;
+            const int qlen = A.read_len[read];
+            const bool do_flt = o.q_occ_frac > 0.0f && mid_occ > 0 && n > mid_occ;
+            const float thr = (float)n * o.q_occ_frac;
+            if (A.mode == 0) {
+                int na = 0;
+                for (int i = lane; i < n; i += 32) {
+                    int c = qc[i];
+                    if (do_flt && c > mid_occ && (float)c > thr) continue;
+                    int st, t = idx_lookup(I, qx[i] >> 8, &st);
+                    if (t <= mid_occ) na += t;
+                }
+#pragma unroll
+                for (int d = 16; d; d >>= 1) na += __shfl_xor_sync(FULL, na, d);
+                if (lane == 0) { A.prob_na[pidx] = na; A.prob_read[pidx] = read; A.prob_ls[pidx] = item; }
+                continue;
+            }
+            // ---------------- fill mode ----------------
+            const int64_t ao = A.prob_aoff[pidx];
+            const int n_a = (int)(A.prob_aoff[pidx + 1] - ao);
+            Anchor *a = A.anchors + ao;
+            Reg *regs = A.regs + A.prob_roff[pidx];
+            const int cap_regs = (int)(A.prob_roff[pidx + 1] - A.prob_roff[pidx]);
+            if (n_a == 0) { if (lane == 0) A.prob_nregs[pidx] = 0, A.prob_nca[pidx] = 0; continue; }
+            uint8_t *wsb = A.warp_scratch + (size_t)(blockIdx.x * CH_WARPS + wid) * A.warp_scratch_stride;
+            ChainScratch cs;
+            chain_scratch_carve(cs, wsb, (size_t)A.max_na + 1);
+            HitScratch hs;
+            hit_scratch_carve(hs, wsb + chain_scratch_bytes((size_t)A.max_na + 1), (size_t)(2 * (A.max_na / 3) + 8));
+            // indices of minimizers that survive the query-occurrence filter (capacity: max read length + 64)
+            int32_t *kept = (int32_t *)(wsb + chain_scratch_bytes((size_t)A.max_na + 1) + hit_scratch_bytes((size_t)(2 * (A.max_na / 3) + 8)));
+            int nk = 0;
+            for (int ib = 0; ib < n; ib += 32) {
+                int i = ib + lane;
+                bool keep = false;
+                if (i < n) { int c = qc[i]; keep = !(do_flt && c > mid_occ && (float)c > thr); }
+                unsigned m = __ballot_sync(FULL, keep);
+                if (keep) kept[nk + __popc(m & ((1u << lane) - 1))] = i;
+                nk += __popc(m);
+            }
+            __syncwarp();
+            int run = 0;
+            for (int jb = 0; jb < nk; jb += 32) {
+                int j = jb + lane, t = 0, st = 0; uint64_t x = 0; uint32_t y = 0; bool tandem = false;
+                if (j < nk) {
+                    int i = kept[j];
+                    x = qx[i]; y = qy[i];
+                    t = idx_lookup(I, x >> 8, &st);
+                    if (t > mid_occ) t = 0;
+                    if (t) {
+                        if (j > 0 && (qx[kept[j - 1]] >> 8) == (x >> 8)) tandem = true;
+                        if (j < nk - 1 && (qx[kept[j + 1]] >> 8) == (x >> 8)) tandem = true;
+                    }
+                }
+                int pre = t;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { int yv = __shfl_up_sync(FULL, pre, d); if (lane >= d) pre += yv; }
+                int tot = __shfl_sync(FULL, pre, 31);
+                pre -= t;
+                const uint32_t q_span = (uint32_t)(x & 0xff), q_pos = y;
+                for (int k = 0; k < t; ++k) {
+                    uint32_t ry = I.occ_y[st + k];
+                    int32_t rpos = (int32_t)(ry >> 1);
+                    Anchor an;
+                    if ((ry & 1) == (q_pos & 1)) {
+                        an.x = (uint64_t)(uint32_t)rpos;
+                        an.y = (uint64_t)q_span << 32 | (q_pos >> 1);
+                    } else {
+                        an.x = 1ULL << 63 | (uint64_t)(uint32_t)rpos;
+                        an.y = (uint64_t)q_span << 32 | (uint32_t)(qlen - ((int32_t)(q_pos >> 1) + 1 - (int32_t)q_span) - 1);
+                    }
+                    if (tandem) an.y |= SEED_TANDEM;
+                    a[run + pre + k] = an;
+                }
+                run += tot;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                rs_sort_emul(a, n_a, KeyX(), cs.sortws);
+                atomicAdd(A.stat_anchors, (unsigned long long)n_a);
+            }
+            __syncwarp();
+            chain_dp_warp(o, n_a, a, cs);
+            int n_u = 0, n_v = 0, rechain = 0, m = 0;
+            if (lane == 0) {
+                chain_backtrack(n_a, cs, o.min_cnt, o.min_chain_score, o.bw, &n_u, &n_v);
+                if (n_u > 0) {
+                    chain_compact(n_u, n_v, cs, a);
+                    if (o.bw_long > o.bw && n_u > 1) {
+                        int32_t st = (int32_t)a[0].y, en = (int32_t)a[(int32_t)cs.u[0] - 1].y;
+                        if (qlen - (en - st) > o.rmq_rescue_size || en - st > qlen * o.rmq_rescue_ratio) {
+                            for (int i = 0; i < n_u; ++i) m += (int32_t)cs.u[i];
+                            rs_sort_emul(a, m, KeyX(), cs.sortws);
+                            rechain = 1;
+                        }
+                    }
+                }
+            }
+            rechain = __shfl_sync(FULL, rechain, 0);
+            m = __shfl_sync(FULL, m, 0);
+            __syncwarp();
+            if (rechain) {
+                chain_rmq_warp(o, m, a, cs);
+                if (lane == 0) {
+                    chain_backtrack(m, cs, o.min_cnt, o.min_chain_score, o.bw_long, &n_u, &n_v);
+                    if (n_u > 0) chain_compact(n_u, n_v, cs, a);
+                }
+            }
+            if (lane == 0) {
+                int n_regs = 0, nca = 0;
+                if (n_u > 0) {
+                    if (n_u > cap_regs) { atomicOr(A.err, TELR_ERR_REGCAP); n_u = cap_regs; }
+                    for (int i = 0; i < n_u; ++i) nca += (int32_t)cs.u[i];
+                    uint32_t hash = A.read_hash[read];
+                    hash ^= wang_hash32((uint32_t)qlen) + o.seed_term;
+                    hash = wang_hash32(hash);
+                    regs_from_chains(hash, qlen, n_u, cs.u, a, regs, hs);
+                    n_regs = n_u;
+                    regs_set_parent(o, n_regs, regs, hs);
+                    regs_select_sub(o, 1, &n_regs, regs, hs, cap_regs);
+                }
+                A.prob_nregs[pidx] = n_regs;
+                A.prob_nca[pidx] = nca;
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace telr

@@ -1,0 +1,313 @@
+// k_sketch.cuh — kernel (a): batched (w,k)-minimizer sketching of reads and contig strands.
+//
+// Replaces mm_sketch() (minimap2 sketch.c) reached from the reference at TELR_te.py:505.
+// Reads are consumed from the 2-bit packed batch with 16-byte vector loads (64 bases per lane);
+// contig strands come from the nt4 byte copies made by k_unpack_contigs.  One CTA walks one sequence
+// in tiles of 2048 steps; every step evaluates, from the w+1 hashes around it, exactly the pushes the
+// sequential ring-buffer algorithm performs at that step (first-window special case, "new minimum",
+// "minimum left the window" with its identical-hash flush), so the emitted list is byte-identical to
+// mm_sketch, including around ambiguous bases.  Two passes: COUNT then WRITE into exact CSR offsets.
+// map-pb's homopolymer compression runs as a per-sequence pre-pass (run ends -> steps).
+#pragma once
+#include <cuda_runtime.h>
+#include "mm_types.cuh"
+
+namespace telr {
+
+constexpr int SK_THREADS = 256;
+constexpr int SK_TILE = 2048;
+constexpr int SK_CH = 64;     // code halo
+constexpr int SK_XH = 32;     // hash halo (>= w)
+
+struct SeqDesc {
+    int64_t off;     // base offset into the packed arrays (kind 0) or byte offset into bytes (kind 1)
+    int32_t len;
+    int32_t kind;
+};
+
+struct SketchArgs {
+    const uint32_t *seq2, *nmask;
+    const uint8_t *bytes;
+    const SeqDesc *seqs;
+    int32_t n_seq, w, k, hpc;
+    // HPC scratch, one slice per CTA
+    uint8_t *hp_code; int32_t *hp_pos; uint16_t *hp_rl; int64_t hp_stride;
+    // COUNT pass output / WRITE pass input
+    int32_t *counts;          // [n_seq]
+    const int64_t *offs;      // [n_seq+1]
+    uint64_t *mz_x; uint32_t *mz_y;
+};
+
+__device__ __forceinline__ int block_excl_scan(int v, int *total, int *smem_ws /* >= 9 ints */)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) smem_ws[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        int s = lane < (SK_THREADS / 32) ? smem_ws[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, s, d);
+            if (lane >= d) s += y;
+        }
+        if (lane < SK_THREADS / 32) smem_ws[lane] = s;
+    }
+    __syncthreads();
+    int base = wid ? smem_ws[wid - 1] : 0;
+    *total = smem_ws[SK_THREADS / 32 - 1];
+    __syncthreads();
+    return base + x - v;
+}
+
+struct SkSmem {
+    uint64_t X[SK_XH + SK_TILE];
+    int32_t pos[SK_XH + SK_TILE];
+    uint16_t rl[SK_CH + SK_TILE + 8];
+    uint8_t code[SK_CH + SK_TILE + 8];
+    uint8_t z[SK_XH + SK_TILE];
+    uint8_t lcap[SK_TILE];
+    int ws[16];
+};
+
+// pushes of the sequential algorithm at local step j (0-based in tile); X index = SK_XH + j
+template <class Emit> __device__ __forceinline__ void sk_step(const SkSmem &S, int j, int w, int k, Emit &emit)
+{
+    const uint64_t MAXV = ~0ULL;
+    const uint64_t *X = S.X + SK_XH + j;        // X[0] = this step, X[-d] = d steps back
+    const uint64_t info = X[0];
+    const int l = S.lcap[j];
+    uint64_t mp = MAXV; int mpd = w;            // previous minimum over steps -w..-1 (rightmost on ties)
+    for (int d = w; d >= 1; --d) { uint64_t v = X[-d]; if (v <= mp) mp = v, mpd = d; }
+    if (l == w + k - 1 && mp != MAXV) {
+        for (int d = w - 1; d >= 1; --d)
+            if (X[-d] == mp && d != mpd) emit(j - d);
+    }
+    if (info <= mp) {
+        if (l >= w + k && mp != MAXV) emit(j - mpd);
+    } else if (mpd == w) {
+        if (l >= w + k - 1 && mp != MAXV) emit(j - mpd);
+        uint64_t mn = MAXV; int mnd = w - 1;
+        for (int d = w - 1; d >= 0; --d) { uint64_t v = X[-d]; if (v <= mn) mn = v, mnd = d; }
+        if (l >= w + k - 1 && mn != MAXV) {
+            for (int d = w - 1; d >= 0; --d)
+                if (X[-d] == mn && d != mnd) emit(j - d);
+        }
+    }
+}
+
+struct SkCount { int n; __device__ __forceinline__ void operator()(int) { ++n; } };
+struct SkWrite {
+    const SkSmem *S; uint64_t *ox; uint32_t *oy; int64_t at;
+    __device__ __forceinline__ void operator()(int jj)
+    {
+        ox[at] = S->X[SK_XH + jj];
+        oy[at] = (uint32_t)S->pos[SK_XH + jj] << 1 | S->z[SK_XH + jj];
+        ++at;
+    }
+};
+
+__device__ __forceinline__ int sk_load_code(const SketchArgs &A, const SeqDesc &sd, int i)
+{
+    if (i < 0 || i >= sd.len) return 4;
+    if (sd.kind) return A.bytes[sd.off + i];
+    int64_t p = sd.off + i;
+    if ((A.nmask[p >> 5] >> (p & 31)) & 1) return 4;
+    return (A.seq2[p >> 4] >> (2 * (p & 15))) & 3;
+}
+
+template <bool WRITE> __global__ void __launch_bounds__(SK_THREADS) k_sketch(SketchArgs A)
+{
+    __shared__ SkSmem S;
+    const int tid = threadIdx.x;
+    const int w = A.w, k = A.k;
+    const uint64_t mask = (1ULL << 2 * k) - 1;
+    const int shift1 = 2 * (k - 1);
+    for (int seq = blockIdx.x; seq < A.n_seq; seq += gridDim.x) {
+        const SeqDesc sd = A.seqs[seq];
+        int n_steps = sd.len;
+        uint8_t *hpc = nullptr; int32_t *hpp = nullptr; uint16_t *hpr = nullptr;
+        if (A.hpc) {
+            // ---- homopolymer compression: one step per run of identical bases, one per ambiguous base ----
+            hpc = A.hp_code + (int64_t)blockIdx.x * A.hp_stride;
+            hpp = A.hp_pos + (int64_t)blockIdx.x * A.hp_stride;
+            hpr = A.hp_rl + (int64_t)blockIdx.x * A.hp_stride;
+            int done = 0, prev_end = -1;
+            for (int T0 = 0; T0 < sd.len; T0 += SK_TILE) {
+                for (int i = tid; i < SK_TILE + 1; i += SK_THREADS) S.code[i] = (uint8_t)sk_load_code(A, sd, T0 + i);
+                __syncthreads();
+                // flags for 8 consecutive positions per thread
+                int nf = 0; unsigned fm = 0;
+                for (int c = 0; c < 8; ++c) {
+                    int i = tid * 8 + c;
+                    if (T0 + i < sd.len) {
+                        int cc = S.code[i];
+                        bool e = cc == 4 || T0 + i == sd.len - 1 || S.code[i + 1] != cc;
+                        if (e) fm |= 1u << c, ++nf;
+                    }
+                }
+                int tot, base = block_excl_scan(nf, &tot, S.ws);
+                // previous run end for the first flagged position of this thread: search backwards
+                // (steps are written with pos; run length = pos - previous step pos)
+                for (int c = 0; c < 8; ++c)
+                    if (fm >> c & 1) {
+                        int i = tid * 8 + c;
+                        hpc[done + base] = S.code[i];
+                        hpp[done + base] = T0 + i;
+                        ++base;
+                    }
+                done += tot;
+                __syncthreads();
+            }
+            (void)prev_end;
+            n_steps = done;
+            __syncthreads();
+            for (int m = tid; m < n_steps; m += SK_THREADS) {
+                int prev = m ? hpp[m - 1] : -1;
+                int r = hpp[m] - prev;
+                hpr[m] = (uint16_t)(r > 65535 ? 65535 : r);
+            }
+            __syncthreads();
+        }
+        // ---- halo init ----
+        for (int i = tid; i < SK_CH; i += SK_THREADS) S.code[i] = 4, S.rl[i] = 0;
+        for (int i = tid; i < SK_XH; i += SK_THREADS) S.X[i] = ~0ULL, S.z[i] = 0, S.pos[i] = 0;
+        int64_t out_run = 0;
+        const int64_t out_base = WRITE ? A.offs[seq] : 0;
+        __syncthreads();
+        for (int T0 = 0; T0 < n_steps; T0 += SK_TILE) {
+            const int tn = min(SK_TILE, n_steps - T0);
+            // ---- (a) stage step codes ----
+            if (A.hpc) {
+                for (int i = tid; i < SK_TILE; i += SK_THREADS) {
+                    bool in = i < tn;
+                    S.code[SK_CH + i] = in ? hpc[T0 + i] : 4;
+                    S.rl[SK_CH + i] = in ? hpr[T0 + i] : 0;
+                    S.pos[SK_XH + i] = in ? hpp[T0 + i] : 0;
+                }
+            } else if (sd.kind == 0) {
+                if (tid < SK_TILE / 64) {        // 64 bases per lane: one uint4 of bases + one uint2 of N bits
+                    int64_t p = sd.off + T0 + (int64_t)tid * 64;
+                    uint4 b4 = make_uint4(0, 0, 0, 0); uint2 n2 = make_uint2(0, 0);
+                    if (T0 + tid * 64 < sd.len) {
+                        b4 = *reinterpret_cast<const uint4 *>(A.seq2 + (p >> 4));
+                        n2 = *reinterpret_cast<const uint2 *>(A.nmask + (p >> 5));
+                    }
+                    uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+                    uint64_t nm = (uint64_t)n2.y << 32 | n2.x;
+                    uint32_t *dst = reinterpret_cast<uint32_t *>(&S.code[SK_CH + tid * 64]);
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        uint32_t wv = bw[q >> 2] >> (8 * (q & 3));
+                        uint32_t out = 0;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            int bi = q * 4 + e;
+                            uint32_t c = (wv >> (2 * e)) & 3;
+                            if ((nm >> bi & 1) || T0 + tid * 64 + bi >= sd.len) c = 4;
+                            out |= c << (8 * e);
+                        }
+                        dst[q] = out;
+                    }
+                }
+                for (int i = tid; i < SK_TILE; i += SK_THREADS) S.pos[SK_XH + i] = T0 + i;
+            } else {
+                for (int i = tid; i < SK_TILE; i += SK_THREADS) {
+                    S.code[SK_CH + i] = i < tn ? A.bytes[sd.off + T0 + i] : 4;
+                    S.pos[SK_XH + i] = T0 + i;
+                }
+            }
+            __syncthreads();
+            // ---- (b) hashes: 8 consecutive steps per thread, rolling k-mers ----
+            {
+                const uint8_t *cd = S.code + SK_CH + tid * 8;
+                const uint16_t *rl = S.rl + SK_CH + tid * 8;
+                const int cap = w + k;
+                int l = 0;
+                for (int b = 1; b <= cap && b <= SK_CH; ++b) { if (cd[-b] == 4) break; l = b; }
+                uint64_t k0 = 0, k1 = 0;
+                int span = 0;
+                {
+                    int nb = l < k - 1 ? l : k - 1;
+                    for (int b = nb; b >= 1; --b) {
+                        uint64_t c = cd[-b];
+                        k0 = (k0 << 2 | c) & mask;
+                        k1 = (k1 >> 2) | (3ULL ^ c) << shift1;
+                    }
+                    if (A.hpc) { int ns = l < k ? l : k; for (int b = 1; b <= ns; ++b) span += rl[-b]; }
+                }
+                for (int c8 = 0; c8 < 8; ++c8) {
+                    int j = tid * 8 + c8;
+                    uint64_t X = ~0ULL; int z = 0;
+                    int c = cd[c8];
+                    if (c < 4) {
+                        k0 = (k0 << 2 | (uint64_t)c) & mask;
+                        k1 = (k1 >> 2) | (3ULL ^ (uint64_t)c) << shift1;
+                        int sp;
+                        if (A.hpc) {
+                            span += rl[c8];
+                            if (l >= k) span -= rl[c8 - k];      // queue already held k runs
+                            sp = span;
+                        } else sp = l + 1 < k ? l + 1 : k;
+                        if (l < cap) ++l;
+                        if (l >= k && sp < 256) {
+                            z = k0 < k1 ? 0 : 1;
+                            X = mix64_masked(z ? k1 : k0, mask) << 8 | (uint64_t)sp;
+                        }
+                    } else l = 0, span = 0;
+                    if (j < tn) { S.X[SK_XH + j] = X; S.z[SK_XH + j] = (uint8_t)z; S.lcap[j] = (uint8_t)l; }
+                    else { S.X[SK_XH + j] = ~0ULL; S.z[SK_XH + j] = 0; S.lcap[j] = 0; }
+                }
+            }
+            __syncthreads();
+            // ---- (c) emission, 256 steps at a time in order ----
+            for (int sub = 0; sub < SK_TILE; sub += SK_THREADS) {
+                if (sub >= tn) break;
+                int j = sub + tid;
+                SkCount cnt; cnt.n = 0;
+                if (j < tn) sk_step(S, j, w, k, cnt);
+                int tot, pre = block_excl_scan(cnt.n, &tot, S.ws);
+                if (WRITE && cnt.n) {
+                    SkWrite wr; wr.S = &S; wr.ox = A.mz_x; wr.oy = A.mz_y; wr.at = out_base + out_run + pre;
+                    sk_step(S, j, w, k, wr);
+                }
+                out_run += tot;
+            }
+            __syncthreads();
+            // ---- (d) carry halos ----
+            if (T0 + SK_TILE < n_steps) {
+                uint8_t c0 = 0; uint16_t r0 = 0; uint64_t x0 = 0; uint8_t z0 = 0; int32_t p0 = 0;
+                if (tid < SK_CH) c0 = S.code[SK_TILE + tid], r0 = S.rl[SK_TILE + tid];
+                if (tid < SK_XH) x0 = S.X[SK_TILE + tid], z0 = S.z[SK_TILE + tid], p0 = S.pos[SK_TILE + tid];
+                __syncthreads();
+                if (tid < SK_CH) S.code[tid] = c0, S.rl[tid] = r0;
+                if (tid < SK_XH) S.X[tid] = x0, S.z[tid] = z0, S.pos[tid] = p0;
+                __syncthreads();
+            }
+        }
+        // ---- final flush: the pending minimum of the last window ----
+        if (tid == 0 && n_steps > 0) {
+            int last = (n_steps - 1) % SK_TILE;     // local index of the last step in the last tile
+            const uint64_t *X = S.X + SK_XH + last;
+            uint64_t mn = ~0ULL; int mnd = 0;
+            for (int d = w - 1; d >= 0; --d) { uint64_t v = X[-d]; if (v <= mn) mn = v, mnd = d; }
+            if (mn != ~0ULL) {
+                if (WRITE) {
+                    int jj = last - mnd;
+                    A.mz_x[out_base + out_run] = mn;
+                    A.mz_y[out_base + out_run] = (uint32_t)S.pos[SK_XH + jj] << 1 | S.z[SK_XH + jj];
+                }
+                ++out_run;
+            }
+            if (!WRITE) A.counts[seq] = (int32_t)out_run;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace telr

@@ -1,0 +1,715 @@
+// telr_af.cu — C ABI (include/telr_af.h) and host orchestration of the stage-4 device pipeline.
+//
+// Stage order per chunk of loci (all on the ctx's stream):
+//   k_unpack_contigs -> k_sketch<COUNT> -> scan -> k_sketch<WRITE> -> k_self_count
+//   -> k_chain<count> -> scans -> k_chain<fill> -> k_worklist -> k_align -> k_depth_af
+// There is no CPU execution path: every entry point fails with TELR_ENODEV when no sm_100 device is present.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+
+#include "../../include/telr_af.h"
+#include "k_sketch.cuh"
+#include "k_misc.cuh"
+#include "k_chain.cuh"
+#include "k_align.cuh"
+#include "k_depth.cuh"
+
+using namespace telr;
+
+#define TELR_VERSION 100
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) { p = nullptr; cudaGetLastError(); if (cudaMalloc(&p, bytes) != cudaSuccess) { p = nullptr; return -1; } want = bytes; }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() { return (T *)p; }
+};
+
+}  // namespace
+
+struct telr_af_ctx {
+    int device = 0, sm_count = 0;
+    cudaStream_t stream = nullptr;
+    int last_cuda = 0;
+    long long launches = 0;
+    size_t ws_limit = 0;
+    int depth_mode = 1;
+    int64_t chunk_bases = 0;
+    int64_t dir_cap = 8 << 20;
+    // device buffers
+    DevBuf b_in[10];            // host-variant copies of the batch arrays
+    DevBuf b_cov, b_af, b_depth;
+    DevBuf b_lrb, b_cboff, b_ctg, b_descs, b_counts, b_mzoff, b_mzx, b_mzy, b_self, b_tabk, b_tabc, b_hpc, b_hpp, b_hpr;
+    DevBuf b_pna, b_pread, b_pls, b_paoff, b_prcap, b_proff, b_pnregs, b_pnca, b_anch, b_regs, b_chws, b_alws, b_work;
+    DevBuf b_blk, b_pblkoff, b_pblkcnt, b_ctr, b_alnout, b_cigout, b_doff, b_big, b_biglock;
+    int n_big = 8; int64_t big_cap = (int64_t)208 << 20;
+    cudaEvent_t ev[10];
+};
+
+static void opt_preset(Opt &o, int preset)
+{
+    memset(&o, 0, sizeof(o));
+    o.k = 15; o.w = 10; o.hpc = 0;
+    o.a = 2; o.b = 4; o.q = 4; o.e = 2; o.q2 = 24; o.e2 = 1; o.sc_ambi = 1;
+    o.zdrop = 400; o.zdrop_inv = 200; o.end_bonus = -1; o.min_dp_max = 80; o.min_ksw_len = 200;
+    o.bw = 500; o.bw_long = 20000; o.max_gap = 5000;
+    o.max_chain_skip = 25; o.max_chain_iter = 5000; o.min_cnt = 3; o.min_chain_score = 40;
+    o.rmq_inner_dist = 1000; o.rmq_size_cap = 100000; o.rmq_rescue_size = 1000; o.rmq_rescue_ratio = 0.1f;
+    float gap_scale = 0.8f, skip_scale = 0.0f;
+    o.mask_level = 0.5f; o.mask_len = INT32_MAX; o.pri_ratio = 0.8f; o.best_n = 5;
+    o.q_occ_frac = 0.01f; o.mid_occ_frac = 2e-4f; o.min_mid_occ = 10; o.max_mid_occ = 1000000;
+    o.seed_term = wang_hash32(11u); o.max_sw_mat = 100000000LL; o.rank_min_len = 500; o.rank_frac = 0.9f; o.max_clip_ratio = 1.0f;
+    if (preset == TELR_PRESET_MAP_PB) { o.hpc = 1; o.k = 19; }
+    else if (preset == TELR_PRESET_MAP_HIFI) {
+        o.k = 19; o.w = 19; o.max_gap = 10000; o.a = 1; o.b = 4; o.q = 6; o.q2 = 26; o.e = 2; o.e2 = 1;
+        o.min_mid_occ = 50; o.max_mid_occ = 500; o.min_dp_max = 200;
+    }
+    o.chn_pen_gap = (float)(gap_scale * 0.01 * o.k);
+    o.chn_pen_skip = (float)(skip_scale * 0.01 * o.k);
+}
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->last_cuda = (int)e_; fprintf(stderr, "[telr_af] CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return TELR_ECUDA; } } while (0)
+#define ENS(buf, bytes) do { if ((buf).ensure((size_t)(bytes)) != 0) { fprintf(stderr, "[telr_af] device allocation of %zu bytes failed\n", (size_t)(bytes)); return TELR_ENOMEM; } } while (0)
+
+// ------------------------------------------------------------------------------------------------
+__global__ void k_build_descs(int n_reads, int n_loci, const int64_t *read_off, const int32_t *read_len,
+                              const int64_t *ctg_boff, const int32_t *contig_len, SeqDesc *d)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_reads) { d[i].off = read_off[i]; d[i].len = read_len[i]; d[i].kind = 0; }
+    else if (i < n_reads + 2 * n_loci) {
+        int j = i - n_reads, s = j >= n_loci, l = s ? j - n_loci : j;
+        d[i].off = ctg_boff[l] + (s ? contig_len[l] : 0); d[i].len = contig_len[l]; d[i].kind = 1;
+    }
+}
+
+__global__ void k_reg_caps(int n, const int32_t *na, int32_t *cap)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) cap[i] = na[i] > 0 ? 2 * (na[i] / 3) + 4 : 0;
+}
+
+__global__ void k_worklist(int n, const int32_t *nregs, int32_t *list, int32_t *count)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && nregs[i] > 0) list[atomicAdd(count, 1)] = i;
+}
+
+struct HostMeta {       // host copies of the small per-read / per-locus arrays
+    std::vector<int32_t> read_len, lrb, contig_len;
+};
+
+// counters layout in b_ctr (int64 slots)
+enum { C_WORK_CHAIN = 0, C_WORK_ALIGN = 1, C_ERR = 2, C_NWORK = 3, C_ANCH = 4, C_CELLS = 5, C_TASKS = 6, C_NBLK = 7, C_NALN = 8, C_NCIG = 9, C_MAXNA = 10, C_SLOTS = 16 };
+
+static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* device pointers */, const HostMeta &hm,
+                     int l0, int l1, telr_af_result *dres /* device pointers for cov2x/af/depth */, const int64_t *h_depth_off,
+                     telr_af_result *stats, int32_t *d_aln_out, int64_t aln_cap, uint32_t *d_cig_out, int64_t cig_cap)
+{
+    cudaStream_t st = ctx->stream;
+    const int n_loci = l1 - l0;
+    const int r0 = hm.lrb[l0], r1 = hm.lrb[l1], n_reads = r1 - r0;
+    const int n_seq = n_reads + 2 * n_loci, n_prob = 2 * n_reads;
+    const int sm = ctx->sm_count;
+    if (n_loci <= 0) return TELR_OK;
+    // ---- chunk-local index arrays ----
+    std::vector<int32_t> lrb(n_loci + 1);
+    std::vector<int64_t> cboff(n_loci + 1);
+    int64_t ctg_total = 0; int max_tlen = 0, max_qlen = 0;
+    for (int l = 0; l < n_loci; ++l) {
+        lrb[l] = hm.lrb[l0 + l] - r0;
+        cboff[l] = ctg_total;
+        int L = hm.contig_len[l0 + l];
+        if (L < 0) return TELR_EINVAL;
+        ctg_total += 2 * (int64_t)L;
+        max_tlen = std::max(max_tlen, L);
+    }
+    lrb[n_loci] = n_reads; cboff[n_loci] = ctg_total;
+    for (int r = r0; r < r1; ++r) max_qlen = std::max(max_qlen, hm.read_len[r]);
+    ENS(ctx->b_lrb, (n_loci + 1) * 4); ENS(ctx->b_cboff, (n_loci + 1) * 8); ENS(ctx->b_ctg, ctg_total + 64);
+    ENS(ctx->b_ctr, C_SLOTS * 8);
+    CK(cudaMemcpyAsync(ctx->b_lrb.p, lrb.data(), (n_loci + 1) * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->b_cboff.p, cboff.data(), (n_loci + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ctx->b_ctr.p, 0, C_SLOTS * 8, st));
+    int64_t *ctr = ctx->b_ctr.as<int64_t>();
+    const int64_t *read_off = db->read_off + r0; const int32_t *read_len = db->read_len + r0; const uint32_t *read_hash = db->read_hash + r0;
+    const int64_t *contig_off = db->contig_off + l0; const int32_t *contig_len = db->contig_len + l0;
+
+    CK(cudaEventRecord(ctx->ev[0], st));
+    k_unpack_contigs<<<std::min(n_loci, sm * 8), 256, 0, st>>>(db->seq2, db->nmask, n_loci, contig_off, contig_len, ctx->b_cboff.as<int64_t>(), ctx->b_ctg.as<uint8_t>());
+    ENS(ctx->b_descs, (size_t)n_seq * sizeof(SeqDesc)); ENS(ctx->b_counts, (size_t)(n_seq + 1) * 4); ENS(ctx->b_mzoff, (size_t)(n_seq + 2) * 8);
+    k_build_descs<<<(n_seq + 255) / 256, 256, 0, st>>>(n_reads, n_loci, read_off, read_len, ctx->b_cboff.as<int64_t>(), contig_len, ctx->b_descs.as<SeqDesc>());
+    // ---- (a) sketch ----
+    SketchArgs sa; memset(&sa, 0, sizeof(sa));
+    sa.seq2 = db->seq2; sa.nmask = db->nmask; sa.bytes = ctx->b_ctg.as<uint8_t>(); sa.seqs = ctx->b_descs.as<SeqDesc>();
+    sa.n_seq = n_seq; sa.w = o.w; sa.k = o.k; sa.hpc = o.hpc;
+    const int sk_grid = std::min(n_seq, sm * 8);
+    if (o.hpc) {
+        int64_t stride = ((int64_t)std::max(max_qlen, max_tlen) + 64) & ~63LL;
+        ENS(ctx->b_hpc, stride * sk_grid); ENS(ctx->b_hpp, stride * sk_grid * 4); ENS(ctx->b_hpr, stride * sk_grid * 2);
+        sa.hp_code = ctx->b_hpc.as<uint8_t>(); sa.hp_pos = ctx->b_hpp.as<int32_t>(); sa.hp_rl = ctx->b_hpr.as<uint16_t>(); sa.hp_stride = stride;
+    }
+    sa.counts = ctx->b_counts.as<int32_t>();
+    k_sketch<false><<<sk_grid, SK_THREADS, 0, st>>>(sa);
+    k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_counts.as<int32_t>(), ctx->b_mzoff.as<int64_t>(), n_seq, nullptr);
+    int64_t n_mz = 0;
+    CK(cudaMemcpyAsync(&n_mz, ctx->b_mzoff.as<int64_t>() + n_seq, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    ENS(ctx->b_mzx, (n_mz + 1) * 8); ENS(ctx->b_mzy, (n_mz + 1) * 4); ENS(ctx->b_self, (n_mz + 1) * 2);
+    sa.offs = ctx->b_mzoff.as<int64_t>(); sa.mz_x = ctx->b_mzx.as<uint64_t>(); sa.mz_y = ctx->b_mzy.as<uint32_t>();
+    k_sketch<true><<<sk_grid, SK_THREADS, 0, st>>>(sa);
+    CK(cudaEventRecord(ctx->ev[1], st));
+    {
+        int64_t max_nmz = (int64_t)max_qlen + 16, tab = 64;
+        while (tab < 2 * max_nmz) tab <<= 1;
+        int grid = std::min(n_reads, sm * 4);
+        if (grid < 1) grid = 1;
+        ENS(ctx->b_tabk, tab * grid * 8); ENS(ctx->b_tabc, tab * grid * 4);
+        k_self_count<<<grid, 256, 0, st>>>(n_reads, ctx->b_mzoff.as<int64_t>(), ctx->b_mzx.as<uint64_t>(), ctx->b_self.as<uint16_t>(),
+                                           ctx->b_tabk.as<uint64_t>(), ctx->b_tabc.as<uint32_t>(), tab);
+    }
+    // ---- (b)+(c) index, seeds, chains ----
+    ENS(ctx->b_pna, (size_t)(n_prob + 1) * 4); ENS(ctx->b_pread, (size_t)(n_prob + 1) * 4); ENS(ctx->b_pls, (size_t)(n_prob + 1) * 4);
+    ENS(ctx->b_paoff, (size_t)(n_prob + 2) * 8); ENS(ctx->b_prcap, (size_t)(n_prob + 1) * 4); ENS(ctx->b_proff, (size_t)(n_prob + 2) * 8);
+    ENS(ctx->b_pnregs, (size_t)(n_prob + 1) * 4); ENS(ctx->b_pnca, (size_t)(n_prob + 1) * 4);
+    ChainArgs ca; memset(&ca, 0, sizeof(ca));
+    ca.o = o; ca.n_loci = n_loci; ca.n_reads = n_reads; ca.mode = 0;
+    ca.locus_read_begin = ctx->b_lrb.as<int32_t>();
+    ca.mz_off = ctx->b_mzoff.as<int64_t>(); ca.mz_x = ctx->b_mzx.as<uint64_t>(); ca.mz_y = ctx->b_mzy.as<uint32_t>(); ca.selfcnt = ctx->b_self.as<uint16_t>();
+    ca.read_len = read_len; ca.read_hash = read_hash;
+    ca.prob_na = ctx->b_pna.as<int32_t>(); ca.prob_read = ctx->b_pread.as<int32_t>(); ca.prob_ls = ctx->b_pls.as<int32_t>();
+    ca.prob_nregs = ctx->b_pnregs.as<int32_t>(); ca.prob_nca = ctx->b_pnca.as<int32_t>();
+    ca.work_counter = (int32_t *)(ctr + C_WORK_CHAIN); ca.err = (int32_t *)(ctr + C_ERR); ca.stat_anchors = (unsigned long long *)(ctr + C_ANCH);
+    const int ch_grid = std::min(2 * n_loci, sm);
+    const size_t ch_smem = sizeof(IdxSmem);
+    CK(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch_smem));
+    k_chain<<<ch_grid, CH_THREADS, ch_smem, st>>>(ca);
+    k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_pna.as<int32_t>(), ctx->b_paoff.as<int64_t>(), n_prob, ctr + C_MAXNA);
+    k_reg_caps<<<(n_prob + 255) / 256, 256, 0, st>>>(n_prob, ctx->b_pna.as<int32_t>(), ctx->b_prcap.as<int32_t>());
+    k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_prcap.as<int32_t>(), ctx->b_proff.as<int64_t>(), n_prob, nullptr);
+    int64_t tot_na = 0, tot_rcap = 0, max_na = 0;
+    CK(cudaMemcpyAsync(&tot_na, ctx->b_paoff.as<int64_t>() + n_prob, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&tot_rcap, ctx->b_proff.as<int64_t>() + n_prob, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&max_na, ctr + C_MAXNA, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    ENS(ctx->b_anch, (tot_na + 1) * sizeof(Anchor)); ENS(ctx->b_regs, (tot_rcap + 1) * sizeof(Reg));
+    const int reg_cap_max = 2 * ((int)max_na / 3) + 8;
+    const size_t ch_stride = chain_scratch_bytes((size_t)max_na + 1) + hit_scratch_bytes((size_t)reg_cap_max) + (((size_t)max_qlen + 64) * 4 & ~(size_t)255) + 256;
+    ENS(ctx->b_chws, ch_stride * (size_t)ch_grid * CH_WARPS);
+    CK(cudaMemsetAsync(ctr + C_WORK_CHAIN, 0, 8, st));
+    ca.mode = 1; ca.prob_aoff = ctx->b_paoff.as<int64_t>(); ca.prob_roff = ctx->b_proff.as<int64_t>();
+    ca.anchors = ctx->b_anch.as<Anchor>(); ca.regs = ctx->b_regs.as<Reg>();
+    ca.warp_scratch = ctx->b_chws.as<uint8_t>(); ca.warp_scratch_stride = ch_stride; ca.max_na = (int)max_na;
+    k_chain<<<ch_grid, CH_THREADS, ch_smem, st>>>(ca);
+    CK(cudaEventRecord(ctx->ev[2], st));
+    // ---- (d) alignment ----
+    ENS(ctx->b_work, (size_t)(n_prob + 1) * 4);
+    k_worklist<<<(n_prob + 255) / 256, 256, 0, st>>>(n_prob, ctx->b_pnregs.as<int32_t>(), ctx->b_work.as<int32_t>(), (int32_t *)(ctr + C_NWORK));
+    int64_t n_work64 = 0;
+    CK(cudaMemcpyAsync(&n_work64, ctr + C_NWORK, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int n_work = (int)(n_work64 & 0xffffffff);
+    int64_t chunk_bases = 0;
+    for (int r = r0; r < r1; ++r) chunk_bases += hm.read_len[r];
+    int64_t blocks_cap = chunk_bases / 2 + (int64_t)n_prob * 8 + 1024;
+    ENS(ctx->b_blk, blocks_cap * 8); ENS(ctx->b_pblkoff, (size_t)(n_prob + 1) * 8); ENS(ctx->b_pblkcnt, (size_t)(n_prob + 1) * 4);
+    CK(cudaMemsetAsync(ctx->b_pblkcnt.p, 0, (size_t)(n_prob + 1) * 4, st));
+    CK(cudaMemsetAsync(ctx->b_pblkoff.p, 0, (size_t)(n_prob + 1) * 8, st));
+    AlignArgs aa; memset(&aa, 0, sizeof(aa));
+    aa.o = o; aa.n_prob = n_prob; aa.read_base = r0; aa.seq2 = db->seq2; aa.nmask = db->nmask; aa.read_off = read_off; aa.read_len = read_len;
+    aa.contig_len = contig_len; aa.ctg_boff = ctx->b_cboff.as<int64_t>(); aa.ctg_bytes = ctx->b_ctg.as<uint8_t>();
+    aa.prob_read = ctx->b_pread.as<int32_t>(); aa.prob_ls = ctx->b_pls.as<int32_t>(); aa.prob_nca = ctx->b_pnca.as<int32_t>();
+    aa.prob_nregs = ctx->b_pnregs.as<int32_t>(); aa.prob_aoff = ctx->b_paoff.as<int64_t>(); aa.prob_roff = ctx->b_proff.as<int64_t>();
+    aa.anchors = ctx->b_anch.as<Anchor>(); aa.regs = ctx->b_regs.as<Reg>();
+    aa.max_qlen = max_qlen; aa.max_tlen = max_tlen; aa.max_na = (int)max_na; aa.reg_cap_max = reg_cap_max;
+    aa.cig_cap = 4 * (max_qlen + max_tlen) + 1024; aa.dir_cap = ctx->dir_cap;
+    ENS(ctx->b_big, (size_t)ctx->n_big * ctx->big_cap); ENS(ctx->b_biglock, 256);
+    CK(cudaMemsetAsync(ctx->b_biglock.p, 0, 256, st));
+    aa.big = ctx->b_big.as<uint8_t>(); aa.big_cap = ctx->big_cap; aa.n_big = ctx->n_big; aa.big_lock = ctx->b_biglock.as<int32_t>();
+    {
+        size_t maxQ = ((size_t)max_qlen + 64) & ~(size_t)15, maxT = ((size_t)max_tlen + 64) & ~(size_t)15;
+        size_t s = 2 * maxQ + 6 * maxT + maxT * 4 + maxT * 24 + (maxQ + maxT) * 4 + (size_t)aa.cig_cap * 4 + ((size_t)max_na + 8) * 4 +
+                   hit_scratch_bytes((size_t)reg_cap_max + 1) + 512 + (size_t)aa.dir_cap;
+        aa.warp_scratch_stride = (s + 255) & ~(size_t)255;
+    }
+    const int al_grid = std::max(1, std::min((n_work + AL_WARPS - 1) / AL_WARPS, sm * 4));
+    ENS(ctx->b_alws, aa.warp_scratch_stride * (size_t)al_grid * AL_WARPS);
+    aa.warp_scratch = ctx->b_alws.as<uint8_t>();
+    aa.work_counter = (int32_t *)(ctr + C_WORK_ALIGN); aa.work_list = ctx->b_work.as<int32_t>(); aa.n_work = n_work;
+    aa.err = (int32_t *)(ctr + C_ERR); aa.stat_cells = (unsigned long long *)(ctr + C_CELLS); aa.stat_tasks = (unsigned long long *)(ctr + C_TASKS);
+    aa.blocks = ctx->b_blk.as<int2>(); aa.n_blocks = (unsigned long long *)(ctr + C_NBLK); aa.blocks_cap = blocks_cap;
+    aa.prob_blk_off = ctx->b_pblkoff.as<int64_t>(); aa.prob_blk_cnt = ctx->b_pblkcnt.as<int32_t>();
+    aa.aln_out = d_aln_out; aa.n_aln = (unsigned long long *)(ctr + C_NALN); aa.aln_cap = aln_cap;
+    aa.cig_out = d_cig_out; aa.n_cig = (unsigned long long *)(ctr + C_NCIG); aa.cig_out_cap = cig_cap;
+    if (d_aln_out) {    // continue numbering across chunks
+        int64_t init[2] = {stats->n_aln, stats->n_cigar};
+        CK(cudaMemcpyAsync(ctr + C_NALN, init, 16, cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaEventRecord(ctx->ev[3], st));
+    if (n_work > 0) k_align<<<al_grid, AL_THREADS, 0, st>>>(aa);
+    CK(cudaEventRecord(ctx->ev[4], st));
+    // ---- (e)+(f) depth, medians, AF ----
+    DepthArgs da; memset(&da, 0, sizeof(da));
+    da.n_loci = n_loci; da.mode = ctx->depth_mode; da.contig_len = contig_len; da.te_start = db->te_start + l0; da.te_end = db->te_end + l0;
+    da.locus_read_begin = ctx->b_lrb.as<int32_t>(); da.prob_blk_off = ctx->b_pblkoff.as<int64_t>(); da.prob_blk_cnt = ctx->b_pblkcnt.as<int32_t>();
+    da.blocks = ctx->b_blk.as<int2>(); da.flank_len = db->flank_len; da.flank_off = db->flank_off; da.te_len = db->te_len; da.te_off = db->te_off;
+    da.cov2x = dres->cov2x + (int64_t)l0 * 8; da.af = dres->af + l0; da.max_len = max_tlen;
+    if (dres->depth) {
+        std::vector<int64_t> doff(n_loci + 1);
+        for (int l = 0; l < n_loci; ++l) doff[l] = h_depth_off[l0 + l];
+        ENS(ctx->b_doff, (n_loci + 1) * 8);
+        CK(cudaMemcpyAsync(ctx->b_doff.p, doff.data(), (size_t)n_loci * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        da.depth = dres->depth; da.depth_off = ctx->b_doff.as<int64_t>();
+    }
+    const size_t dp_smem = ((size_t)max_tlen + 8) * 4;
+    if (dp_smem > 220 * 1024) return TELR_EUNSUPPORTED;
+    CK(cudaFuncSetAttribute(k_depth_af, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dp_smem));
+    k_depth_af<<<std::min(n_loci, sm * 4), DP_THREADS, dp_smem, st>>>(da);
+    CK(cudaEventRecord(ctx->ev[5], st));
+    int64_t hc[C_SLOTS];
+    CK(cudaMemcpyAsync(hc, ctr, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    const int err = (int)(hc[C_ERR] & 0xffffffff);
+    if (err) {
+        fprintf(stderr, "[telr_af] device pipeline flagged error mask 0x%x (1 regcap 2 cigcap 4 kcap 8 dircap 16 idxcap 32 blkcap 64 alncap)\n", err);
+        return (err & 16) ? TELR_EUNSUPPORTED : TELR_ECAP;
+    }
+    stats->dp_cells += hc[C_CELLS]; stats->n_dp_tasks += hc[C_TASKS]; stats->n_anchors += hc[C_ANCH]; stats->n_minimizers += n_mz;
+    stats->n_aln_blocks += hc[C_NBLK];
+    ctx->launches += 14 + (n_work > 0 ? 1 : 0);   // unpack, descs, sketch x2, scan x3, self_count, chain x2, reg_caps, worklist, align, depth_af
+    if (d_aln_out) { stats->n_aln = hc[C_NALN]; stats->n_cigar = hc[C_NCIG]; }
+    float ms;
+    static const int pairs[5][3] = {{0, 1, 0}, {1, 2, 1}, {2, 3, 2}, {3, 4, 3}, {4, 5, 6}};
+    for (auto &p : pairs) { cudaEventElapsedTime(&ms, ctx->ev[p[0]], ctx->ev[p[1]]); stats->ms_stage[p[2]] += ms; }
+    return TELR_OK;
+}
+
+static int run_device(telr_af_ctx *ctx, const telr_af_batch *db, const HostMeta &hm, telr_af_result *dres, telr_af_result *stats,
+                      int32_t *d_aln_out, int64_t aln_cap, uint32_t *d_cig_out, int64_t cig_cap)
+{
+    Opt o;
+    if (db->preset < 0 || db->preset > 2) return TELR_EINVAL;
+    opt_preset(o, db->preset);
+    const int n_loci = db->n_loci;
+    std::vector<int64_t> depth_off(n_loci + 1, 0);
+    for (int l = 0; l < n_loci; ++l) depth_off[l + 1] = depth_off[l] + 2 * (int64_t)hm.contig_len[l];
+    stats->dp_cells = stats->n_dp_tasks = stats->n_anchors = stats->n_minimizers = stats->n_aln_blocks = 0;
+    stats->n_aln = stats->n_cigar = 0;
+    for (int i = 0; i < 8; ++i) stats->ms_stage[i] = 0.f;
+    // chunk loci by read bases
+    const int64_t budget = ctx->chunk_bases > 0 ? ctx->chunk_bases : (int64_t)384 << 20;
+    int l0 = 0;
+    while (l0 < n_loci) {
+        int l1 = l0; int64_t acc = 0;
+        while (l1 < n_loci) {
+            int64_t lb = 0;
+            for (int r = hm.lrb[l1]; r < hm.lrb[l1 + 1]; ++r) lb += hm.read_len[r];
+            if (l1 > l0 && acc + lb > budget) break;
+            acc += lb; ++l1;
+        }
+        int rc = run_chunk(ctx, o, db, hm, l0, l1, dres, depth_off.data(), stats, d_aln_out, aln_cap, d_cig_out, cig_cap);
+        if (rc != TELR_OK) return rc;
+        l0 = l1;
+    }
+    return TELR_OK;
+}
+
+static int validate_host_meta(const telr_af_batch *b, const HostMeta &hm)
+{
+    if (b->n_loci < 0 || b->n_reads < 0) return TELR_EINVAL;
+    if (hm.lrb[0] != 0 || hm.lrb[b->n_loci] != b->n_reads) return TELR_EINVAL;
+    for (int l = 0; l < b->n_loci; ++l) if (hm.lrb[l + 1] < hm.lrb[l]) return TELR_EINVAL;
+    for (int r = 0; r < b->n_reads; ++r) if (hm.read_len[r] <= 0) return TELR_EINVAL;
+    return TELR_OK;
+}
+
+extern "C" {
+
+int telr_af_version(void) { return TELR_VERSION; }
+
+const char *telr_af_strerror(int code)
+{
+    switch (code) {
+    case TELR_OK: return "ok";
+    case TELR_EINVAL: return "invalid argument or malformed batch";
+    case TELR_ENOMEM: return "out of host or device memory";
+    case TELR_ECUDA: return "CUDA runtime error";
+    case TELR_ENODEV: return "no sm_100 CUDA device available";
+    case TELR_ECAP: return "an internal capacity was exceeded";
+    case TELR_EUNSUPPORTED: return "input outside the implemented scope";
+    default: return "unknown error";
+    }
+}
+
+int telr_af_last_cuda(const telr_af_ctx *ctx) { return ctx ? ctx->last_cuda : 0; }
+long long telr_af_launch_count(const telr_af_ctx *ctx) { return ctx ? ctx->launches : 0; }
+void *telr_af_stream(const telr_af_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int telr_af_create(telr_af_ctx **out, int device, size_t workspace_bytes)
+{
+    if (!out) return TELR_EINVAL;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) { cudaGetLastError(); return TELR_ENODEV; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return TELR_ENODEV;
+    if (prop.major != 10) { fprintf(stderr, "[telr_af] device %d is sm_%d%d; this library is built for sm_100a only\n", device, prop.major, prop.minor); return TELR_ENODEV; }
+    telr_af_ctx *ctx = new telr_af_ctx();
+    ctx->device = device; ctx->sm_count = prop.multiProcessorCount; ctx->ws_limit = workspace_bytes;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return TELR_ECUDA; }
+    for (auto &e : ctx->ev) cudaEventCreate(&e);
+    const char *dm = getenv("TELR_DEPTH_MODE");
+    if (dm) ctx->depth_mode = atoi(dm) ? 1 : 0;
+    const char *cb = getenv("TELR_CHUNK_MBASES");
+    if (cb) ctx->chunk_bases = (int64_t)atoll(cb) << 20;
+    const char *dc = getenv("TELR_DIR_MB");
+    if (dc) ctx->dir_cap = (int64_t)atoll(dc) << 20;
+    *out = ctx;
+    return TELR_OK;
+}
+
+int telr_af_destroy(telr_af_ctx *ctx)
+{
+    if (!ctx) return TELR_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *all[] = {&ctx->b_cov, &ctx->b_af, &ctx->b_depth, &ctx->b_lrb, &ctx->b_cboff, &ctx->b_ctg, &ctx->b_descs, &ctx->b_counts, &ctx->b_mzoff,
+                     &ctx->b_mzx, &ctx->b_mzy, &ctx->b_self, &ctx->b_tabk, &ctx->b_tabc, &ctx->b_hpc, &ctx->b_hpp, &ctx->b_hpr, &ctx->b_pna, &ctx->b_pread,
+                     &ctx->b_pls, &ctx->b_paoff, &ctx->b_prcap, &ctx->b_proff, &ctx->b_pnregs, &ctx->b_pnca, &ctx->b_anch, &ctx->b_regs, &ctx->b_chws,
+                     &ctx->b_alws, &ctx->b_work, &ctx->b_blk, &ctx->b_pblkoff, &ctx->b_pblkcnt, &ctx->b_ctr, &ctx->b_alnout, &ctx->b_cigout, &ctx->b_doff,
+                     &ctx->b_big, &ctx->b_biglock};
+    for (auto *b : all) b->release();
+    for (auto &b : ctx->b_in) b.release();
+    for (auto &e : ctx->ev) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return TELR_OK;
+}
+
+int telr_af_run(telr_af_ctx *ctx, const telr_af_batch *hb, telr_af_result *hr)
+{
+    if (!ctx || !hb || !hr || !hr->cov2x || !hr->af) return TELR_EINVAL;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return TELR_ECUDA;
+    cudaStream_t st = ctx->stream;
+    HostMeta hm;
+    hm.read_len.assign(hb->read_len, hb->read_len + hb->n_reads);
+    hm.lrb.assign(hb->locus_read_begin, hb->locus_read_begin + hb->n_loci + 1);
+    hm.contig_len.assign(hb->contig_len, hb->contig_len + hb->n_loci);
+    int rc = validate_host_meta(hb, hm);
+    if (rc) return rc;
+    if (hb->n_bases % 64) return TELR_EINVAL;
+    // ---- H2D ----
+    telr_af_batch db = *hb;
+    const void *src[10] = {hb->seq2, hb->nmask, hb->read_off, hb->read_len, hb->read_hash, hb->locus_read_begin, hb->contig_off, hb->contig_len, hb->te_start, hb->te_end};
+    const size_t bytes[10] = {(size_t)hb->n_bases / 4, (size_t)hb->n_bases / 8, (size_t)hb->n_reads * 8, (size_t)hb->n_reads * 4, (size_t)hb->n_reads * 4,
+                              (size_t)(hb->n_loci + 1) * 4, (size_t)hb->n_loci * 8, (size_t)hb->n_loci * 4, (size_t)hb->n_loci * 4, (size_t)hb->n_loci * 4};
+    for (int i = 0; i < 10; ++i) {
+        ENS(ctx->b_in[i], bytes[i] + 64);
+        if (bytes[i]) CK(cudaMemcpyAsync(ctx->b_in[i].p, src[i], bytes[i], cudaMemcpyHostToDevice, st));
+    }
+    db.seq2 = ctx->b_in[0].as<uint32_t>(); db.nmask = ctx->b_in[1].as<uint32_t>(); db.read_off = ctx->b_in[2].as<int64_t>();
+    db.read_len = ctx->b_in[3].as<int32_t>(); db.read_hash = ctx->b_in[4].as<uint32_t>(); db.locus_read_begin = ctx->b_in[5].as<int32_t>();
+    db.contig_off = ctx->b_in[6].as<int64_t>(); db.contig_len = ctx->b_in[7].as<int32_t>(); db.te_start = ctx->b_in[8].as<int32_t>();
+    db.te_end = ctx->b_in[9].as<int32_t>();
+    int64_t depth_n = 0;
+    for (int l = 0; l < hb->n_loci; ++l) depth_n += 2 * (int64_t)hm.contig_len[l];
+    telr_af_result dres; memset(&dres, 0, sizeof(dres));
+    ENS(ctx->b_cov, (size_t)hb->n_loci * 32 + 64); ENS(ctx->b_af, (size_t)hb->n_loci * 8 + 64);
+    dres.cov2x = ctx->b_cov.as<int32_t>(); dres.af = ctx->b_af.as<double>();
+    if (hr->depth) { ENS(ctx->b_depth, (size_t)depth_n * 4 + 64); dres.depth = ctx->b_depth.as<int32_t>(); }
+    int32_t *d_aln = nullptr; uint32_t *d_cig = nullptr;
+    if (hr->aln && hr->cigar) {
+        ENS(ctx->b_alnout, (size_t)hr->aln_cap * 64 + 64); ENS(ctx->b_cigout, (size_t)hr->cigar_cap * 4 + 64);
+        d_aln = ctx->b_alnout.as<int32_t>(); d_cig = ctx->b_cigout.as<uint32_t>();
+    }
+    rc = run_device(ctx, &db, hm, &dres, hr, d_aln, hr->aln_cap, d_cig, hr->cigar_cap);
+    if (rc) return rc;
+    // ---- D2H ----
+    CK(cudaMemcpyAsync(hr->cov2x, dres.cov2x, (size_t)hb->n_loci * 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hr->af, dres.af, (size_t)hb->n_loci * 8, cudaMemcpyDeviceToHost, st));
+    if (hr->depth) CK(cudaMemcpyAsync(hr->depth, dres.depth, (size_t)depth_n * 4, cudaMemcpyDeviceToHost, st));
+    std::vector<int32_t> raw;
+    if (d_aln) {
+        raw.resize((size_t)hr->n_aln * 16 + 16);
+        if (hr->n_aln) CK(cudaMemcpyAsync(raw.data(), d_aln, (size_t)hr->n_aln * 64, cudaMemcpyDeviceToHost, st));
+        if (hr->n_cigar) CK(cudaMemcpyAsync(hr->cigar, d_cig, (size_t)hr->n_cigar * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    if (d_aln) {
+        // records arrive in completion order; present them in (locus, strand, read, rank) order
+        std::vector<int64_t> ord(hr->n_aln);
+        for (int64_t i = 0; i < hr->n_aln; ++i) ord[i] = i;
+        std::sort(ord.begin(), ord.end(), [&](int64_t a, int64_t b) {
+            const int32_t *x = &raw[a * 16], *y = &raw[b * 16];       // problem index orders by (locus, strand, read)
+            if (x[14] != y[14]) return x[14] < y[14];
+            return x[15] < y[15];
+        });
+        for (int64_t i = 0; i < hr->n_aln; ++i) {
+            const int32_t *x = &raw[ord[i] * 16];
+            telr_aln &a = hr->aln[i];
+            a.read = x[0]; a.strand = x[1]; a.rs = x[2]; a.re = x[3]; a.qs = x[4]; a.qe = x[5]; a.rev = x[6]; a.flag = x[7];
+            a.dp_max = x[8]; a.mlen = x[9]; a.blen = x[10]; a.n_cigar = x[11];
+            a.cigar_off = (int64_t)(uint32_t)x[12] | (int64_t)x[13] << 32;
+        }
+    }
+    return TELR_OK;
+}
+
+int telr_af_run_device(telr_af_ctx *ctx, const telr_af_batch *db, telr_af_result *dr)
+{
+    if (!ctx || !db || !dr || !dr->cov2x || !dr->af) return TELR_EINVAL;
+    if (dr->aln || dr->cigar) return TELR_EINVAL;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return TELR_ECUDA;
+    HostMeta hm;
+    hm.read_len.resize(db->n_reads); hm.lrb.resize(db->n_loci + 1); hm.contig_len.resize(db->n_loci);
+    CK(cudaMemcpyAsync(hm.read_len.data(), db->read_len, (size_t)db->n_reads * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hm.lrb.data(), db->locus_read_begin, (size_t)(db->n_loci + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hm.contig_len.data(), db->contig_len, (size_t)db->n_loci * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int rc = validate_host_meta(db, hm);
+    if (rc) return rc;
+    telr_af_result dres = *dr;
+    rc = run_device(ctx, db, hm, &dres, dr, nullptr, 0, nullptr, 0);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TELR_OK;
+}
+
+int telr_af_sketch(telr_af_ctx *ctx, const uint32_t *seq2, const uint32_t *nmask, int64_t n_bases, int32_t n_seq,
+                   const int64_t *seq_off, const int32_t *seq_len, int32_t w, int32_t k, int32_t hpc,
+                   uint64_t *mz_x, uint64_t *mz_y, int64_t mz_cap, int64_t *mz_off)
+{
+    if (!ctx || n_seq < 0 || (k & 1) == 0 || k > 28 || w <= 0 || w > SK_XH || w + k > SK_CH) return TELR_EINVAL;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return TELR_ECUDA;
+    cudaStream_t st = ctx->stream;
+    ENS(ctx->b_in[0], n_bases / 4 + 64); ENS(ctx->b_in[1], n_bases / 8 + 64);
+    CK(cudaMemcpyAsync(ctx->b_in[0].p, seq2, n_bases / 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->b_in[1].p, nmask, n_bases / 8, cudaMemcpyHostToDevice, st));
+    std::vector<SeqDesc> d(n_seq);
+    int max_len = 0;
+    for (int i = 0; i < n_seq; ++i) { d[i].off = seq_off[i]; d[i].len = seq_len[i]; d[i].kind = 0; max_len = std::max(max_len, seq_len[i]); }
+    ENS(ctx->b_descs, (size_t)n_seq * sizeof(SeqDesc) + 64); ENS(ctx->b_counts, (size_t)(n_seq + 1) * 4); ENS(ctx->b_mzoff, (size_t)(n_seq + 2) * 8);
+    CK(cudaMemcpyAsync(ctx->b_descs.p, d.data(), (size_t)n_seq * sizeof(SeqDesc), cudaMemcpyHostToDevice, st));
+    SketchArgs sa; memset(&sa, 0, sizeof(sa));
+    sa.seq2 = ctx->b_in[0].as<uint32_t>(); sa.nmask = ctx->b_in[1].as<uint32_t>(); sa.seqs = ctx->b_descs.as<SeqDesc>();
+    sa.n_seq = n_seq; sa.w = w; sa.k = k; sa.hpc = hpc;
+    const int grid = std::max(1, std::min(n_seq, ctx->sm_count * 8));
+    if (hpc) {
+        int64_t stride = ((int64_t)max_len + 64) & ~63LL;
+        ENS(ctx->b_hpc, stride * grid); ENS(ctx->b_hpp, stride * grid * 4); ENS(ctx->b_hpr, stride * grid * 2);
+        sa.hp_code = ctx->b_hpc.as<uint8_t>(); sa.hp_pos = ctx->b_hpp.as<int32_t>(); sa.hp_rl = ctx->b_hpr.as<uint16_t>(); sa.hp_stride = stride;
+    }
+    sa.counts = ctx->b_counts.as<int32_t>();
+    k_sketch<false><<<grid, SK_THREADS, 0, st>>>(sa);
+    k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_counts.as<int32_t>(), ctx->b_mzoff.as<int64_t>(), n_seq, nullptr);
+    CK(cudaMemcpyAsync(mz_off, ctx->b_mzoff.p, (size_t)(n_seq + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    int64_t n_mz = mz_off[n_seq];
+    if (n_mz > mz_cap) return TELR_ECAP;
+    ENS(ctx->b_mzx, (n_mz + 1) * 8); ENS(ctx->b_mzy, (n_mz + 1) * 4);
+    sa.offs = ctx->b_mzoff.as<int64_t>(); sa.mz_x = ctx->b_mzx.as<uint64_t>(); sa.mz_y = ctx->b_mzy.as<uint32_t>();
+    k_sketch<true><<<grid, SK_THREADS, 0, st>>>(sa);
+    std::vector<uint32_t> y32(n_mz + 1);
+    CK(cudaMemcpyAsync(mz_x, ctx->b_mzx.p, (size_t)n_mz * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(y32.data(), ctx->b_mzy.p, (size_t)n_mz * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    for (int64_t i = 0; i < n_mz; ++i) mz_y[i] = y32[i];
+    return TELR_OK;
+}
+
+int telr_af_depth_af(telr_af_ctx *ctx, int32_t n_loci, const int32_t *contig_len, const int32_t *te_start, const int32_t *te_end,
+                     int32_t flank_len, int32_t flank_off, int32_t te_len, int32_t te_off, int64_t n_blocks,
+                     const int32_t *blk_ls, const int32_t *blk_start, const int32_t *blk_len, int32_t *depth, int32_t *cov2x, double *af)
+{
+    if (!ctx || n_loci <= 0 || !cov2x || !af) return TELR_EINVAL;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return TELR_ECUDA;
+    cudaStream_t st = ctx->stream;
+    // one pseudo-read per (locus, strand): bucket the blocks on the host
+    std::vector<int32_t> lrb(n_loci + 1), cnt(2 * n_loci, 0);
+    std::vector<int64_t> off(2 * n_loci + 1, 0), doff(n_loci + 1, 0);
+    for (int l = 0; l <= n_loci; ++l) lrb[l] = l;
+    int max_len = 0;
+    for (int l = 0; l < n_loci; ++l) { doff[l + 1] = doff[l] + 2 * (int64_t)contig_len[l]; max_len = std::max(max_len, contig_len[l]); }
+    for (int64_t i = 0; i < n_blocks; ++i) { if (blk_ls[i] < 0 || blk_ls[i] >= 2 * n_loci) return TELR_EINVAL; ++cnt[blk_ls[i]]; }
+    for (int i = 0; i < 2 * n_loci; ++i) off[i + 1] = off[i] + cnt[i];
+    std::vector<int2> blk(n_blocks + 1);
+    std::vector<int64_t> fill(off.begin(), off.end() - 1);
+    for (int64_t i = 0; i < n_blocks; ++i) blk[fill[blk_ls[i]]++] = make_int2(blk_start[i], blk_len[i]);
+    // problem index of (locus l, strand s) with one read per locus is 2*l + s
+    ENS(ctx->b_lrb, (n_loci + 1) * 4); ENS(ctx->b_pblkoff, (size_t)(2 * n_loci + 1) * 8); ENS(ctx->b_pblkcnt, (size_t)(2 * n_loci + 1) * 4);
+    ENS(ctx->b_blk, (size_t)(n_blocks + 1) * 8); ENS(ctx->b_in[7], (size_t)n_loci * 4 + 64); ENS(ctx->b_in[8], (size_t)n_loci * 4 + 64); ENS(ctx->b_in[9], (size_t)n_loci * 4 + 64);
+    ENS(ctx->b_cov, (size_t)n_loci * 32 + 64); ENS(ctx->b_af, (size_t)n_loci * 8 + 64); ENS(ctx->b_doff, (size_t)(n_loci + 1) * 8);
+    ENS(ctx->b_depth, (size_t)doff[n_loci] * 4 + 64);
+    CK(cudaMemcpyAsync(ctx->b_lrb.p, lrb.data(), (size_t)(n_loci + 1) * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->b_pblkoff.p, off.data(), (size_t)(2 * n_loci) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->b_pblkcnt.p, cnt.data(), (size_t)(2 * n_loci) * 4, cudaMemcpyHostToDevice, st));
+    if (n_blocks) CK(cudaMemcpyAsync(ctx->b_blk.p, blk.data(), (size_t)n_blocks * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->b_in[7].p, contig_len, (size_t)n_loci * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->b_in[8].p, te_start, (size_t)n_loci * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->b_in[9].p, te_end, (size_t)n_loci * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->b_doff.p, doff.data(), (size_t)(n_loci + 1) * 8, cudaMemcpyHostToDevice, st));
+    DepthArgs da; memset(&da, 0, sizeof(da));
+    da.n_loci = n_loci; da.mode = ctx->depth_mode; da.contig_len = ctx->b_in[7].as<int32_t>(); da.te_start = ctx->b_in[8].as<int32_t>();
+    da.te_end = ctx->b_in[9].as<int32_t>(); da.locus_read_begin = ctx->b_lrb.as<int32_t>();
+    da.prob_blk_off = ctx->b_pblkoff.as<int64_t>(); da.prob_blk_cnt = ctx->b_pblkcnt.as<int32_t>(); da.blocks = ctx->b_blk.as<int2>();
+    da.flank_len = flank_len; da.flank_off = flank_off; da.te_len = te_len; da.te_off = te_off;
+    da.depth = ctx->b_depth.as<int32_t>(); da.depth_off = ctx->b_doff.as<int64_t>();
+    da.cov2x = ctx->b_cov.as<int32_t>(); da.af = ctx->b_af.as<double>(); da.max_len = max_len;
+    const size_t dp_smem = ((size_t)max_len + 8) * 4;
+    if (dp_smem > 220 * 1024) return TELR_EUNSUPPORTED;
+    CK(cudaFuncSetAttribute(k_depth_af, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dp_smem));
+    k_depth_af<<<std::min(n_loci, ctx->sm_count * 4), DP_THREADS, dp_smem, st>>>(da);
+    CK(cudaMemcpyAsync(cov2x, ctx->b_cov.p, (size_t)n_loci * 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(af, ctx->b_af.p, (size_t)n_loci * 8, cudaMemcpyDeviceToHost, st));
+    if (depth) CK(cudaMemcpyAsync(depth, ctx->b_depth.p, (size_t)doff[n_loci] * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    return TELR_OK;
+}
+
+}  // extern "C"
+
+// ---- DP stage entry point ---------------------------------------------------------------------
+struct DpStageArgs {
+    Opt o; int32_t n_tasks; const telr_dp_task *tasks; const uint8_t *q, *t; telr_dp_out *out;
+    uint32_t *cig; unsigned long long *n_cig; int64_t cig_cap;
+    uint8_t *warp_scratch; size_t stride; int32_t maxQ, maxT; int64_t dir_cap;
+    uint8_t *big; int64_t big_cap; int32_t n_big; int32_t *big_lock;
+    int32_t *work_counter, *err; unsigned long long *cells;
+};
+
+__global__ void __launch_bounds__(AL_THREADS) k_dp_stage(const __grid_constant__ DpStageArgs A)
+{
+    __shared__ DpRes RS[AL_WARPS];
+    __shared__ DpTask TS[AL_WARPS];
+    __shared__ unsigned long long CS[AL_WARPS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint8_t *base = A.warp_scratch + (size_t)(blockIdx.x * AL_WARPS + wid) * A.stride;
+    const size_t maxT = (size_t)A.maxT, maxQ = (size_t)A.maxQ;
+    DpScratch S;
+    S.u = (int8_t *)base; base += maxT; S.v = (int8_t *)base; base += maxT; S.x = (int8_t *)base; base += maxT;
+    S.y = (int8_t *)base; base += maxT; S.x2 = (int8_t *)base; base += maxT; S.y2 = (int8_t *)base; base += maxT;
+    S.H = (int32_t *)base; base += maxT * 4;
+    S.ll = (int32_t *)base; base += maxT * 24;
+    S.ezcap = (int32_t)(maxQ + maxT); S.ezcig = (uint32_t *)base; base += (size_t)S.ezcap * 4;
+    base = (uint8_t *)(((uintptr_t)base + 255) & ~(uintptr_t)255);
+    S.dir = base; S.dir_cap = A.dir_cap;
+    S.big = A.big; S.big_cap = A.big_cap; S.n_big = A.n_big; S.big_lock = A.big_lock;
+    for (;;) {
+        int i = 0;
+        if (lane == 0) i = atomicAdd(A.work_counter, 1);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= A.n_tasks) break;
+        if (lane == 0) {
+            const telr_dp_task &t = A.tasks[i];
+            DpTask &T = TS[wid];
+            T.kind = 0; T.q = A.q + t.q_off; T.t = A.t + t.t_off; T.qstep = T.tstep = 1; T.qcomp = 0;
+            T.qlen = t.qlen; T.tlen = t.tlen; T.w = t.w; T.zdrop = t.zdrop; T.end_bonus = t.end_bonus; T.flag = t.flag;
+            CS[wid] = 0;
+        }
+        __syncwarp();
+        warp_extd2(A.o, TS[wid], RS[wid], S, &CS[wid], A.err);
+        __syncwarp();
+        if (lane == 0) {
+            const DpRes &R = RS[wid];
+            telr_dp_out &o = A.out[i];
+            o.max = R.max; o.max_q = R.max_q; o.max_t = R.max_t; o.mqe = R.mqe; o.mqe_t = R.mqe_t; o.mte = R.mte; o.mte_q = R.mte_q;
+            o.score = R.score; o.zdropped = R.zdropped; o.reach_end = R.reach_end; o.n_cigar = R.n_cigar; o.cells = (int64_t)CS[wid];
+            long long co = (long long)atomicAdd(A.n_cig, (unsigned long long)R.n_cigar);
+            o.cigar_off = co;
+            if (co + R.n_cigar <= A.cig_cap) for (int k = 0; k < R.n_cigar; ++k) A.cig[co + k] = R.cigar[k];
+            else atomicOr(A.err, 64);
+            atomicAdd(A.cells, CS[wid]);
+        }
+        __syncwarp();
+    }
+}
+
+extern "C" int telr_af_dp(telr_af_ctx *ctx, int32_t preset, int32_t n_tasks, const telr_dp_task *tasks, const uint8_t *qseq, int64_t qbytes,
+                          const uint8_t *tseq, int64_t tbytes, telr_dp_out *out, uint32_t *cigar, int64_t cigar_cap)
+{
+    if (!ctx || n_tasks < 0 || preset < 0 || preset > 2) return TELR_EINVAL;
+    if (n_tasks == 0) return TELR_OK;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return TELR_ECUDA;
+    cudaStream_t st = ctx->stream;
+    DpStageArgs A; memset(&A, 0, sizeof(A));
+    opt_preset(A.o, preset);
+    int maxQ = 0, maxT = 0;
+    for (int i = 0; i < n_tasks; ++i) { maxQ = std::max(maxQ, tasks[i].qlen); maxT = std::max(maxT, tasks[i].tlen); }
+    A.maxQ = (maxQ + 64) & ~15; A.maxT = (maxT + 64) & ~15; A.dir_cap = ctx->dir_cap;
+    A.stride = ((size_t)A.maxT * (6 + 4 + 24) + (size_t)(A.maxQ + A.maxT) * 4 + 512 + (size_t)A.dir_cap + 255) & ~(size_t)255;
+    const int grid = std::max(1, std::min((n_tasks + AL_WARPS - 1) / AL_WARPS, ctx->sm_count * 4));
+    ENS(ctx->b_alws, A.stride * (size_t)grid * AL_WARPS);
+    ENS(ctx->b_in[0], qbytes + 64); ENS(ctx->b_in[1], tbytes + 64); ENS(ctx->b_in[2], (size_t)n_tasks * sizeof(telr_dp_task));
+    ENS(ctx->b_in[3], (size_t)n_tasks * sizeof(telr_dp_out)); ENS(ctx->b_cigout, (size_t)cigar_cap * 4 + 64); ENS(ctx->b_ctr, C_SLOTS * 8);
+    CK(cudaMemcpyAsync(ctx->b_in[0].p, qseq, qbytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->b_in[1].p, tseq, tbytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->b_in[2].p, tasks, (size_t)n_tasks * sizeof(telr_dp_task), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ctx->b_ctr.p, 0, C_SLOTS * 8, st));
+    int64_t *ctr = ctx->b_ctr.as<int64_t>();
+    A.n_tasks = n_tasks; A.tasks = ctx->b_in[2].as<telr_dp_task>(); A.q = ctx->b_in[0].as<uint8_t>(); A.t = ctx->b_in[1].as<uint8_t>();
+    A.out = ctx->b_in[3].as<telr_dp_out>(); A.cig = ctx->b_cigout.as<uint32_t>(); A.n_cig = (unsigned long long *)(ctr + C_NCIG); A.cig_cap = cigar_cap;
+    A.warp_scratch = ctx->b_alws.as<uint8_t>(); A.work_counter = (int32_t *)(ctr + C_WORK_ALIGN); A.err = (int32_t *)(ctr + C_ERR);
+    A.cells = (unsigned long long *)(ctr + C_CELLS);
+    ENS(ctx->b_big, (size_t)ctx->n_big * ctx->big_cap); ENS(ctx->b_biglock, 256);
+    CK(cudaMemsetAsync(ctx->b_biglock.p, 0, 256, st));
+    A.big = ctx->b_big.as<uint8_t>(); A.big_cap = ctx->big_cap; A.n_big = ctx->n_big; A.big_lock = ctx->b_biglock.as<int32_t>();
+    k_dp_stage<<<grid, AL_THREADS, 0, st>>>(A);
+    int64_t hc[C_SLOTS];
+    CK(cudaMemcpyAsync(hc, ctr, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out, ctx->b_in[3].p, (size_t)n_tasks * sizeof(telr_dp_out), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if (hc[C_ERR] & 0xffffffff) return TELR_ECAP;
+    if (hc[C_NCIG]) CK(cudaMemcpy(cigar, ctx->b_cigout.p, (size_t)hc[C_NCIG] * 4, cudaMemcpyDeviceToHost));
+    return TELR_OK;
+}
+
+// ---- host helpers ------------------------------------------------------------------------------
+extern "C" int telr_pack_seq(const char *s, int32_t len, int64_t off, uint32_t *seq2, uint32_t *nmask)
+{
+    if ((off & 63) || len < 0) return TELR_EINVAL;
+    int64_t nw = ((int64_t)len + 63) / 64 * 4;
+    memset(seq2 + off / 16, 0, (size_t)nw * 4);
+    memset(nmask + off / 32, 0, (size_t)(nw / 2) * 4);
+    static const int8_t lut[256] = {
+#define N4 4, 4, 4, 4
+#define N16 N4, N4, N4, N4
+        N16, N16, N16, N16,
+        4, 0, 4, 1, 4, 4, 4, 2, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 3, 3, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,
+        4, 0, 4, 1, 4, 4, 4, 2, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 3, 3, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,
+        N16, N16, N16, N16, N16, N16, N16, N16};
+    for (int32_t i = 0; i < len; ++i) {
+        int c = lut[(uint8_t)s[i]];
+        int64_t p = off + i;
+        if (c < 4) seq2[p >> 4] |= (uint32_t)c << (2 * (p & 15));
+        else nmask[p >> 5] |= 1u << (p & 31);
+    }
+    return TELR_OK;
+}
+
+extern "C" uint32_t telr_name_hash(const char *s)
+{
+    uint32_t h = (uint32_t)*s;
+    if (h) for (++s; *s; ++s) h = (h << 5) - h + (uint32_t)*s;
+    return h;
+}

@@ -79,9 +79,11 @@ def make_cfg(name: str, **over) -> tuple[SynthCfg, str]:
     return cfg, preset
 
 
-def generate(name: str, first_locus: int = 0, n_loci: int | None = None, **over) -> Batch:
-    """Generate loci [first_locus, first_locus+n_loci) of configuration ``name``."""
+def generate(name: str, first_locus: int = 0, n_loci: int | None = None, total_loci: int | None = None, **over) -> Batch:
+    """Generate loci [first_locus, first_locus+n_loci) of configuration ``name`` (``total_loci`` widens the job)."""
     cfg, preset = make_cfg(name, **over)
+    if total_loci is not None:
+        cfg.n_loci_total = int(total_loci)
     if n_loci is None:
         n_loci = cfg.n_loci_total - first_locus
     out = SynthOut()
