@@ -346,9 +346,9 @@ __global__ void __launch_bounds__(AL_THREADS) k_align(const __grid_constant__ Al
     S.y = (int8_t *)base; base += maxT; S.x2 = (int8_t *)base; base += maxT; S.y2 = (int8_t *)base; base += maxT;
     S.H = (int32_t *)base; base += maxT * 4;
     S.ll = (int32_t *)base; base += maxT * 4 * 6;
-    S.ezcap = (int32_t)(maxQ + maxT); S.ezcig = (uint32_t *)base; base += (size_t)S.ezcap * 4;
-    uint32_t *cig = (uint32_t *)base; base += (size_t)A.cig_cap * 4;
-    int32_t *K = (int32_t *)base; base += ((size_t)A.max_na + 8) * 4;
+    S.ezcap = (int32_t)(maxQ + maxT); S.ezcig = (uint32_t *)base; base += (size_t)S.ezcap * 4;     // maxQ, maxT are multiples of 16
+    uint32_t *cig = (uint32_t *)base; base += ((size_t)A.cig_cap * 4 + 15) & ~(size_t)15;
+    int32_t *K = (int32_t *)base; base += (((size_t)A.max_na + 8) * 4 + 15) & ~(size_t)15;
     uint8_t *hsb = base; base += hit_scratch_bytes((size_t)A.reg_cap_max + 1);
     base = (uint8_t *)(((uintptr_t)base + 255) & ~(uintptr_t)255);
     S.dir = base; S.dir_cap = A.dir_cap;

@@ -44,10 +44,22 @@ struct ChainArgs {
     const int64_t *prob_roff;                      // [n_prob+1]   region capacity offsets
     Anchor *anchors; Reg *regs;
     int32_t *prob_nregs, *prob_nca;
-    uint8_t *warp_scratch; size_t warp_scratch_stride; int32_t max_na;
+    uint8_t *warp_scratch; size_t warp_scratch_stride; int32_t max_na;   // per-warp: kept-minimizer list of the fill pass
     int32_t *work_counter; int32_t *err;
     unsigned long long *stat_anchors;
+    // per-problem scratch for the chaining kernels (ChainScratch + HitScratch carved at prob_soff[p])
+    uint8_t *prob_scratch; const int64_t *prob_soff;
+    int32_t *prob_nu, *prob_m;      // chains found; anchors to re-chain (0 = no re-chaining)
+    int32_t n_prob;
 };
+
+__device__ __forceinline__ void prob_carve(const ChainArgs &A, int p, int n_a, ChainScratch &cs, HitScratch &hs, int *cap_regs)
+{
+    uint8_t *b = A.prob_scratch + A.prob_soff[p];
+    chain_scratch_carve(cs, b, (size_t)n_a + 1);
+    *cap_regs = 2 * (n_a / 3) + 4;
+    hit_scratch_carve(hs, b + chain_scratch_bytes((size_t)n_a + 1), (size_t)*cap_regs + 4);
+}
 
 __device__ __forceinline__ uint32_t idx_hash(uint64_t key) { return (uint32_t)(mix64(key) >> 24); }
 
@@ -214,23 +226,81 @@ __device__ void chain_dp_warp(const Opt &o, int n, const Anchor *a, ChainScratch
     }
 }
 
-// re-chaining pass: the range-minimum query over finished anchors is a warp-wide scan
+// ---- re-chaining pass (mg_lchain_rmq).  The outer range-minimum query is a warp-wide scan over the active
+// anchors; the inner tree (anchors within rmq_inner_dist on the target) is kept as an array W sorted by
+// (query position, index), maintained incrementally with warp-parallel shifts, and scanned downwards 32
+// candidates at a time with the same prefix-scan emulation of the skip rule as the first pass. ----
+__device__ __forceinline__ bool key_lt(const Anchor *a, int j1, int32_t y2, int j2)   // (y_j1, j1) < (y2, j2)
+{
+    int32_t y1 = (int32_t)a[j1].y;
+    return y1 < y2 || (y1 == y2 && j1 < j2);
+}
+// number of elements of W with key < (y, j)
+__device__ __forceinline__ int w_lower(const int32_t *W, int nw, const Anchor *a, int32_t y, int j)
+{
+    int lo = 0, hi = nw;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (key_lt(a, W[mid], y, j)) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+__device__ void w_insert(int32_t *W, int &nw, const Anchor *a, int j)
+{
+    const int lane = threadIdx.x & 31;
+    const int pos = w_lower(W, nw, a, (int32_t)a[j].y, j);
+    for (int top = nw - 1; top >= pos; top -= 32) {      // shift [pos, nw) right by one, highest chunk first
+        int k = top - lane, v = 0;
+        if (k >= pos) v = W[k];
+        __syncwarp();
+        if (k >= pos) W[k + 1] = v;
+        __syncwarp();
+    }
+    if (lane == 0) W[pos] = j;
+    ++nw;
+    __syncwarp();
+}
+__device__ void w_erase(int32_t *W, int &nw, const Anchor *a, int j)
+{
+    const int lane = threadIdx.x & 31;
+    const int pos = w_lower(W, nw, a, (int32_t)a[j].y, j);
+    if (pos >= nw || W[pos] != j) return;
+    for (int b = pos + 1; b < nw; b += 32) {             // shift (pos, nw) left by one, lowest chunk first
+        int k = b + lane, v = 0;
+        if (k < nw) v = W[k];
+        __syncwarp();
+        if (k < nw) W[k - 1] = v;
+        __syncwarp();
+    }
+    --nw;
+    __syncwarp();
+}
+
 __device__ void chain_rmq_warp(const Opt &o, int n, const Anchor *a, ChainScratch &s)
 {
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
-    for (int i = lane; i < n; i += 32) s.t[i] = -1, s.v[i] = 0;
+    int32_t *f = s.f, *p = s.p, *v = s.v, *t = s.t, *W = s.ord;
+    for (int i = lane; i < n; i += 32) t[i] = -1, v[i] = 0;
     __syncwarp();
     RmqWin w;
     rmq_win_init(w, o);
+    int nw = 0;
     for (int i = 0; i < n; ++i) {
-        rmq_win_advance(w, o, i, a);
-        const int32_t yi = (int32_t)a[i].y;
+        // ---- window maintenance (same order of operations as the two trees upstream: insert, then erase) ----
+        {
+            const int old_i0 = w.i0, old_sti = w.st_inner;
+            rmq_win_advance(w, o, i, a);
+            if (w.max_dist_inner > 0) {
+                for (int j = old_i0; j < w.i0; ++j) w_insert(W, nw, a, j);
+                for (int j = old_sti; j < w.st_inner; ++j) w_erase(W, nw, a, j);
+            }
+        }
+        const Anchor ai = a[i];
+        const int32_t yi = (int32_t)ai.y;
+        // ---- outer RMQ ----
         int best = -1; double bp = 0.0; int32_t by = 0;
         for (int j = (w.st < w.i0 ? w.st : w.i0) + lane; j < w.i0; j += 32) {
             const Anchor aj = a[j];
             if (!rmq_in_range(aj, j, yi, w.max_dist)) continue;
-            double pri = rmq_pri(aj, s.f[j], o.chn_pen_gap);
+            double pri = rmq_pri(aj, f[j], o.chn_pen_gap);
             if (best < 0 || rmq_better(pri, (int32_t)aj.y, j, bp, by, best)) best = j, bp = pri, by = (int32_t)aj.y;
         }
 #pragma unroll
@@ -238,7 +308,67 @@ __device__ void chain_rmq_warp(const Opt &o, int n, const Anchor *a, ChainScratc
             int ob = __shfl_xor_sync(FULL, best, d); double op = __shfl_xor_sync(FULL, bp, d); int32_t oy = __shfl_xor_sync(FULL, by, d);
             if (ob >= 0 && (best < 0 || rmq_better(op, oy, ob, bp, by, best))) best = ob, bp = op, by = oy;
         }
-        if (lane == 0) rmq_step(o, n, i, a, s, best, w.st_inner, w.i0, w.max_dist_inner);
+        int max_j = -1;
+        int32_t max_f = (int32_t)(ai.y >> 32 & 0xff);
+        if (best >= 0) {
+            int exact, width;
+            int32_t sc = f[best] + link_score_simple(ai, a[best], o.chn_pen_gap, o.chn_pen_skip, &exact, &width);
+            if (width <= o.bw_long && sc > max_f) max_f = sc, max_j = best;
+            if (!exact && w.max_dist_inner > 0 && yi > 0) {
+                // candidates: keys <= (yi - 1, n), i.e. y <= yi - 1; walk down from the largest
+                int top = w_lower(W, nw, a, yi, -1) - 1;         // (y, j) < (yi, -1)  <=>  y <= yi - 1
+                int n_skip = 0;
+                const int32_t ylo = yi - w.max_dist_inner;
+                for (; top >= 0; top -= 32) {
+                    const int k = top - lane;
+                    int j = -1; int32_t scj = INT32_MIN; int pj = -1; bool inr = false;
+                    if (k >= 0) {
+                        j = W[k];
+                        inr = (int32_t)a[j].y >= ylo;
+                        if (inr) {
+                            int w2;
+                            int32_t sj = f[j] + link_score_simple(ai, a[j], o.chn_pen_gap, o.chn_pen_skip, 0, &w2);
+                            if (w2 <= o.bw_long) scj = sj, pj = p[j];
+                        }
+                    }
+                    const unsigned inm = __ballot_sync(FULL, inr);        // in-range lanes form a prefix (W is sorted)
+                    const bool valid = scj != INT32_MIN;
+                    if (valid && pj >= 0) t[pj] = i;
+                    __syncwarp();
+                    const bool tj = valid && t[j] == i;
+                    int32_t inc = valid ? scj : INT32_MIN;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { int32_t yv = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc = inc > yv ? inc : yv; }
+                    int32_t exc = __shfl_up_sync(FULL, inc, 1);
+                    if (lane == 0) exc = INT32_MIN;
+                    const int32_t pm = exc > max_f ? exc : max_f;
+                    const bool is_new = valid && scj > pm;
+                    const bool is_skip = valid && !is_new && tj;
+                    int P = is_skip ? 1 : (is_new ? -1 : 0);
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { int yv = __shfl_up_sync(FULL, P, d); if (lane >= d) P += yv; }
+                    int M = P;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { int yv = __shfl_up_sync(FULL, M, d); if (lane >= d) M = M < yv ? M : yv; }
+                    const int N = P - (M < -n_skip ? M : -n_skip);
+                    const unsigned brk = __ballot_sync(FULL, is_skip && N > o.max_chain_skip);
+                    const int bl = brk ? __ffs(brk) - 1 : 32;
+                    const unsigned newm = __ballot_sync(FULL, is_new) & (bl >= 32 ? FULL : ((1u << bl) - 1));
+                    if (newm) {
+                        int ln = 31 - __clz(newm);
+                        max_f = __shfl_sync(FULL, scj, ln);
+                        max_j = __shfl_sync(FULL, j, ln);
+                    }
+                    if (brk) break;
+                    if (inm != FULL) break;                                // ran past the y window (or the array)
+                    n_skip = __shfl_sync(FULL, N, 31);
+                }
+            }
+        }
+        if (lane == 0) {
+            f[i] = max_f, p[i] = max_j;
+            v[i] = max_j >= 0 && v[max_j] > max_f ? v[max_j] : max_f;
+        }
         __syncwarp();
     }
 }
@@ -298,16 +428,9 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const __grid_constant__ Ch
             const int64_t ao = A.prob_aoff[pidx];
             const int n_a = (int)(A.prob_aoff[pidx + 1] - ao);
             Anchor *a = A.anchors + ao;
-            Reg *regs = A.regs + A.prob_roff[pidx];
-            const int cap_regs = (int)(A.prob_roff[pidx + 1] - A.prob_roff[pidx]);
-            if (n_a == 0) { if (lane == 0) A.prob_nregs[pidx] = 0, A.prob_nca[pidx] = 0; continue; }
+            if (n_a == 0) continue;
             uint8_t *wsb = A.warp_scratch + (size_t)(blockIdx.x * CH_WARPS + wid) * A.warp_scratch_stride;
-            ChainScratch cs;
-            chain_scratch_carve(cs, wsb, (size_t)A.max_na + 1);
-            HitScratch hs;
-            hit_scratch_carve(hs, wsb + chain_scratch_bytes((size_t)A.max_na + 1), (size_t)(2 * (A.max_na / 3) + 8));
-            // indices of minimizers that survive the query-occurrence filter (capacity: max read length + 64)
-            int32_t *kept = (int32_t *)(wsb + chain_scratch_bytes((size_t)A.max_na + 1) + hit_scratch_bytes((size_t)(2 * (A.max_na / 3) + 8)));
+            int32_t *kept = (int32_t *)wsb;    // indices of minimizers that survive the query-occurrence filter
             int nk = 0;
             for (int ib = 0; ib < n; ib += 32) {
                 int i = ib + lane;
@@ -353,58 +476,113 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const __grid_constant__ Ch
                 }
                 run += tot;
             }
-            __syncwarp();
-            if (lane == 0) {
-                rs_sort_emul(a, n_a, KeyX(), cs.sortws);
-                atomicAdd(A.stat_anchors, (unsigned long long)n_a);
-            }
-            __syncwarp();
-            chain_dp_warp(o, n_a, a, cs);
-            int n_u = 0, n_v = 0, rechain = 0, m = 0;
-            if (lane == 0) {
-                chain_backtrack(n_a, cs, o.min_cnt, o.min_chain_score, o.bw, &n_u, &n_v);
-                if (n_u > 0) {
-                    chain_compact(n_u, n_v, cs, a);
-                    if (o.bw_long > o.bw && n_u > 1) {
-                        int32_t st = (int32_t)a[0].y, en = (int32_t)a[(int32_t)cs.u[0] - 1].y;
-                        if (qlen - (en - st) > o.rmq_rescue_size || en - st > qlen * o.rmq_rescue_ratio) {
-                            for (int i = 0; i < n_u; ++i) m += (int32_t)cs.u[i];
-                            rs_sort_emul(a, m, KeyX(), cs.sortws);
-                            rechain = 1;
-                        }
-                    }
-                }
-            }
-            rechain = __shfl_sync(FULL, rechain, 0);
-            m = __shfl_sync(FULL, m, 0);
-            __syncwarp();
-            if (rechain) {
-                chain_rmq_warp(o, m, a, cs);
-                if (lane == 0) {
-                    chain_backtrack(m, cs, o.min_cnt, o.min_chain_score, o.bw_long, &n_u, &n_v);
-                    if (n_u > 0) chain_compact(n_u, n_v, cs, a);
-                }
-            }
-            if (lane == 0) {
-                int n_regs = 0, nca = 0;
-                if (n_u > 0) {
-                    if (n_u > cap_regs) { atomicOr(A.err, TELR_ERR_REGCAP); n_u = cap_regs; }
-                    for (int i = 0; i < n_u; ++i) nca += (int32_t)cs.u[i];
-                    uint32_t hash = A.read_hash[read];
-                    hash ^= wang_hash32((uint32_t)qlen) + o.seed_term;
-                    hash = wang_hash32(hash);
-                    regs_from_chains(hash, qlen, n_u, cs.u, a, regs, hs);
-                    n_regs = n_u;
-                    regs_set_parent(o, n_regs, regs, hs);
-                    regs_select_sub(o, 1, &n_regs, regs, hs, cap_regs);
-                }
-                A.prob_nregs[pidx] = n_regs;
-                A.prob_nca[pidx] = nca;
-            }
+            if (lane == 0) atomicAdd(A.stat_anchors, (unsigned long long)n_a);
             __syncwarp();
         }
         __syncthreads();
     }
+}
+
+// ---- sequential steps, one THREAD per problem (latency hidden by thread-level parallelism) ----
+__global__ void __launch_bounds__(128) k_chain_sort(const __grid_constant__ ChainArgs A)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= A.n_prob) return;
+    const int n_a = (int)(A.prob_aoff[p + 1] - A.prob_aoff[p]);
+    A.prob_nu[p] = 0; A.prob_m[p] = 0; A.prob_nregs[p] = 0; A.prob_nca[p] = 0;
+    if (n_a == 0) return;
+    ChainScratch cs; HitScratch hs; int cap;
+    prob_carve(A, p, n_a, cs, hs, &cap);
+    rs_sort_emul(A.anchors + A.prob_aoff[p], n_a, KeyX(), cs.sortws);
+}
+
+// chaining DP, one WARP per problem
+__global__ void __launch_bounds__(256) k_chain_dp(const __grid_constant__ ChainArgs A)
+{
+    const int lane = threadIdx.x & 31;
+    const int nw = gridDim.x * (blockDim.x >> 5);
+    for (int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < A.n_prob; p += nw) {
+        const int n_a = (int)(A.prob_aoff[p + 1] - A.prob_aoff[p]);
+        if (n_a == 0) continue;
+        ChainScratch cs; HitScratch hs; int cap;
+        prob_carve(A, p, n_a, cs, hs, &cap);
+        chain_dp_warp(A.o, n_a, A.anchors + A.prob_aoff[p], cs);
+        (void)lane;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_chain_bt(const __grid_constant__ ChainArgs A)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= A.n_prob) return;
+    const int n_a = (int)(A.prob_aoff[p + 1] - A.prob_aoff[p]);
+    if (n_a == 0) return;
+    const Opt &o = A.o;
+    ChainScratch cs; HitScratch hs; int cap;
+    prob_carve(A, p, n_a, cs, hs, &cap);
+    Anchor *a = A.anchors + A.prob_aoff[p];
+    const int qlen = A.read_len[A.prob_read[p]];
+    int n_u = 0, n_v = 0, m = 0;
+    chain_backtrack(n_a, cs, o.min_cnt, o.min_chain_score, o.bw, &n_u, &n_v);
+    if (n_u > 0) {
+        chain_compact(n_u, n_v, cs, a);
+        if (o.bw_long > o.bw && n_u > 1) {
+            int32_t st = (int32_t)a[0].y, en = (int32_t)a[(int32_t)cs.u[0] - 1].y;
+            if (qlen - (en - st) > o.rmq_rescue_size || en - st > qlen * o.rmq_rescue_ratio) {
+                for (int i = 0; i < n_u; ++i) m += (int32_t)cs.u[i];
+                rs_sort_emul(a, m, KeyX(), cs.sortws);
+            }
+        }
+    }
+    A.prob_nu[p] = n_u; A.prob_m[p] = m;
+}
+
+// re-chaining DP, one WARP per flagged problem
+__global__ void __launch_bounds__(256) k_chain_rmq(const __grid_constant__ ChainArgs A)
+{
+    const int nw = gridDim.x * (blockDim.x >> 5);
+    for (int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < A.n_prob; p += nw) {
+        const int m = A.prob_m[p];
+        if (m == 0) continue;
+        const int n_a = (int)(A.prob_aoff[p + 1] - A.prob_aoff[p]);
+        ChainScratch cs; HitScratch hs; int cap;
+        prob_carve(A, p, n_a, cs, hs, &cap);
+        chain_rmq_warp(A.o, m, A.anchors + A.prob_aoff[p], cs);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_chain_regs(const __grid_constant__ ChainArgs A)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= A.n_prob) return;
+    const int n_a = (int)(A.prob_aoff[p + 1] - A.prob_aoff[p]);
+    if (n_a == 0) return;
+    const Opt &o = A.o;
+    ChainScratch cs; HitScratch hs; int cap_regs;
+    prob_carve(A, p, n_a, cs, hs, &cap_regs);
+    Anchor *a = A.anchors + A.prob_aoff[p];
+    Reg *regs = A.regs + A.prob_roff[p];
+    const int read = A.prob_read[p], qlen = A.read_len[read];
+    int n_u = A.prob_nu[p], n_v = 0;
+    const int m = A.prob_m[p];
+    if (m > 0) {
+        chain_backtrack(m, cs, o.min_cnt, o.min_chain_score, o.bw_long, &n_u, &n_v);
+        if (n_u > 0) chain_compact(n_u, n_v, cs, a);
+    }
+    int n_regs = 0, nca = 0;
+    if (n_u > 0) {
+        if (n_u > cap_regs) { atomicOr(A.err, TELR_ERR_REGCAP); n_u = cap_regs; }
+        for (int i = 0; i < n_u; ++i) nca += (int32_t)cs.u[i];
+        uint32_t hash = A.read_hash[read];
+        hash ^= wang_hash32((uint32_t)qlen) + o.seed_term;
+        hash = wang_hash32(hash);
+        regs_from_chains(hash, qlen, n_u, cs.u, a, regs, hs);
+        n_regs = n_u;
+        regs_set_parent(o, n_regs, regs, hs);
+        regs_select_sub(o, 1, &n_regs, regs, hs, cap_regs);
+    }
+    A.prob_nregs[p] = n_regs;
+    A.prob_nca[p] = nca;
 }
 
 }  // namespace telr

@@ -57,6 +57,7 @@ struct telr_af_ctx {
     DevBuf b_cov, b_af, b_depth;
     DevBuf b_lrb, b_cboff, b_ctg, b_descs, b_counts, b_mzoff, b_mzx, b_mzy, b_self, b_tabk, b_tabc, b_hpc, b_hpp, b_hpr;
     DevBuf b_pna, b_pread, b_pls, b_paoff, b_prcap, b_proff, b_pnregs, b_pnca, b_anch, b_regs, b_chws, b_alws, b_work;
+    DevBuf b_psb, b_psoff, b_pscr, b_pnu, b_pm;
     DevBuf b_blk, b_pblkoff, b_pblkcnt, b_ctr, b_alnout, b_cigout, b_doff, b_big, b_biglock;
     int n_big = 8; int64_t big_cap = (int64_t)208 << 20;
     cudaEvent_t ev[10];
@@ -99,10 +100,14 @@ __global__ void k_build_descs(int n_reads, int n_loci, const int64_t *read_off, 
     }
 }
 
-__global__ void k_reg_caps(int n, const int32_t *na, int32_t *cap)
+__global__ void k_reg_caps(int n, const int32_t *na, int32_t *cap, int32_t *sbytes)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) cap[i] = na[i] > 0 ? 2 * (na[i] / 3) + 4 : 0;
+    if (i < n) {
+        int a = na[i];
+        cap[i] = a > 0 ? 2 * (a / 3) + 4 : 0;
+        sbytes[i] = a > 0 ? (int32_t)(chain_scratch_bytes((size_t)a + 1) + hit_scratch_bytes((size_t)(2 * (a / 3) + 8))) : 0;
+    }
 }
 
 __global__ void k_worklist(int n, const int32_t *nregs, int32_t *list, int32_t *count)
@@ -201,22 +206,35 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
     CK(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch_smem));
     k_chain<<<ch_grid, CH_THREADS, ch_smem, st>>>(ca);
     k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_pna.as<int32_t>(), ctx->b_paoff.as<int64_t>(), n_prob, ctr + C_MAXNA);
-    k_reg_caps<<<(n_prob + 255) / 256, 256, 0, st>>>(n_prob, ctx->b_pna.as<int32_t>(), ctx->b_prcap.as<int32_t>());
+    ENS(ctx->b_psb, (size_t)(n_prob + 1) * 4); ENS(ctx->b_psoff, (size_t)(n_prob + 2) * 8); ENS(ctx->b_pnu, (size_t)(n_prob + 1) * 4); ENS(ctx->b_pm, (size_t)(n_prob + 1) * 4);
+    k_reg_caps<<<(n_prob + 255) / 256, 256, 0, st>>>(n_prob, ctx->b_pna.as<int32_t>(), ctx->b_prcap.as<int32_t>(), ctx->b_psb.as<int32_t>());
     k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_prcap.as<int32_t>(), ctx->b_proff.as<int64_t>(), n_prob, nullptr);
-    int64_t tot_na = 0, tot_rcap = 0, max_na = 0;
+    k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_psb.as<int32_t>(), ctx->b_psoff.as<int64_t>(), n_prob, nullptr);
+    int64_t tot_na = 0, tot_rcap = 0, max_na = 0, tot_scr = 0;
     CK(cudaMemcpyAsync(&tot_na, ctx->b_paoff.as<int64_t>() + n_prob, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&tot_rcap, ctx->b_proff.as<int64_t>() + n_prob, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&tot_scr, ctx->b_psoff.as<int64_t>() + n_prob, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&max_na, ctr + C_MAXNA, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    ENS(ctx->b_anch, (tot_na + 1) * sizeof(Anchor)); ENS(ctx->b_regs, (tot_rcap + 1) * sizeof(Reg));
+    ENS(ctx->b_anch, (tot_na + 1) * sizeof(Anchor)); ENS(ctx->b_regs, (tot_rcap + 1) * sizeof(Reg)); ENS(ctx->b_pscr, tot_scr + 256);
     const int reg_cap_max = 2 * ((int)max_na / 3) + 8;
-    const size_t ch_stride = chain_scratch_bytes((size_t)max_na + 1) + hit_scratch_bytes((size_t)reg_cap_max) + (((size_t)max_qlen + 64) * 4 & ~(size_t)255) + 256;
+    const size_t ch_stride = (((size_t)max_qlen + 64) * 4 + 255) & ~(size_t)255;
     ENS(ctx->b_chws, ch_stride * (size_t)ch_grid * CH_WARPS);
     CK(cudaMemsetAsync(ctr + C_WORK_CHAIN, 0, 8, st));
     ca.mode = 1; ca.prob_aoff = ctx->b_paoff.as<int64_t>(); ca.prob_roff = ctx->b_proff.as<int64_t>();
     ca.anchors = ctx->b_anch.as<Anchor>(); ca.regs = ctx->b_regs.as<Reg>();
     ca.warp_scratch = ctx->b_chws.as<uint8_t>(); ca.warp_scratch_stride = ch_stride; ca.max_na = (int)max_na;
+    ca.prob_scratch = ctx->b_pscr.as<uint8_t>(); ca.prob_soff = ctx->b_psoff.as<int64_t>();
+    ca.prob_nu = ctx->b_pnu.as<int32_t>(); ca.prob_m = ctx->b_pm.as<int32_t>(); ca.n_prob = n_prob;
     k_chain<<<ch_grid, CH_THREADS, ch_smem, st>>>(ca);
+    {
+        const int tb = (n_prob + 127) / 128, wg = std::max(1, std::min((n_prob + 7) / 8, sm * 8));
+        k_chain_sort<<<tb, 128, 0, st>>>(ca);
+        k_chain_dp<<<wg, 256, 0, st>>>(ca);
+        k_chain_bt<<<tb, 128, 0, st>>>(ca);
+        k_chain_rmq<<<wg, 256, 0, st>>>(ca);
+        k_chain_regs<<<tb, 128, 0, st>>>(ca);
+    }
     CK(cudaEventRecord(ctx->ev[2], st));
     // ---- (d) alignment ----
     ENS(ctx->b_work, (size_t)(n_prob + 1) * 4);
@@ -294,7 +312,7 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
     }
     stats->dp_cells += hc[C_CELLS]; stats->n_dp_tasks += hc[C_TASKS]; stats->n_anchors += hc[C_ANCH]; stats->n_minimizers += n_mz;
     stats->n_aln_blocks += hc[C_NBLK];
-    ctx->launches += 14 + (n_work > 0 ? 1 : 0);   // unpack, descs, sketch x2, scan x3, self_count, chain x2, reg_caps, worklist, align, depth_af
+    ctx->launches += 20 + (n_work > 0 ? 1 : 0);   // unpack, descs, sketch x2, scan x4, self_count, chain x2 + sort/dp/bt/rmq/regs, reg_caps, worklist, align, depth_af
     if (d_aln_out) { stats->n_aln = hc[C_NALN]; stats->n_cigar = hc[C_NCIG]; }
     float ms;
     static const int pairs[5][3] = {{0, 1, 0}, {1, 2, 1}, {2, 3, 2}, {3, 4, 3}, {4, 5, 6}};
@@ -395,7 +413,7 @@ int telr_af_destroy(telr_af_ctx *ctx)
                      &ctx->b_mzx, &ctx->b_mzy, &ctx->b_self, &ctx->b_tabk, &ctx->b_tabc, &ctx->b_hpc, &ctx->b_hpp, &ctx->b_hpr, &ctx->b_pna, &ctx->b_pread,
                      &ctx->b_pls, &ctx->b_paoff, &ctx->b_prcap, &ctx->b_proff, &ctx->b_pnregs, &ctx->b_pnca, &ctx->b_anch, &ctx->b_regs, &ctx->b_chws,
                      &ctx->b_alws, &ctx->b_work, &ctx->b_blk, &ctx->b_pblkoff, &ctx->b_pblkcnt, &ctx->b_ctr, &ctx->b_alnout, &ctx->b_cigout, &ctx->b_doff,
-                     &ctx->b_big, &ctx->b_biglock};
+                     &ctx->b_big, &ctx->b_biglock, &ctx->b_psb, &ctx->b_psoff, &ctx->b_pscr, &ctx->b_pnu, &ctx->b_pm};
     for (auto *b : all) b->release();
     for (auto &b : ctx->b_in) b.release();
     for (auto &e : ctx->ev) cudaEventDestroy(e);
