@@ -836,6 +836,8 @@ static void append_cigar(actx_t *c, reg_t *r, uint32_t n_cigar, const uint32_t *
     }
 }
 
+int64_t orc_cell_stats[8];   /* debugging: cells by task class */
+int64_t orc_size_hist[4][16];
 static void align_pair(actx_t *c, int qlen, const uint8_t *qseq, int tlen, const uint8_t *tseq, int w, int end_bonus,
                        int zdrop, int flag)
 {
@@ -851,6 +853,17 @@ static void align_pair(actx_t *c, int qlen, const uint8_t *qseq, int tlen, const
     orc_ksw_extd2(qlen, qseq, tlen, tseq, o->a, o->b, o->sc_ambi, o->q, o->e, o->q2, o->e2, w, zdrop, end_bonus, flag, ez);
     c->cells += ez->cells;
     c->n_tasks++;
+    {
+        int cls = (flag & ORC_KSW_APPROX_MAX) ? 0 : (flag & ORC_KSW_EXTZ_ONLY) ? 2 : 1, b = 0;
+        int mx = qlen > tlen ? qlen : tlen;
+        while ((1 << (b + 5)) < mx && b < 15) ++b;
+#pragma omp atomic
+        orc_cell_stats[cls] += ez->cells;
+#pragma omp atomic
+        orc_cell_stats[4 + cls] += 1;
+#pragma omp atomic
+        orc_size_hist[cls][b] += ez->cells;
+    }
 }
 
 static inline void update_max_zdrop(int32_t score, int i, int j, int32_t *max, int *max_i, int *max_j, int e,

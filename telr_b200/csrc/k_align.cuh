@@ -17,6 +17,8 @@ namespace telr {
 
 constexpr int AL_THREADS = 128;
 constexpr int AL_WARPS = AL_THREADS / 32;
+constexpr int DP_SCOLS = 1024;         // columns of DP state kept in shared memory per warp (power of two)
+struct DpWarpSmem { int8_t st[6][DP_SCOLS]; int32_t H[DP_SCOLS]; };
 
 struct DpScratch {
     int8_t *u, *v, *x, *y, *x2, *y2;   // [maxT] each
@@ -24,6 +26,8 @@ struct DpScratch {
     int32_t *ll;                       // [6 * maxT] local-probe rows
     uint8_t *dir; int64_t dir_cap;
     uint32_t *ezcig; int32_t ezcap;
+    // shared-memory circular window of DP_SCOLS columns (used when the live band fits)
+    int8_t *s_state; int32_t *s_H;
     // shared pool of large traceback buffers for the rare task that does not fit `dir`
     uint8_t *big; int64_t big_cap; int32_t n_big; int32_t *big_lock;
 };
@@ -70,7 +74,8 @@ struct EzPush {
 };
 
 // two-piece affine extension / global DP, warp-wide.  R lives in shared memory.
-__device__ void warp_extd2(const Opt &o, const DpTask &T, DpRes &R, DpScratch &S, unsigned long long *cells_acc, int32_t *err)
+template <bool SMEM>
+__device__ void warp_extd2_impl(const Opt &o, const DpTask &T, DpRes &R, DpScratch &S, unsigned long long *cells_acc, int32_t *err)
 {
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
@@ -112,11 +117,16 @@ __device__ void warp_extd2(const Opt &o, const DpTask &T, DpRes &R, DpScratch &S
         p = S.big + (int64_t)big_slot * S.big_cap;
     }
     const bool approx = flag & KSW_APPROX_MAX, right = flag & KSW_RIGHT;
-    int8_t *u = S.u, *v = S.v, *x = S.x, *y = S.y, *x2 = S.x2, *y2 = S.y2;
-    int32_t *H = S.H;
-    for (int t = lane; t < tlen; t += 32) {
-        u[t] = v[t] = x[t] = y[t] = (int8_t)(-q - e);
-        x2[t] = y2[t] = (int8_t)(-q2 - e2);
+    // column t lives at slot (t & CM): the whole target for the global variant, a circular window in shared memory otherwise
+    constexpr int CM = SMEM ? DP_SCOLS - 1 : 0x7fffffff;
+    int8_t *u = SMEM ? S.s_state : S.u, *v = SMEM ? S.s_state + DP_SCOLS : S.v, *x = SMEM ? S.s_state + 2 * DP_SCOLS : S.x;
+    int8_t *y = SMEM ? S.s_state + 3 * DP_SCOLS : S.y, *x2 = SMEM ? S.s_state + 4 * DP_SCOLS : S.x2, *y2 = SMEM ? S.s_state + 5 * DP_SCOLS : S.y2;
+    int32_t *H = SMEM ? S.s_H : S.H;
+    if (!SMEM) {
+        for (int t = lane; t < tlen; t += 32) {
+            u[t] = v[t] = x[t] = y[t] = (int8_t)(-q - e);
+            x2[t] = y2[t] = (int8_t)(-q2 - e2);
+        }
     }
     __syncwarp();
     // uniform running state (identical in every lane)
@@ -137,19 +147,27 @@ __device__ void warp_extd2(const Opt &o, const DpTask &T, DpRes &R, DpScratch &S
         const int bnd = r == 0 ? -q - e : r < long_thres ? -e : r == long_thres ? long_diff : -e2;
         int sx1, sx21, sv1;        // left neighbour of the first cell
         if (st > 0) {
-            if (st - 1 >= pst && st - 1 <= pen) sx1 = x[st - 1], sx21 = x2[st - 1], sv1 = v[st - 1];
+            if (st - 1 >= pst && st - 1 <= pen) sx1 = x[(st - 1) & CM], sx21 = x2[(st - 1) & CM], sv1 = v[(st - 1) & CM];
             else sx1 = -q - e, sx21 = -q2 - e2, sv1 = -q - e;
         } else sx1 = -q - e, sx21 = -q2 - e2, sv1 = bnd;
-        if (en == r && lane == 0) { y[r] = (int8_t)(-q - e); y2[r] = (int8_t)(-q2 - e2); u[r] = (int8_t)bnd; }
+        if (lane == 0) {
+            if (SMEM && en > pen) {     // a column enters the band: its slot still holds column en - DP_SCOLS
+                const int se = en & CM;
+                u[se] = v[se] = x[se] = y[se] = (int8_t)(-q - e);
+                x2[se] = y2[se] = (int8_t)(-q2 - e2);
+            }
+            if (en == r) { y[r & CM] = (int8_t)(-q - e); y2[r & CM] = (int8_t)(-q2 - e2); u[r & CM] = (int8_t)bnd; }
+        }
         __syncwarp();
         uint8_t *pr = p + (int64_t)r * ncol;
         for (int c = (en - st) >> 5; c >= 0; --c) {
             const int t = st + (c << 5) + lane;
             const bool act = t <= en;
             int ut = 0, yt = 0, y2t = 0, v1 = sv1, x1 = sx1, x21 = sx21, z = 0;
+            const int ts = t & CM, tp = (t - 1) & CM;
             if (act) {
-                ut = u[t], yt = y[t], y2t = y2[t];
-                if (t > st) v1 = v[t - 1], x1 = x[t - 1], x21 = x2[t - 1];
+                ut = u[ts], yt = y[ts], y2t = y2[ts];
+                if (t > st) v1 = v[tp], x1 = x[tp], x21 = x2[tp];
                 int qc = dp_base(T.q, T.qstep, T.qcomp, r - t), tc = dp_base(T.t, T.tstep, 0, t);
                 z = (qc > 3 || tc > 3) ? -o.sc_ambi : qc == tc ? o.a : -o.b;
             }
@@ -168,20 +186,20 @@ __device__ void warp_extd2(const Opt &o, const DpTask &T, DpRes &R, DpScratch &S
                     d = z > b2 ? d : 4; z = z > b2 ? z : b2;
                 }
                 if (z > o.a) z = o.a;
-                u[t] = (int8_t)(z - v1);
-                v[t] = (int8_t)(z - ut);
+                u[ts] = (int8_t)(z - v1);
+                v[ts] = (int8_t)(z - ut);
                 int tmp = z - q;  a -= tmp, b -= tmp;
                 tmp = z - q2;     a2 -= tmp, b2 -= tmp;
                 if (!right) {
-                    x[t] = (int8_t)((a > 0 ? a : 0) - qe);     d |= a > 0 ? 0x08 : 0;
-                    y[t] = (int8_t)((b > 0 ? b : 0) - qe);     d |= b > 0 ? 0x10 : 0;
-                    x2[t] = (int8_t)((a2 > 0 ? a2 : 0) - qe2); d |= a2 > 0 ? 0x20 : 0;
-                    y2[t] = (int8_t)((b2 > 0 ? b2 : 0) - qe2); d |= b2 > 0 ? 0x40 : 0;
+                    x[ts] = (int8_t)((a > 0 ? a : 0) - qe);     d |= a > 0 ? 0x08 : 0;
+                    y[ts] = (int8_t)((b > 0 ? b : 0) - qe);     d |= b > 0 ? 0x10 : 0;
+                    x2[ts] = (int8_t)((a2 > 0 ? a2 : 0) - qe2); d |= a2 > 0 ? 0x20 : 0;
+                    y2[ts] = (int8_t)((b2 > 0 ? b2 : 0) - qe2); d |= b2 > 0 ? 0x40 : 0;
                 } else {
-                    x[t] = (int8_t)((a >= 0 ? a : 0) - qe);     d |= a >= 0 ? 0x08 : 0;
-                    y[t] = (int8_t)((b >= 0 ? b : 0) - qe);     d |= b >= 0 ? 0x10 : 0;
-                    x2[t] = (int8_t)((a2 >= 0 ? a2 : 0) - qe2); d |= a2 >= 0 ? 0x20 : 0;
-                    y2[t] = (int8_t)((b2 >= 0 ? b2 : 0) - qe2); d |= b2 >= 0 ? 0x40 : 0;
+                    x[ts] = (int8_t)((a >= 0 ? a : 0) - qe);     d |= a >= 0 ? 0x08 : 0;
+                    y[ts] = (int8_t)((b >= 0 ? b : 0) - qe);     d |= b >= 0 ? 0x10 : 0;
+                    x2[ts] = (int8_t)((a2 >= 0 ? a2 : 0) - qe2); d |= a2 >= 0 ? 0x20 : 0;
+                    y2[ts] = (int8_t)((b2 >= 0 ? b2 : 0) - qe2); d |= b2 >= 0 ? 0x40 : 0;
                 }
                 pr[t - st] = (uint8_t)d;
             }
@@ -190,18 +208,18 @@ __device__ void warp_extd2(const Opt &o, const DpTask &T, DpRes &R, DpScratch &S
         if (!approx) {
             int32_t max_H, max_t, Hen, Hst;
             if (r > 0) {
-                Hen = en > 0 ? H[en - 1] + u[en] : H[en] + v[en];     // uniform load, before H[en-1] is advanced
+                Hen = en > 0 ? H[(en - 1) & CM] + u[en & CM] : H[en & CM] + v[en & CM];     // uniform load, before H[en-1] is advanced
                 __syncwarp();
                 const int en1 = st + (en - st) / 4 * 4;
                 int32_t bh = KSW_NEG_INF * 2; int brank = 0x7fffffff, bt = -1, hst = 0;
                 for (int t = st + lane; t < en; t += 32) {
-                    int32_t h = H[t] + v[t];
-                    H[t] = h;
+                    int32_t h = H[t & CM] + v[t & CM];
+                    H[t & CM] = h;
                     if (t == st) hst = h;
                     int rank = t < en1 ? 1 + (((t - st) & 3) << 20) + ((t - st) >> 2) : 1 + (4 << 20) + (t - en1);
                     if (h > bh || (h == bh && rank < brank)) bh = h, brank = rank, bt = t;
                 }
-                if (lane == 0) { H[en] = Hen; if (Hen > bh || (Hen == bh)) bh = Hen, brank = 0, bt = en; }
+                if (lane == 0) { H[en & CM] = Hen; if (Hen > bh || (Hen == bh)) bh = Hen, brank = 0, bt = en; }
 #pragma unroll
                 for (int d = 16; d; d >>= 1) {
                     int32_t oh = __shfl_xor_sync(FULL, bh, d); int orank = __shfl_xor_sync(FULL, brank, d), ot = __shfl_xor_sync(FULL, bt, d);
@@ -230,10 +248,10 @@ __device__ void warp_extd2(const Opt &o, const DpTask &T, DpRes &R, DpScratch &S
         } else {
             if (r > 0) {
                 if (last_H0_t >= st && last_H0_t <= en && last_H0_t + 1 >= st && last_H0_t + 1 <= en) {
-                    int d0 = v[last_H0_t], d1 = u[last_H0_t + 1];
+                    int d0 = v[last_H0_t & CM], d1 = u[(last_H0_t + 1) & CM];
                     if (d0 > d1) H0 += d0; else H0 += d1, ++last_H0_t;
-                } else if (last_H0_t >= st && last_H0_t <= en) H0 += v[last_H0_t];
-                else ++last_H0_t, H0 += u[last_H0_t];
+                } else if (last_H0_t >= st && last_H0_t <= en) H0 += v[last_H0_t & CM];
+                else ++last_H0_t, H0 += u[last_H0_t & CM];
             } else H0 = (int32_t)v[0] - qe, last_H0_t = 0;
             if (r == nr - 1 && en == tlen - 1) ez_score = H0;
         }
@@ -279,6 +297,15 @@ __device__ void warp_extd2(const Opt &o, const DpTask &T, DpRes &R, DpScratch &S
         if (big_slot >= 0) { __threadfence(); atomicExch(&S.big_lock[big_slot], 0); }
     }
     __syncwarp();
+}
+
+__device__ __forceinline__ void warp_extd2(const Opt &o, const DpTask &T, DpRes &R, DpScratch &S, unsigned long long *cells_acc, int32_t *err)
+{
+    int w = T.w < 0 ? (T.tlen > T.qlen ? T.tlen : T.qlen) : T.w;
+    int ncol = T.qlen < T.tlen ? T.qlen : T.tlen;
+    if (ncol > w + 1) ncol = w + 1;
+    if (S.s_state && ncol + 2 <= DP_SCOLS) warp_extd2_impl<true>(o, T, R, S, cells_acc, err);
+    else warp_extd2_impl<false>(o, T, R, S, cells_acc, err);
 }
 
 // local affine Smith-Waterman score probe with end coordinates (first maximum in target-major order)
@@ -332,6 +359,7 @@ struct AlWarpSmem { AlnCtx c; DpTask task; DpRes res; int more; };
 __global__ void __launch_bounds__(AL_THREADS) k_align(const __grid_constant__ AlignArgs A)
 {
     __shared__ AlWarpSmem WS[AL_WARPS];
+    __shared__ DpWarpSmem DS[AL_WARPS];
     const Opt &o = A.o;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned FULL = 0xffffffffu;
@@ -353,6 +381,7 @@ __global__ void __launch_bounds__(AL_THREADS) k_align(const __grid_constant__ Al
     base = (uint8_t *)(((uintptr_t)base + 255) & ~(uintptr_t)255);
     S.dir = base; S.dir_cap = A.dir_cap;
     S.big = A.big; S.big_cap = A.big_cap; S.n_big = A.n_big; S.big_lock = A.big_lock;
+    S.s_state = &DS[wid].st[0][0]; S.s_H = DS[wid].H;
 
     for (;;) {
         int wi = 0;

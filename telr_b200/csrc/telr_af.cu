@@ -620,6 +620,7 @@ __global__ void __launch_bounds__(AL_THREADS) k_dp_stage(const __grid_constant__
     __shared__ DpRes RS[AL_WARPS];
     __shared__ DpTask TS[AL_WARPS];
     __shared__ unsigned long long CS[AL_WARPS];
+    __shared__ DpWarpSmem DS[AL_WARPS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint8_t *base = A.warp_scratch + (size_t)(blockIdx.x * AL_WARPS + wid) * A.stride;
     const size_t maxT = (size_t)A.maxT, maxQ = (size_t)A.maxQ;
@@ -632,6 +633,7 @@ __global__ void __launch_bounds__(AL_THREADS) k_dp_stage(const __grid_constant__
     base = (uint8_t *)(((uintptr_t)base + 255) & ~(uintptr_t)255);
     S.dir = base; S.dir_cap = A.dir_cap;
     S.big = A.big; S.big_cap = A.big_cap; S.n_big = A.n_big; S.big_lock = A.big_lock;
+    S.s_state = &DS[wid].st[0][0]; S.s_H = DS[wid].H;
     for (;;) {
         int i = 0;
         if (lane == 0) i = atomicAdd(A.work_counter, 1);
