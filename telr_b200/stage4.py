@@ -1,0 +1,287 @@
+"""Drop-in replacement for TELR's stage-4 function ``get_af`` (reference src/telr/TELR_te.py:578-838).
+
+Same signature, same returned dict (9 keys per locus), same side files:
+  <vcf_parsed>.new                      (TELR_assembly.py:388-415)
+  <out>/telr_reads/<locus>.reads.fa     (TELR_assembly.py:429-456, TELR_te.py:615-617)
+  <contig_dir>/<locus>.cns.ctg1.revcomp.fa  (TELR_te.py:624-627)
+  <vcf_parsed>.freq, <vcf_parsed>.revcomp.freq   (TELR_te.py:677-755)
+The body between them - per locus 2 x `minimap2 -a -x <preset>`, up to 8 x `samtools depth`, medians - runs on
+the GPU through the C ABI (include/telr_af.h).  Intermediate *.realign.sort.bam files are not produced.
+
+Install into a TELR checkout with:   import telr.telr, telr_b200.stage4;  telr.telr.get_af = telr_b200.stage4.get_af
+"""
+from __future__ import annotations
+
+import logging
+import math
+import os
+import statistics
+import threading
+import time
+
+import numpy as np
+
+from . import lib
+from .bamio import BamIndex
+from .batch import Batch, PRESETS, name_hash, pack_sequences
+
+_COMP = bytes.maketrans(b"ACGTacgtNnUuRYKMSWBDHVrykmswbdhv", b"TGCAtgcaNnAaYRMKSWVHDByrmkswvhdb")
+
+
+def format_time(t):       # TELR_utility.py:34-41
+    from datetime import datetime, timedelta
+    d = datetime(1, 1, 1) + timedelta(seconds=t)
+    if d.hour == 0 and d.minute == 0:
+        return "%d seconds" % (d.second)
+    elif d.hour == 0 and d.minute != 0:
+        return "%d minutes %d seconds" % (d.minute, d.second)
+    return "%d hours %d minutes %d seconds" % (d.hour, d.minute, d.second)
+
+
+def read_fasta(path):
+    """[(id, sequence)] of a FASTA or FASTQ file; id = first whitespace-delimited token (Biopython record.id)."""
+    recs = []
+    with open(path, "rb") as fh:
+        first = fh.read(1)
+        fh.seek(0)
+        if first == b"@":
+            while True:
+                h = fh.readline()
+                if not h:
+                    break
+                s = fh.readline().strip()
+                fh.readline()
+                fh.readline()
+                recs.append((h[1:].split()[0].decode(), s))
+        else:
+            name, chunks = None, []
+            for line in fh:
+                if line.startswith(b">"):
+                    if name is not None:
+                        recs.append((name, b"".join(chunks)))
+                    name, chunks = (line[1:].split() or [b""])[0].decode(), []
+                else:
+                    chunks.append(line.strip())
+            if name is not None:
+                recs.append((name, b"".join(chunks)))
+    return recs
+
+
+def median_str(cov2x: int, n: int) -> str:
+    """str(statistics.median(values)) given 2*median and the number of values (int for odd n, float for even n)."""
+    if cov2x == -1:
+        return "None"
+    if cov2x < 0:
+        raise statistics.StatisticsError("no median for empty data")   # the reference dies here too (TELR_te.py:882)
+    if n % 2 == 1:
+        return str(cov2x // 2)
+    return str(cov2x / 2)
+
+
+def window_sizes(L, s, e, fl, fo, ti, to):
+    """Number of depth values samtools returns for the 4 windows of one strand (te5p, te3p, flank5p, flank3p)."""
+    def n(S, E):
+        return max(0, min(E, L) - max(S - 1, 0))
+    if ti and s + to + ti < e:
+        a, b = n(s + to, s + to + ti), n(e - ti - to, e - to)
+    else:
+        a = b = n(s, e)
+    return a, b, n(s - fl - fo, s - fo), n(e + fo, e + fl + fo)
+
+
+def te_flank_ratio(te_cov, flank_cov):      # TELR_te.py:564-575
+    if te_cov and flank_cov:
+        ratio = te_cov / flank_cov
+        return None if ratio > 1.5 else ratio
+    return None
+
+
+def combine_af(taf_5p, taf_3p):             # TELR_te.py:818-835
+    if taf_5p and taf_3p:
+        freq = (taf_5p + taf_3p) / 2 if abs(taf_5p - taf_3p) <= 0.3 else None
+    elif taf_5p:
+        freq = taf_5p
+    elif taf_3p:
+        freq = taf_3p
+    else:
+        freq = None
+    if freq:
+        if freq > 1:
+            freq = 1
+    return round(freq, 3) if freq else None
+
+
+def run_batch(batch: Batch, devices=None, **kw):
+    """Run the GPU path on one or several devices (loci sharded by read bases, host-side gather, no collective)."""
+    if devices is None:
+        env = os.environ.get("TELR_B200_DEVICES")
+        devices = [int(x) for x in env.split(",")] if env else [0]
+    if len(devices) == 1:
+        ctx = lib.Context(devices[0])
+        try:
+            r = ctx.run(batch, **kw)
+            return r.cov2x, r.af, r
+        finally:
+            ctx.close()
+    shards = partition_loci(batch, len(devices))
+    cov = np.zeros((batch.n_loci, 8), np.int32)
+    af = np.zeros(batch.n_loci, np.float64)
+    errs = []
+
+    def work(dev, loci):
+        try:
+            if not loci:
+                return
+            ctx = lib.Context(dev)
+            try:
+                r = ctx.run(batch.subset(loci))
+                cov[loci] = r.cov2x
+                af[loci] = r.af
+            finally:
+                ctx.close()
+        except Exception as ex:     # noqa: BLE001
+            errs.append(ex)
+    th = [threading.Thread(target=work, args=(d, s)) for d, s in zip(devices, shards)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    if errs:
+        raise errs[0]
+    return cov, af, None
+
+
+def partition_loci(batch: Batch, n: int):
+    """Longest-processing-time-first assignment of loci to n shards by read bases x contig length."""
+    lrb = batch.locus_read_begin
+    csum = np.concatenate([[0], np.cumsum(batch.read_len.astype(np.int64))])
+    cost = (csum[lrb[1:]] - csum[lrb[:-1]]) + batch.contig_len.astype(np.int64)
+    order = np.argsort(-cost, kind="stable")
+    loads = [0] * n
+    shards = [[] for _ in range(n)]
+    for l in order:
+        k = min(range(n), key=lambda i: loads[i])
+        shards[k].append(int(l))
+        loads[k] += int(cost[l])
+    return [sorted(s) for s in shards]
+
+
+def get_af(out, sample_name, bam, raw_reads, contig_te_annotation, contig_dir, vcf_parsed, flank_intervel_size, flank_offset,
+           te_interval_size, te_offset, presets, thread):
+    logging.info("Estimating allele frequency...")
+    start_time = time.time()
+    presets = "map-ont" if presets == "ont" else "map-pb"         # TELR_te.py:595-598
+
+    # ---- prep_assembly_inputs(read_type="all"): reads in the +-1 kb breakpoint window of every locus ----
+    telr_reads_dir = os.path.join(out, "telr_reads")
+    os.makedirs(telr_reads_dir, exist_ok=True)
+    window = 1000
+    bam_idx = BamIndex(bam)
+    raw = dict(read_fasta(raw_reads))
+    rows, locus_reads = [], []
+    with open(vcf_parsed) as fh, open(vcf_parsed + ".new", "w") as new:
+        for line in fh:
+            entry = line.replace("\n", "").split("\t")
+            bp = round((int(entry[1]) + int(entry[2])) / 2)        # banker's rounding, as the reference
+            names = sorted(set(bam_idx.fetch(entry[0], max(bp - window, 0), bp + window)))
+            new.write(line.replace("\n", "") + "\t" + str(len(names)) + "\n")
+            rows.append(entry)
+            locus_reads.append(names)
+    loci = []
+    for entry, names in zip(rows, locus_reads):
+        contig_name = "_".join(entry[0:3])
+        with open(os.path.join(telr_reads_dir, contig_name + ".reads.fa"), "wb") as fa:
+            for n in names:
+                if n not in raw:
+                    raise KeyError(n)                              # SeqIO.index(...).get_raw raises KeyError
+                fa.write(b">" + n.encode() + b"\n" + raw[n] + b"\n")
+        contig = os.path.join(contig_dir, contig_name + ".cns.ctg1.fa")
+        if not os.path.isfile(contig):
+            print(contig_name + " no assembly")
+            loci.append(None)
+            continue
+        recs = read_fasta(contig)
+        with open(os.path.join(contig_dir, contig_name + ".cns.ctg1.revcomp.fa"), "w") as fo:
+            for rid, seq in recs:
+                fo.write(">" + rid + "\n" + seq.translate(_COMP)[::-1].decode() + "\n")
+        loci.append((contig_name, recs[0][1] if recs else b"", names))
+
+    logging.info("Perform local realignment...")
+    start_time = time.time()
+    # contig annotation: last BED row per contig wins (dict overwrite, TELR_te.py:656-675)
+    coords = {}
+    with open(contig_te_annotation) as fh:
+        for line in fh:
+            entry = line.replace("\n", "").split("\t")
+            contig = os.path.join(contig_dir, entry[0] + ".cns.ctg1.fa")
+            if os.path.isfile(contig) and os.stat(contig).st_size != 0:
+                coords[entry[0]] = (int(entry[1]), int(entry[2]))
+
+    # ---- pack the batch ----
+    live = [i for i, l in enumerate(loci) if l is not None and len(l[1]) > 0]
+    seqs, rlen_hash = [], []
+    lrb = [0]
+    for i in live:
+        name, ctg, names = loci[i]
+        seqs.append(ctg)
+        for n in names:
+            seqs.append(raw[n])
+            rlen_hash.append(name_hash(n))
+        lrb.append(len(rlen_hash))
+    L = lib.lib()
+    seq2, nmask, offs, lens = pack_sequences(seqs, L)
+    is_ctg = np.zeros(len(seqs), bool)
+    k = 0
+    for j, i in enumerate(live):
+        is_ctg[k] = True
+        k += 1 + (lrb[j + 1] - lrb[j])
+    te_s = np.array([coords.get(loci[i][0], (-1, -1))[0] for i in live], np.int32)
+    te_e = np.array([coords.get(loci[i][0], (-1, -1))[1] for i in live], np.int32)
+    batch = Batch(PRESETS[presets], seq2, nmask, offs[~is_ctg].copy(), lens[~is_ctg].copy(), np.array(rlen_hash, np.uint32),
+                  np.array(lrb, np.int32), offs[is_ctg].copy(), lens[is_ctg].copy(), te_s, te_e,
+                  int(flank_intervel_size), int(flank_offset), int(te_interval_size or 0), int(te_offset))
+    empty = [j for j in range(len(live)) if lrb[j + 1] == lrb[j]]
+    if batch.n_loci:
+        try:
+            cov2x, af, _ = run_batch(batch)
+        except Exception as e:     # noqa: BLE001   (TELR_te.py:649-652)
+            print(e)
+            print("Local realignment failed, exiting...")
+            raise SystemExit(1)
+    else:
+        cov2x, af = np.zeros((0, 8), np.int32), np.zeros(0)
+    logging.info("Local realignment finished in " + format_time(time.time() - start_time))
+    del empty
+
+    # ---- .freq / .revcomp.freq, then the AF block exactly as the reference parses them back ----
+    pos_of = {i: j for j, i in enumerate(live)}
+    fl, fo, ti, to = int(flank_intervel_size), int(flank_offset), int(te_interval_size or 0), int(te_offset)
+    te_freq = {}
+    for strand, suffix in ((0, ".freq"), (1, ".revcomp.freq")):
+        with open(vcf_parsed + suffix, "w") as fo_:
+            for i, entry in enumerate(rows):
+                if i not in pos_of:
+                    continue
+                name = loci[i][0]
+                if name not in coords:
+                    continue
+                j = pos_of[i]
+                Lc = int(batch.contig_len[j])
+                s, e = coords[name]
+                if strand:
+                    s, e = Lc - e, Lc - s
+                ns = window_sizes(Lc, s, e, fl, fo, ti, to)
+                vals = [median_str(int(cov2x[j, strand * 4 + k]), ns[k]) for k in range(4)]
+                fo_.write("\t".join(entry + vals) + "\n")
+                cov = [None if v == "None" else float(v) for v in vals]
+                d = te_freq.setdefault(name, {})
+                sfx = "_rc" if strand else ""
+                d["te_5p_cov" + sfx], d["te_3p_cov" + sfx], d["flank_5p_cov" + sfx], d["flank_3p_cov" + sfx] = cov
+                if strand:
+                    freq = combine_af(te_flank_ratio(d["te_5p_cov"], d["flank_5p_cov"]), te_flank_ratio(d["te_5p_cov_rc"], d["flank_5p_cov_rc"]))
+                    g = af[j]                       # device value before clamp/round; must agree with the Python formula
+                    if freq is None:
+                        assert math.isnan(g), (name, g)
+                    else:
+                        assert abs(round(1 if g > 1 else g, 3) - freq) < 1e-9, (name, g, freq)
+                    d["freq"] = freq
+    logging.info("Allele frequency estimation finished in " + format_time(time.time() - start_time))
+    return te_freq

@@ -71,3 +71,19 @@ def ref_af_block(freq_path, freq_rc_path):
     mod = ast.Module(body=[fns["get_te_flank_ratio"]] + blk, type_ignores=[])
     exec(compile(mod, REF, "exec"), ns)
     return ns["te_freq"]
+
+
+def synth_depth(seed: int, L: int, s: int, e: int):
+    """Deterministic pseudo-random fw/rc depth arrays (own LCG, so fixtures only need to store the seed)."""
+    st = (seed * 2862933555777941757 + 3037000493) & 0xFFFFFFFFFFFFFFFF
+
+    def nxt():
+        nonlocal st
+        st = (st * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
+        return st >> 33
+    base = nxt() % 61
+    zero = nxt() % 7 == 0
+    bump = nxt() % 26
+    dfw = [0 if zero else max(0, base + nxt() % 17 - 8 + (15 if s <= i < e else 0)) for i in range(L)]
+    drc = [max(0, base + nxt() % 17 - 8 + (bump if L - e <= i < L - s else 0)) for i in range(L)]
+    return dfw, drc

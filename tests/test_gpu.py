@@ -1,0 +1,234 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+Bit-exact for alignment coordinates/CIGARs, per-base depth, coverage integers, DP cell counts; AF within 1e-9."""
+import ctypes as C
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from telr_b200 import lib, stage4, synth
+from telr_b200.batch import pack_sequences
+from tests import orc, util
+from tests.test_host import _make_stage3_artifacts
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx(built):
+    c = lib.Context(0)
+    yield c
+    c.close()
+
+
+def _seqs(rng, hpc, with_n):
+    seqs = []
+    for ln in (1, 5, 14, 15, 24, 25, 26, 100, 2047, 2048, 2049, 4096, 4100, 10000, 33333):
+        s = rng.integers(0, 4, ln).astype(np.uint8)
+        if hpc:
+            for _ in range(ln // 50):
+                p = rng.integers(0, ln); s[p:p + rng.integers(2, 12)] = s[p]
+        if ln > 300:
+            s[200:290] = np.tile(s[200:207], 13)[:90]           # tandem array: identical hashes inside windows
+        b = np.array(list(b"ACGT"), np.uint8)[s]
+        if with_n and ln > 30:
+            for _ in range(max(1, ln // 400)):
+                b[rng.integers(0, ln)] = ord("N")
+        seqs.append(bytes(b))
+    return seqs
+
+
+@pytest.mark.parametrize("w,k,hpc", [(10, 15, 0), (10, 19, 1), (19, 19, 0)])
+@pytest.mark.parametrize("with_n", [False, True])
+def test_sketch_matches_oracle(ctx, w, k, hpc, with_n):
+    rng = np.random.default_rng(7 + w + k + hpc)
+    seqs = _seqs(rng, hpc, with_n)
+    seq2, nmask, offs, lens = pack_sequences(seqs)
+    x, y, off = ctx.sketch(seq2, nmask, offs, lens, w, k, hpc)
+    for i, s in enumerate(seqs):
+        nt4 = np.array([{65: 0, 67: 1, 71: 2, 84: 3}.get(c, 4) for c in s], np.uint8)
+        ox, oy = orc.sketch(nt4, w, k, hpc)
+        assert (ox == x[off[i]:off[i + 1]]).all() and (oy == y[off[i]:off[i + 1]]).all(), (len(s), w, k, hpc)
+
+
+def test_sketch_empty_batch(ctx):
+    x, y, off = ctx.sketch(np.zeros(0, np.uint32), np.zeros(0, np.uint32), np.zeros(0, np.int64), np.zeros(0, np.int32), 10, 15)
+    assert len(x) == 0 and off.tolist() == [0]
+
+
+@pytest.mark.parametrize("mode", ["0", "1"])
+def test_depth_and_af_stage(built, mode, monkeypatch):
+    monkeypatch.setenv("TELR_DEPTH_MODE", mode)          # 0: shared-memory atomics per base, 1: boundary marks + scan
+    c = lib.Context(0)
+    rng = np.random.default_rng(3)
+    nl = 48
+    clen = rng.integers(600, 9000, nl).astype(np.int32)
+    ts = np.array([rng.integers(0, L - 150) for L in clen], np.int32)
+    te = np.array([min(L, s + rng.integers(20, 4000)) for L, s in zip(clen, ts)], np.int32)
+    ts[0] = 300; ts[1] = 299; te[2] = ts[2] + 60; ts[3] = -1
+    bl, bs, bn = [], [], []
+    for l in range(nl):
+        for s in range(2):
+            for _ in range(rng.integers(0, 120) if l != 5 else 0):
+                st = rng.integers(0, clen[l]); ln = rng.integers(1, 3000)
+                bl.append(2 * l + s); bs.append(st); bn.append(min(ln, clen[l] - st))
+    depth, cov, af = c.depth_af(clen, ts, te, np.array(bl), np.array(bs), np.array(bn))
+    off = 0
+    for l in range(nl):
+        L = int(clen[l]); d = [np.zeros(L, np.int32), np.zeros(L, np.int32)]
+        for q, st, ln in zip(bl, bs, bn):
+            if q >> 1 == l:
+                d[q & 1][st:st + ln] += 1
+        assert (depth[off:off + L] == d[0]).all() and (depth[off + L:off + 2 * L] == d[1]).all()
+        off += 2 * L
+        if ts[l] < 0:
+            assert (cov[l] == -2).all() and np.isnan(af[l])
+            continue
+        c8 = np.zeros(8, np.int32); a = C.c_double()
+        orc.lib().orc_cov_af(d[0].ctypes.data, d[1].ctypes.data, L, int(ts[l]), int(te[l]), 100, 200, 50, 50, c8.ctypes.data, C.byref(a))
+        assert (c8 == cov[l]).all(), (l, c8, cov[l])
+        assert (np.isnan(a.value) and np.isnan(af[l])) or a.value == af[l]
+    c.close()
+
+
+def _mut(rng, s, rate):
+    out = []
+    for ch in s:
+        r = rng.random()
+        if r < rate / 3:
+            continue
+        if r < 2 * rate / 3:
+            out.append(ch); out.append(rng.integers(0, 4)); continue
+        out.append((ch + 1 + rng.integers(0, 3)) % 4 if r < rate else ch)
+    return np.array(out, np.uint8)
+
+
+@pytest.mark.parametrize("preset", [0, 2])
+def test_dp_stage_matches_oracle(ctx, preset):
+    rng = np.random.default_rng(21 + preset)
+    o = orc.opt(preset)
+    tasks, qs, ts_ = [], [], []
+    qo = to = 0
+    spec = [(50, 0x08, 30001, 400, -1, .1), (300, 0x08, 30001, 400, -1, .12), (1000, 0x08, 30001, 400, -1, .12), (300, 0, 30001, 400, -1, .12),
+            (700, 0x40, 751, 400, -1, .12), (700, 0xC2, 751, 400, -1, .12), (2500, 0x40, 751, 400, -1, .15), (2500, 0xC2, 751, 200, -1, .15),
+            (33, 0x40, 751, 400, -1, .5), (1, 0x08, 30001, 400, -1, 0.), (400, 0x40, 751, 400, -1, .9), (3000, 0x40, 100, 400, -1, .1),
+            (1500, 0x08, 1200, 400, -1, .1), (1300, 0x40, 40, 400, 10, .05)] * 3
+    for (ql, flag, w, zd, eb, rate) in spec:
+        t = rng.integers(0, 4, max(1, int(ql * rng.uniform(.7, 1.4)))).astype(np.uint8)
+        q = _mut(rng, t, rate)[:ql] if rate < .8 else rng.integers(0, 4, ql).astype(np.uint8)
+        if len(q) == 0:
+            q = np.zeros(1, np.uint8)
+        if ql == 300 and flag == 0:
+            t = np.concatenate([t[:100], rng.integers(0, 4, 2500).astype(np.uint8), t[100:]])
+        if rng.random() < .3 and len(q) > 40:
+            q[rng.integers(0, len(q))] = 4
+        tasks.append((qo, to, len(q), len(t), w, zd, eb, flag)); qs.append(q); ts_.append(t); qo += len(q); to += len(t)
+    out, cig = ctx.dp(preset, np.array(tasks, lib.DPTASK_DTYPE), np.concatenate(qs), np.concatenate(ts_))
+    for i, (q, t) in enumerate(zip(qs, ts_)):
+        w, zd, eb, flag = tasks[i][4:]
+        ref = orc.ksw_extd2(q, t, o, w, zd, eb, flag); g = out[i]
+        names = ["zdropped", "reach_end", "cells"]
+        if not flag & 0x08:
+            names += ["max", "max_q", "max_t"]
+        if not (flag & 0x40) and not ref["zdropped"]:
+            names += ["score"]
+        if flag & 0x40 and not ref["zdropped"]:
+            names += ["mqe", "mqe_t"]
+        assert all(int(ref[n]) == int(g[n]) for n in names), (i, {n: (int(ref[n]), int(g[n])) for n in names})
+        gc = cig[g["cigar_off"]: g["cigar_off"] + g["n_cigar"]]
+        assert len(gc) == len(ref["cigar"]) and (gc == ref["cigar"]).all(), i
+
+
+@pytest.mark.parametrize("cfg,n,kw", [("ont_3k_50x", 10, {}), ("clr_3k_40x", 6, {}), ("hifi_3k_40x", 6, {}),
+                                      ("poly_10k_200x", 2, dict(depth=60)), ("ont_3k_50x", 4, dict(p_n=0.002))])
+def test_full_pipeline_matches_oracle(ctx, cfg, n, kw):
+    b = synth.generate(cfg, 0, n, **kw)
+    r = ctx.run(b, want_depth=True, want_aln=True)
+    ro = orc.af_run(b, threads=0)
+    util.assert_same_results(r, ro)
+    assert r.c.dp_cells == ro.c.dp_cells and r.c.n_anchors == ro.c.n_anchors
+
+
+def test_config1_repo_fixture(ctx):
+    """BASELINE.json configs[0]: the locus built from the reference's test FASTAs (map-pb)."""
+    b = util.load_config1()
+    gold = json.load(open(os.path.join(util.ROOT, "tests", "golden", "config1_oracle.json")))
+    r = ctx.run(b, want_depth=True, want_aln=True)
+    assert r.cov2x.tolist() == gold["cov2x"] and int(r.c.dp_cells) == gold["dp_cells"] and int(r.c.n_aln) == gold["n_aln"]
+    assert hashlib.sha1(r.depth.tobytes()).hexdigest() == gold["depth_sha1"]
+    assert [[int(a[f]) for f in ("read", "strand", "rs", "re", "qs", "qe", "rev", "flag", "dp_max", "n_cigar")] for a in r.alns] == gold["aln"]
+    assert [None if np.isnan(v) else float(v) for v in r.af] == gold["af"]
+
+
+def test_edge_cases_empty_and_ragged(ctx):
+    b = synth.generate("ont_3k_50x", 0, 5, depth=8)
+    # locus 1 loses its reads, locus 2 its contig, locus 3 its annotation
+    keep = np.ones(b.n_reads, bool); keep[b.locus_read_begin[1]:b.locus_read_begin[2]] = False
+    lrb = np.concatenate([[0], np.cumsum([int(keep[b.locus_read_begin[l]:b.locus_read_begin[l + 1]].sum()) for l in range(5)])]).astype(np.int32)
+    from telr_b200.batch import Batch
+    b2 = Batch(b.preset, b.seq2, b.nmask, b.read_off[keep].copy(), b.read_len[keep].copy(), b.read_hash[keep].copy(), lrb, b.contig_off.copy(),
+               b.contig_len.copy(), b.te_start.copy(), b.te_end.copy())
+    b2.contig_len[2] = 0
+    b2.te_start[3] = -1
+    r = ctx.run(b2, want_depth=True, want_aln=True)
+    ro = orc.af_run(b2, threads=0)
+    util.assert_same_results(r, ro)
+    assert (r.cov2x[2] == -2).all() and (r.cov2x[3] == -2).all() and r.cov2x[1, 0] == 0
+    empty = synth.generate("ont_3k_50x", 0, 1, depth=8).subset([])
+    r0 = ctx.run(empty)
+    assert r0.cov2x.shape == (0, 8)
+
+
+def test_chunking_and_rerun_are_identical(built, monkeypatch):
+    b = synth.generate("ont_3k_50x", 0, 12, depth=12)
+    c1 = lib.Context(0)
+    r1 = c1.run(b, want_depth=True, want_aln=True)
+    r1b = c1.run(b, want_depth=True, want_aln=True)            # same ctx again: workspace reuse
+    monkeypatch.setenv("TELR_CHUNK_MBASES", "1")               # force several chunks of loci
+    c2 = lib.Context(0)
+    r2 = c2.run(b, want_depth=True, want_aln=True)
+    for r in (r1b, r2):
+        util.assert_same_results(r, r1)
+        assert r.c.dp_cells == r1.c.dp_cells
+    c1.close(); c2.close()
+
+
+def test_get_af_dropin(built, tmp_path):
+    """The stage API on files, GPU backend, against the same host code fed by the oracle."""
+    b = synth.generate("ont_3k_50x", 0, 4, depth=10)
+    kw = _make_stage3_artifacts(tmp_path, b, drop_contig=1)
+    te_freq = stage4.get_af(**kw)
+    ref = orc.af_run(b.subset([0, 2, 3]), threads=0, want_depth=False, want_aln=False)
+    names = [f"chr1_{10000 * (l + 1)}_{10000 * (l + 1) + 1}" for l in range(4)]
+    assert set(te_freq) == {names[0], names[2], names[3]}
+    for j, l in enumerate((0, 2, 3)):
+        d = te_freq[names[l]]
+        got = [d[k] for k in ("te_5p_cov", "te_3p_cov", "flank_5p_cov", "flank_3p_cov", "te_5p_cov_rc", "te_3p_cov_rc", "flank_5p_cov_rc", "flank_3p_cov_rc")]
+        assert got == [None if c == -1 else c / 2 for c in ref.cov2x[j].tolist()]
+        g = ref.af[j]
+        assert d["freq"] == (None if np.isnan(g) else round(1 if g > 1 else g, 3))
+
+
+def test_full_size_properties(ctx):
+    """Properties at a larger size than the oracle is run on: depth equals the M-block sum, rerun determinism."""
+    b = synth.generate("ont_3k_50x", 100, 60)
+    r = ctx.run(b, want_depth=True, want_aln=True)
+    al = r.alns
+    off = np.concatenate([[0], np.cumsum(2 * b.contig_len.astype(np.int64))])
+    locus_of_read = np.repeat(np.arange(b.n_loci), np.diff(b.locus_read_begin))
+    marks = np.zeros(len(r.depth) + 1, np.int64)
+    for i in np.nonzero((al["flag"] & 0x100) == 0)[0]:
+        a = al[i]; c = r.cigar_of(i); op, ln = c & 0xf, (c >> 4).astype(np.int64)
+        l = locus_of_read[a["read"]]; base = off[l] + a["strand"] * b.contig_len[l]
+        ref_adv = np.where((op == 0) | (op == 2), ln, 0)
+        starts = base + a["rs"] + np.concatenate([[0], np.cumsum(ref_adv)[:-1]])
+        m = op == 0
+        np.add.at(marks, starts[m], 1); np.add.at(marks, starts[m] + ln[m], -1)
+    assert (np.cumsum(marks)[:-1] == r.depth).all()
+    assert int(r.c.n_aln_blocks) == int(sum(((r.cigar_of(i) & 0xf) == 0).sum() for i in np.nonzero((al["flag"] & 0x100) == 0)[0]))
+    r2 = ctx.run(b, want_depth=True)
+    assert (r2.depth == r.depth).all() and (r2.cov2x == r.cov2x).all()
+    ok = ~np.isnan(r.af)
+    assert ok.mean() > 0.8 and np.abs(np.minimum(r.af[ok], 1) - b.meta["truth_af"][ok]).mean() < 0.12      # estimates track the simulated truth

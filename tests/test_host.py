@@ -1,0 +1,188 @@
+"""Host-side pieces without a GPU: C-ABI library loads and exports every symbol of include/telr_af.h, fails
+loudly without a device, BAM I/O, batch packing, the get_af drop-in's file handling, and the N>1 sharding path
+(world_size-2 gloo)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from telr_b200 import bamio, lib, stage4, synth
+from telr_b200.batch import Batch, PRESETS, name_hash, pack_sequences
+from tests import orc, util
+
+
+def test_cabi_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(util.ROOT, "include", "telr_af.h")).read()
+    declared = set(re.findall(r"\b(telr_[a-z_0-9]+)\s*\(", hdr))
+    L = C.CDLL(lib.SO_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert declared == set(lib.EXPORTS)
+    assert lib.lib().telr_af_version() >= 100
+    assert lib.lib().telr_af_strerror(-4).decode().startswith("no sm_100")
+
+
+def test_no_device_fails_loudly(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(lib.TelrError) as ei:
+        lib.Context(0)
+    assert ei.value.code == -4          # TELR_ENODEV: there is no CPU fallback
+
+
+def test_pack_and_hash_helpers(built):
+    L = lib.lib()
+    seqs = [b"ACGTNNacgtRYK" * 7, b"T" * 64, b"G"]
+    s2a, nma, offa, lena = pack_sequences(seqs)             # numpy path
+    s2b, nmb, offb, lenb = pack_sequences(seqs, L)          # C helper
+    assert (s2a == s2b).all() and (nma == nmb).all() and (offa == offb).all()
+    b = Batch(0, s2a, nma, offa[1:], lena[1:], np.zeros(2, np.uint32), np.array([0, 2], np.int32), offa[:1], lena[:1],
+              np.array([1], np.int32), np.array([2], np.int32))
+    u = b.unpack(0, len(seqs[0]))
+    assert u[:6].tolist() == [0, 1, 2, 3, 4, 4] and u[10] == 4
+    for nm in ("L000001_R0003", "m150806_161050_42131/92222/1146_17405", "x"):
+        assert L.telr_name_hash(nm.encode()) == name_hash(nm) == orc.lib().orc_name_hash(nm.encode())
+
+
+def test_synth_is_deterministic_and_shardable(built):
+    a = synth.generate("ont_3k_50x", 0, 6, depth=8)
+    b1 = synth.generate("ont_3k_50x", 0, 3, depth=8)
+    b2 = synth.generate("ont_3k_50x", 3, 3, depth=8)
+    assert (a.contig_len == np.concatenate([b1.contig_len, b2.contig_len])).all()
+    assert (a.read_hash == np.concatenate([b1.read_hash, b2.read_hash])).all()
+    sub = a.subset([3, 4, 5])
+    assert (sub.seq2 == b2.seq2).all() and (sub.read_len == b2.read_len).all() and (sub.te_start == b2.te_start).all()
+
+
+def test_bam_roundtrip_and_fetch(tmp_path):
+    recs = [dict(name="r1", ref_id=0, pos=100, cigar=[(0, 50), (2, 10), (0, 40)], seq_len=90),
+            dict(name="r2", ref_id=0, pos=900, cigar=[(4, 5), (0, 300)], seq_len=305, flag=256),
+            dict(name="r3", ref_id=0, pos=1200, cigar=[(0, 10)], seq_len=10, flag=2048),
+            dict(name="r4", ref_id=1, pos=0, cigar=[(0, 10)], seq_len=10)]
+    p = str(tmp_path / "t.bam")
+    bamio.write_bam(p, [("chrA", 5000), ("chrB", 100)], recs)
+    idx = bamio.BamIndex(p)
+    assert idx.refs == [("chrA", 5000), ("chrB", 100)]
+    assert list(idx.fetch("chrA", 0, 100)) == []                 # r1 starts at 100: half-open window
+    assert list(idx.fetch("chrA", 199, 200)) == ["r1"]           # reference span 100 (50M10D40M) -> [100, 200)
+    assert list(idx.fetch("chrA", 200, 901)) == ["r2"]           # secondary records count too
+    assert sorted(idx.fetch("chrA", 0, 5000)) == ["r1", "r2", "r3"]
+    with pytest.raises(ValueError):
+        list(idx.fetch("chrZ", 0, 1))
+
+
+def _make_stage3_artifacts(tmp_path, b: Batch, drop_contig=None, drop_annot=None):
+    """Write the files get_af() consumes (vcf_parsed, BAM, raw reads, contigs, BED) for a synthetic batch."""
+    out = tmp_path / "out"; cdir = tmp_path / "contigs"; out.mkdir(); cdir.mkdir()
+    acgt = np.array(list(b"ACGTN"), np.uint8)
+    rows, bed, recs, fa = [], [], [], []
+    for l in range(b.n_loci):
+        start = 10000 * (l + 1)
+        name = f"chr1_{start}_{start + 1}"
+        rows.append("\t".join(["chr1", str(start), str(start + 1), "100", "10", "0.5", f"id{l}", "ACGT", "rA,rB", "PASS", "0/1", "5", "5", "0.9"]))
+        if l != drop_contig:
+            (cdir / f"{name}.cns.ctg1.fa").write_bytes(b">ctg1\n" + acgt[b.unpack(int(b.contig_off[l]), int(b.contig_len[l]))].tobytes() + b"\n")
+        if l != drop_annot:
+            bed.append(f"{name}\t1\t2\tdummy\t.\t+")            # overwritten by the next row: last row per contig wins
+            bed.append(f"{name}\t{b.te_start[l]}\t{b.te_end[l]}\tjockey\t.\t+")
+        for r in range(b.locus_read_begin[l], b.locus_read_begin[l + 1]):
+            rn = f"L{l:06d}_R{r - b.locus_read_begin[l]:04d}"
+            recs.append(dict(name=rn, ref_id=0, pos=start - 500 + (r % 7), cigar=[(0, 600)], seq_len=0))
+            fa.append(b">" + rn.encode() + b" extra words\n" + acgt[b.unpack(int(b.read_off[r]), int(b.read_len[r]))].tobytes() + b"\n")
+    recs.append(dict(name="far_away", ref_id=0, pos=5, cigar=[(0, 50)], seq_len=0))
+    fa.append(b">far_away\nACGT\n")
+    recs.sort(key=lambda r: r["pos"])
+    bamio.write_bam(str(tmp_path / "reads.bam"), [("chr1", 10 ** 6)], recs)
+    (tmp_path / "raw.fa").write_bytes(b"".join(fa))
+    (tmp_path / "vcf.tsv").write_text("\n".join(rows) + "\n")
+    (tmp_path / "te.bed").write_text("\n".join(bed) + "\n")
+    return dict(out=str(out), sample_name="s", bam=str(tmp_path / "reads.bam"), raw_reads=str(tmp_path / "raw.fa"),
+                contig_te_annotation=str(tmp_path / "te.bed"), contig_dir=str(cdir), vcf_parsed=str(tmp_path / "vcf.tsv"),
+                flank_intervel_size=100, flank_offset=200, te_interval_size=50, te_offset=50, presets="ont", thread=1)
+
+
+def test_get_af_host_logic_with_oracle_backend(built, tmp_path, monkeypatch):
+    """The drop-in's file handling and dict/.freq construction, with the device call replaced by the oracle
+    (the product path itself is exercised on the GPU in test_gpu.py::test_get_af_dropin)."""
+    b = synth.generate("ont_3k_50x", 0, 4, depth=10)
+    kw = _make_stage3_artifacts(tmp_path, b, drop_contig=1, drop_annot=2)
+    seen = {}
+
+    def fake_run_batch(batch, devices=None, **k):
+        seen["batch"] = batch
+        r = orc.af_run(batch, threads=0, want_depth=False, want_aln=False)
+        return r.cov2x, r.af, None
+    monkeypatch.setattr(stage4, "run_batch", fake_run_batch)
+    te_freq = stage4.get_af(**kw)
+    names = [f"chr1_{10000 * (l + 1)}_{10000 * (l + 1) + 1}" for l in range(4)]
+    assert set(te_freq) == {names[0], names[3]}                  # locus 1 has no contig, locus 2 no annotation
+    gb = seen["batch"]
+    assert gb.n_loci == 3 and gb.preset == PRESETS["map-ont"]
+    keep = [0, 2, 3]
+    ref = orc.af_run(b.subset(keep), threads=0, want_depth=False, want_aln=False)
+    # reads were re-gathered through BAM + FASTA in sorted-name order = generator order: identical batch content
+    assert (gb.read_len == b.subset(keep).read_len).all() and (gb.read_hash == b.subset(keep).read_hash).all()
+    for j, l in ((0, 0), (2, 3)):
+        d = te_freq[names[l]]
+        assert set(d) == {"te_5p_cov", "te_3p_cov", "flank_5p_cov", "flank_3p_cov", "te_5p_cov_rc", "te_3p_cov_rc", "flank_5p_cov_rc", "flank_3p_cov_rc", "freq"}
+        for k, key in enumerate(["te_5p_cov", "te_3p_cov", "flank_5p_cov", "flank_3p_cov", "te_5p_cov_rc", "te_3p_cov_rc", "flank_5p_cov_rc", "flank_3p_cov_rc"]):
+            c2 = int(ref.cov2x[j, k])
+            assert d[key] == (None if c2 == -1 else c2 / 2)
+        g = ref.af[j]
+        assert d["freq"] == (None if np.isnan(g) else round(1 if g > 1 else g, 3))
+    # side files
+    new = open(kw["vcf_parsed"] + ".new").read().splitlines()
+    assert len(new) == 4 and all(len(x.split("\t")) == 15 for x in new)
+    assert [int(x.split("\t")[14]) for x in new] == np.diff(b.locus_read_begin).tolist()
+    freq = open(kw["vcf_parsed"] + ".freq").read().splitlines()
+    rc = open(kw["vcf_parsed"] + ".revcomp.freq").read().splitlines()
+    assert len(freq) == 2 and len(rc) == 2 and all(len(x.split("\t")) == 18 for x in freq + rc)
+    assert os.path.isfile(os.path.join(kw["out"], "telr_reads", names[1] + ".reads.fa"))     # written even without a contig
+    rcfa = open(os.path.join(kw["contig_dir"], names[0] + ".cns.ctg1.revcomp.fa")).read().splitlines()
+    fw = open(os.path.join(kw["contig_dir"], names[0] + ".cns.ctg1.fa")).read().splitlines()
+    assert rcfa[0] == ">ctg1" and rcfa[1] == fw[1][::-1].translate(str.maketrans("ACGT", "TGCA"))
+
+
+def test_partition_is_balanced_and_complete(built):
+    b = synth.generate("ont_3k_50x", 0, 16, depth=6)
+    for n in (1, 2, 3, 8):
+        sh = stage4.partition_loci(b, n)
+        assert sorted(sum(sh, [])) == list(range(16))
+        cost = [sum(int(b.read_len[b.locus_read_begin[l]:b.locus_read_begin[l + 1]].sum()) for l in s) for s in sh]
+        assert max(cost) <= 1.6 * (sum(cost) / n) + max(int(b.read_len.sum()) // 16, 1)
+
+
+def _shard_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    b = synth.generate("ont_3k_50x", 0, 6, depth=6)
+    mine = stage4.partition_loci(b, world)[rank]
+    r = orc.af_run(b.subset(mine), threads=1, want_depth=False, want_aln=False)      # stand-in for the device call
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (mine, r.cov2x.tolist()))
+    if rank == 0:
+        cov = np.zeros((b.n_loci, 8), np.int32)
+        for loci, c in gathered:
+            cov[loci] = np.array(c, np.int32)
+        q.put(cov.tolist())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_gloo(built):
+    """N>1 path: loci sharded by rank, independent work, host-side gather in locus order (no data-path collective)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    ps = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    cov = np.array(q.get(timeout=300), np.int32)
+    [p.join(60) for p in ps]
+    b = synth.generate("ont_3k_50x", 0, 6, depth=6)
+    ref = orc.af_run(b, threads=0, want_depth=False, want_aln=False)
+    assert (cov == ref.cov2x).all()
