@@ -124,6 +124,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--loci", type=int, default=int(os.environ.get("TELR_BENCH_LOCI", "0")), help="loci per GPU (0 = the configuration's full size)")
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("TELR_STREAMS", "1")), help="concurrent contexts (streams) per GPU, each on its own slice of loci")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -145,32 +146,39 @@ def main():
     per_gpu = args.loci or cfg_loci
     # weak scaling: every rank owns its own shard of loci [rank*per_gpu, (rank+1)*per_gpu) (locus ids are global)
     batch = synth.generate(WORKLOAD, rank * per_gpu, per_gpu, total_loci=max(cfg_loci, world * per_gpu))
-    ctx = lib.Context(local)
-    stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=torch.device("cuda", local))
-
-    # ---- device-resident copy of the batch (torch tensors are only device memory here) ----
     dev = torch.device("cuda", local)
+    # K contexts (= K streams with their own workspaces) share the GPU; each owns a contiguous slice of this rank's loci so
+    # that one slice's latency-bound phases and stragglers overlap with another slice's DP
+    K = max(1, min(args.streams, batch.n_loci))
+    cuts = [batch.n_loci * i // K for i in range(K + 1)]
     names = ["seq2", "nmask", "read_off", "read_len", "read_hash", "locus_read_begin", "contig_off", "contig_len", "te_start", "te_end"]
-    host = {n: getattr(batch, n) for n in names}
+
     def to_t(a):
-        if a.dtype == np.uint32:
-            return torch.from_numpy(a.view(np.int32))
-        return torch.from_numpy(a)
-    pinned = {n: to_t(host[n]).pin_memory() for n in names}
-    dten = {n: pinned[n].to(dev, non_blocking=False) for n in names}
-    cov_d = torch.zeros((batch.n_loci, 8), dtype=torch.int32, device=dev)
-    af_d = torch.zeros(batch.n_loci, dtype=torch.float64, device=dev)
-    cb = CBatch(batch.preset, batch.flank_len, batch.flank_off, batch.te_len, batch.te_off, batch.n_loci, batch.n_reads, batch.n_bases,
-                *[dten[n].data_ptr() for n in names])
-    cres = CResult()
-    cres.cov2x, cres.af = cov_d.data_ptr(), af_d.data_ptr()
-    # host-buffer variant uses the pinned copies
-    hb = CBatch(batch.preset, batch.flank_len, batch.flank_off, batch.te_len, batch.te_off, batch.n_loci, batch.n_reads, batch.n_bases,
-                *[pinned[n].data_ptr() for n in names])
-    cov_h = torch.zeros((batch.n_loci, 8), dtype=torch.int32).pin_memory()
-    af_h = torch.zeros(batch.n_loci, dtype=torch.float64).pin_memory()
-    hres = CResult()
-    hres.cov2x, hres.af = cov_h.data_ptr(), af_h.data_ptr()
+        return torch.from_numpy(a.view(np.int32)) if a.dtype == np.uint32 else torch.from_numpy(a)
+
+    class Slice:
+        pass
+    slices = []
+    for i in range(K):
+        sl = Slice()
+        sl.b = batch.subset(range(cuts[i], cuts[i + 1])) if K > 1 else batch
+        sl.ctx = lib.Context(local)
+        sl.pinned = {n: to_t(getattr(sl.b, n)).pin_memory() for n in names}
+        sl.dten = {n: sl.pinned[n].to(dev) for n in names}
+        sl.cov_d = torch.zeros((sl.b.n_loci, 8), dtype=torch.int32, device=dev)
+        sl.af_d = torch.zeros(sl.b.n_loci, dtype=torch.float64, device=dev)
+        hd = (sl.b.preset, sl.b.flank_len, sl.b.flank_off, sl.b.te_len, sl.b.te_off, sl.b.n_loci, sl.b.n_reads, sl.b.n_bases)
+        sl.cb = CBatch(*hd, *[sl.dten[n].data_ptr() for n in names])
+        sl.cres = CResult()
+        sl.cres.cov2x, sl.cres.af = sl.cov_d.data_ptr(), sl.af_d.data_ptr()
+        sl.hb = CBatch(*hd, *[sl.pinned[n].data_ptr() for n in names])
+        sl.cov_h = torch.zeros((sl.b.n_loci, 8), dtype=torch.int32).pin_memory()
+        sl.af_h = torch.zeros(sl.b.n_loci, dtype=torch.float64).pin_memory()
+        sl.hres = CResult()
+        sl.hres.cov2x, sl.hres.af = sl.cov_h.data_ptr(), sl.af_h.data_ptr()
+        slices.append(sl)
+    ctx = slices[0].ctx
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
 
     def barrier():
         if world > 1:
@@ -184,6 +192,7 @@ def main():
         e0.record(stream)
         for _ in range(steps):
             fn()
+        torch.cuda.synchronize()
         e1.record(stream)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
@@ -197,25 +206,48 @@ def main():
     stage_ms = {}
     cells = [0]
 
-    def step_dev():
-        ctx.run_device(cb, cres)
-        for i in range(8):
-            stage_ms[i] = stage_ms.get(i, 0.0) + float(cres.ms_stage[i])
-        cells[0] += int(cres.dp_cells)
+    def fan_out(fn):
+        if K == 1:
+            return fn(slices[0])
+        errs = []
 
-    def step_host():
-        rc = lib.lib().telr_af_run(ctx._h, C.byref(hb), C.byref(hres))
+        def run(sl):
+            try:
+                fn(sl)
+            except Exception as ex:       # noqa: BLE001
+                errs.append(ex)
+        th = [threading.Thread(target=run, args=(sl,)) for sl in slices]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        if errs:
+            raise errs[0]
+
+    def one_dev(sl):
+        sl.ctx.run_device(sl.cb, sl.cres)
+
+    def step_dev():
+        fan_out(one_dev)
+        for sl in slices:
+            for i in range(8):
+                stage_ms[i] = stage_ms.get(i, 0.0) + float(sl.cres.ms_stage[i])
+            cells[0] += int(sl.cres.dp_cells)
+
+    def one_host(sl):
+        rc = lib.lib().telr_af_run(sl.ctx._h, C.byref(sl.hb), C.byref(sl.hres))
         if rc != 0:
             raise lib.TelrError(rc, "telr_af_run")
+
+    def step_host():
+        fan_out(one_host)
 
     for _ in range(max(args.warmup, 3)):
         step_dev()
     stage_ms.clear(); cells[0] = 0
     sampler = ClockSampler(local)
     sampler.start()
-    l0 = ctx.launches
+    l0 = sum(sl.ctx.launches for sl in slices)
     dev_s, wall_s = timed(step_dev, args.steps)
-    launches = ctx.launches - l0
+    launches = sum(sl.ctx.launches for sl in slices) - l0
     clocks = sampler.finish()
     step_host()
     e2e_dev_s, e2e_wall = timed(step_host, args.steps)
@@ -225,7 +257,7 @@ def main():
     e2e = total_loci * args.steps / e2e_wall
     # roofline of the dominant kernel (k_align): GCUPS against the integer-ALU peak at the observed SM clock
     hbm_gbs, sm_max_mhz, peak_kind = measured_peaks()
-    align_s = stage_ms.get(3, 0.0) / 1e3
+    align_s = stage_ms.get(3, 0.0) / 1e3 / K        # K contexts run concurrently: per-context kernel time overlaps
     gcups = cells[0] / align_s / 1e9 if align_s > 0 else 0.0
     f_mhz = clocks["sm_mhz"] or sm_max_mhz
     nsm = torch.cuda.get_device_properties(local).multi_processor_count
@@ -244,7 +276,7 @@ def main():
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int8/int32 (integer DP), fp32 chain penalty, fp64 AF", "data": "synthetic",
             "config": {"workload": WORKLOAD, "loci_per_gpu": per_gpu, "preset": "map-ont", "reads": int(batch.n_reads), "read_bases": int(batch.read_len.astype(np.int64).sum()),
-                       "l2": "inputs larger than L2 (packed batch %.0f MB per GPU)" % (h2d / 1e6), "sharding": "by locus, no collective"},
+                       "l2": "inputs larger than L2 (packed batch %.0f MB per GPU)" % (h2d / 1e6), "sharding": "by locus, no collective", "streams_per_gpu": K},
             "gcups": gcups, "dp_cells_per_step": cells[0] // max(args.steps, 1),
             "stage_ms_per_step": {k: stage_ms.get(i, 0.0) / args.steps for i, k in enumerate(["sketch", "seed_chain", "plan", "align_dp", "", "", "depth_af"]) if k},
             "roofline": {"kernel": "k_align (base-level DP)", "bound": "int_alu", "achieved": gcups, "peak": peak_gcups, "unit": "GCUPS",
@@ -255,7 +287,8 @@ def main():
             "gpu_launches": launches, "clocks": clocks, "wall_ms_per_step": wall_s / args.steps * 1e3,
         }
         print(json.dumps(line), flush=True)
-    ctx.close()
+    for sl in slices:
+        sl.ctx.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -12,11 +12,13 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "mm_align.cuh"
+#include "k_fill.cuh"
 
 namespace telr {
 
 constexpr int AL_THREADS = 128;
 constexpr int AL_WARPS = AL_THREADS / 32;
+constexpr int DPU = 4;                 // independent 32-cell chunks per lane per DP iteration
 constexpr int DP_SCOLS = 1024;         // columns of DP state kept in shared memory per warp (power of two)
 struct DpWarpSmem { int8_t st[6][DP_SCOLS]; int32_t H[DP_SCOLS]; };
 
@@ -26,35 +28,42 @@ struct DpScratch {
     int32_t *ll;                       // [6 * maxT] local-probe rows
     uint8_t *dir; int64_t dir_cap;
     uint32_t *ezcig; int32_t ezcap;
+    uint32_t *bnd;                     // fast fill path: pass-boundary values, 3 words per query row pair
     // shared-memory circular window of DP_SCOLS columns (used when the live band fits)
     int8_t *s_state; int32_t *s_H;
-    // shared pool of large traceback buffers for the rare task that does not fit `dir`
-    uint8_t *big; int64_t big_cap; int32_t n_big; int32_t *big_lock;
+};
+
+// ---- round-based alignment (BSP): plan (thread/problem) -> dp (warp/task) -> traceback (thread/task) ----
+struct AlWork {                 // per work item (a problem with at least one chain)
+    int32_t pidx, done, pending, has_task;
+    int64_t dir_off;            // this round's slice of the pool (direction bytes or local-probe rows / spilled DP state)
+    int64_t cig_off, ez_off;    // CIGAR arena and per-task CIGAR buffer (uint32 units) in AlignArgs::cigs
+    int32_t cig_cap, ez_cap;
 };
 
 struct AlignArgs {
     Opt o;
-    int32_t n_prob, read_base;       // read_base: global index of this chunk's first read
-    const uint32_t *seq2, *nmask;
-    const int64_t *read_off; const int32_t *read_len;
+    const Opt *d_opt;           // the same options in device global memory (AlnCtx::o outlives a kernel launch)
+    int32_t n_prob, read_base, n_work;
+    const int32_t *read_len;
     const int32_t *contig_len; const int64_t *ctg_boff; const uint8_t *ctg_bytes;
+    const uint8_t *read_bytes; const int64_t *rbyte_off;       // nt4 bytes of every read: forward then reverse complement
     const int32_t *prob_read, *prob_ls, *prob_nca;
     int32_t *prob_nregs;
     const int64_t *prob_aoff, *prob_roff;
     Anchor *anchors; Reg *regs;
-    // per-warp scratch
-    uint8_t *warp_scratch; size_t warp_scratch_stride;
-    int32_t max_qlen, max_tlen, max_na, cig_cap, reg_cap_max; int64_t dir_cap;
-    uint8_t *big; int64_t big_cap; int32_t n_big; int32_t *big_lock;
-    // outputs
-    int32_t *work_counter; const int32_t *work_list; int32_t n_work;
+    uint8_t *prob_scratch; const int64_t *prob_soff;           // chaining scratch, reused (HitScratch, long-gap list)
+    const int32_t *work_list;
+    AlWork *work; AlnCtx *actx; DpTask *tasks; DpRes *res;
+    uint32_t *cigs;
+    uint8_t *warp_scratch; size_t warp_scratch_stride; int32_t max_tlen, max_qlen, use_fast; int64_t dir_cap;    // per resident warp: spilled DP state + traceback bytes
+    uint8_t *big; int64_t big_cap; int32_t n_big; int32_t *big_lock;                          // shared large traceback buffers
+    unsigned long long *rc;      // [2] work queue head
     int32_t *err;
     unsigned long long *stat_cells, *stat_tasks;
-    // M-blocks for the depth kernel
     int2 *blocks; unsigned long long *n_blocks; int64_t blocks_cap;
     int64_t *prob_blk_off; int32_t *prob_blk_cnt;
-    // optional alignment records
-    int32_t *aln_out;   /* 14 ints per record */ unsigned long long *n_aln; int64_t aln_cap;
+    int32_t *aln_out; unsigned long long *n_aln; int64_t aln_cap;
     uint32_t *cig_out; unsigned long long *n_cig; int64_t cig_out_cap;
 };
 
@@ -97,24 +106,10 @@ __device__ void warp_extd2_impl(const Opt &o, const DpTask &T, DpRes &R, DpScrat
     int ncol = qlen < tlen ? qlen : tlen;
     if (ncol > w + 1) ncol = w + 1;
     uint8_t *p = S.dir;
-    int big_slot = -1;
     if ((int64_t)(qlen + tlen - 1) * ncol > S.dir_cap) {
-        if ((int64_t)(qlen + tlen - 1) * ncol > S.big_cap || S.n_big <= 0) {
-            if (lane == 0) { atomicOr(err, TELR_ERR_DIRCAP); R.zdropped = 1; }
-            __syncwarp();
-            return;
-        }
-        if (lane == 0) {        // take one of the shared large buffers (holders never wait on anything)
-            unsigned ns = 64;
-            for (int s = (blockIdx.x * AL_WARPS + (threadIdx.x >> 5)) % S.n_big;; s = (s + 1) % S.n_big) {
-                if (atomicCAS(&S.big_lock[s], 0, 1) == 0) { big_slot = s; break; }
-                __nanosleep(ns);
-                if (ns < 4096) ns <<= 1;
-            }
-            __threadfence();
-        }
-        big_slot = __shfl_sync(FULL, big_slot, 0);
-        p = S.big + (int64_t)big_slot * S.big_cap;
+        if (lane == 0) { atomicOr(err, TELR_ERR_DIRCAP); R.zdropped = 1; }
+        __syncwarp();
+        return;
     }
     const bool approx = flag & KSW_APPROX_MAX, right = flag & KSW_RIGHT;
     // column t lives at slot (t & CM): the whole target for the global variant, a circular window in shared memory otherwise
@@ -160,20 +155,31 @@ __device__ void warp_extd2_impl(const Opt &o, const DpTask &T, DpRes &R, DpScrat
         }
         __syncwarp();
         uint8_t *pr = p + (int64_t)r * ncol;
-        for (int c = (en - st) >> 5; c >= 0; --c) {
-            const int t = st + (c << 5) + lane;
-            const bool act = t <= en;
-            int ut = 0, yt = 0, y2t = 0, v1 = sv1, x1 = sx1, x21 = sx21, z = 0;
-            const int ts = t & CM, tp = (t - 1) & CM;
-            if (act) {
-                ut = u[ts], yt = y[ts], y2t = y2[ts];
-                if (t > st) v1 = v[tp], x1 = x[tp], x21 = x2[tp];
-                int qc = dp_base(T.q, T.qstep, T.qcomp, r - t), tc = dp_base(T.t, T.tstep, 0, t);
-                z = (qc > 3 || tc > 3) ? -o.sc_ambi : qc == tc ? o.a : -o.b;
+        // DPU chunks of 32 cells per lane per iteration (independent dependency chains); groups run from high t to
+        // low t and every group loads all its inputs before storing, so in-place updates never overtake a reader
+        const int nchunks = ((en - st) >> 5) + 1;
+        for (int cb = ((nchunks - 1) / DPU) * DPU; cb >= 0; cb -= DPU) {
+            int ut[DPU], yt[DPU], y2t[DPU], v1[DPU], x1[DPU], x21[DPU], zz[DPU], tt[DPU];
+#pragma unroll
+            for (int k = 0; k < DPU; ++k) {
+                const int t = st + ((cb + k) << 5) + lane;
+                tt[k] = (cb + k < nchunks && t <= en) ? t : -1;
+                ut[k] = yt[k] = y2t[k] = zz[k] = 0; v1[k] = sv1, x1[k] = sx1, x21[k] = sx21;
+                if (tt[k] >= 0) {
+                    const int ts = t & CM, tp = (t - 1) & CM;
+                    ut[k] = u[ts], yt[k] = y[ts], y2t[k] = y2[ts];
+                    if (t > st) v1[k] = v[tp], x1[k] = x[tp], x21[k] = x2[tp];
+                    int qc = dp_base(T.q, T.qstep, T.qcomp, r - t), tc = dp_base(T.t, T.tstep, 0, t);
+                    zz[k] = (qc > 3 || tc > 3) ? -o.sc_ambi : qc == tc ? o.a : -o.b;
+                }
             }
             __syncwarp();
-            if (act) {
-                int a = x1 + v1, b = yt + ut, a2 = x21 + v1, b2 = y2t + ut, d;
+#pragma unroll
+            for (int k = 0; k < DPU; ++k) {
+                if (tt[k] < 0) continue;
+                const int t = tt[k], ts = t & CM;
+                int z = zz[k];
+                int a = x1[k] + v1[k], b = yt[k] + ut[k], a2 = x21[k] + v1[k], b2 = y2t[k] + ut[k], d;
                 if (!right) {
                     d = a > z ? 1 : 0;  z = z > a ? z : a;
                     d = b > z ? 2 : d;  z = z > b ? z : b;
@@ -186,8 +192,8 @@ __device__ void warp_extd2_impl(const Opt &o, const DpTask &T, DpRes &R, DpScrat
                     d = z > b2 ? d : 4; z = z > b2 ? z : b2;
                 }
                 if (z > o.a) z = o.a;
-                u[ts] = (int8_t)(z - v1);
-                v[ts] = (int8_t)(z - ut);
+                u[ts] = (int8_t)(z - v1[k]);
+                v[ts] = (int8_t)(z - ut[k]);
                 int tmp = z - q;  a -= tmp, b -= tmp;
                 tmp = z - q2;     a2 -= tmp, b2 -= tmp;
                 if (!right) {
@@ -261,42 +267,60 @@ __device__ void warp_extd2_impl(const Opt &o, const DpTask &T, DpRes &R, DpScrat
         atomicAdd(cells_acc, cells);
         R.max = ez_max; R.max_t = ez_max_t; R.max_q = ez_max_q; R.mqe = ez_mqe; R.mqe_t = ez_mqe_t;
         R.mte = ez_mte; R.mte_q = ez_mte_q; R.score = ez_score; R.zdropped = zdropped;
-        // ---- traceback (ksw_backtrack) ----
-        int i0 = -1, j0 = -1;
-        if (!zdropped && !(flag & KSW_EXTZ_ONLY)) i0 = tlen - 1, j0 = qlen - 1;
-        else if (!zdropped && (flag & KSW_EXTZ_ONLY) && ez_mqe + T.end_bonus > ez_max) R.reach_end = 1, i0 = ez_mqe_t, j0 = qlen - 1;
-        else if (ez_max_t >= 0 && ez_max_q >= 0) i0 = ez_max_t, j0 = ez_max_q;
-        if (i0 >= 0 && j0 >= 0) {
-            EzPush ep; ep.c = S.ezcig; ep.n = 0; ep.cap = S.ezcap;
-            int i = i0, j = j0, state = 0;
-            while (i >= 0 && j >= 0) {
-                int r = i + j, force_state = -1;
-                int st = 0, en = tlen - 1;
-                if (st < r - qlen + 1) st = r - qlen + 1;
-                if (en > r) en = r;
-                if (st < (r - w + 1) >> 1) st = (r - w + 1) >> 1;
-                if (en > (r + w) >> 1) en = (r + w) >> 1;
-                if (i < st) force_state = 2;
-                if (i > en) force_state = 1;
-                uint32_t tmp = force_state < 0 ? p[(int64_t)r * ncol + (i - st)] : 0;
-                if (state == 0) state = tmp & 7;
-                else if (!(tmp >> (state + 2) & 1)) state = 0;
-                if (state == 0) state = tmp & 7;
-                if (force_state >= 0) state = force_state;
-                if (state == 0) ep.push(0, 1), --i, --j;
-                else if (state == 1 || state == 3) ep.push(2, 1), --i;
-                else ep.push(1, 1), --j;
-            }
-            if (i >= 0) ep.push(2, i + 1);
-            if (j >= 0) ep.push(1, j + 1);
-            if (ep.n > ep.cap) { atomicOr(err, TELR_ERR_CIGCAP); ep.n = 0; }
-            if (!(flag & KSW_REV_CIGAR))
-                for (int k = 0; k < ep.n >> 1; ++k) { uint32_t t = ep.c[k]; ep.c[k] = ep.c[ep.n - 1 - k]; ep.c[ep.n - 1 - k] = t; }
-            R.n_cigar = ep.n;
-        }
-        if (big_slot >= 0) { __threadfence(); atomicExch(&S.big_lock[big_slot], 0); }
     }
     __syncwarp();
+}
+
+// memory a forward pass needs for its direction bytes (row r of the anti-diagonal sweep at r * ncol)
+__host__ __device__ __forceinline__ int64_t dp_dir_bytes(int qlen, int tlen, int w_in)
+{
+    if (qlen <= 0 || tlen <= 0) return 0;
+    int w = w_in < 0 ? (tlen > qlen ? tlen : qlen) : w_in;
+    int ncol = qlen < tlen ? qlen : tlen;
+    if (ncol > w + 1) ncol = w + 1;
+    return (int64_t)(qlen + tlen - 1) * ncol;
+}
+
+// ksw_backtrack over the direction bytes written by warp_extd2; sequential, one thread
+__device__ void extd2_traceback(const DpTask &T, DpRes &R, const uint8_t *p, uint32_t *ezcig, int ezcap, int32_t *err)
+{
+    const int qlen = T.qlen, tlen = T.tlen, flag = T.flag;
+    R.n_cigar = 0; R.cigar = ezcig; R.reach_end = 0;
+    if (qlen <= 0 || tlen <= 0) return;
+    const int w = T.w < 0 ? (tlen > qlen ? tlen : qlen) : T.w;
+    int ncol = qlen < tlen ? qlen : tlen;
+    if (ncol > w + 1) ncol = w + 1;
+    int i0 = -1, j0 = -1;
+    if (!R.zdropped && !(flag & KSW_EXTZ_ONLY)) i0 = tlen - 1, j0 = qlen - 1;
+    else if (!R.zdropped && (flag & KSW_EXTZ_ONLY) && R.mqe + T.end_bonus > R.max) R.reach_end = 1, i0 = R.mqe_t, j0 = qlen - 1;
+    else if (R.max_t >= 0 && R.max_q >= 0) i0 = R.max_t, j0 = R.max_q;
+    if (i0 < 0 || j0 < 0) return;
+    EzPush ep; ep.c = ezcig; ep.n = 0; ep.cap = ezcap;
+    int i = i0, j = j0, state = 0;
+    while (i >= 0 && j >= 0) {
+        int r = i + j, force_state = -1;
+        int st = 0, en = tlen - 1;
+        if (st < r - qlen + 1) st = r - qlen + 1;
+        if (en > r) en = r;
+        if (st < (r - w + 1) >> 1) st = (r - w + 1) >> 1;
+        if (en > (r + w) >> 1) en = (r + w) >> 1;
+        if (i < st) force_state = 2;
+        if (i > en) force_state = 1;
+        uint32_t tmp = force_state < 0 ? p[(int64_t)r * ncol + (i - st)] : 0;
+        if (state == 0) state = tmp & 7;
+        else if (!(tmp >> (state + 2) & 1)) state = 0;
+        if (state == 0) state = tmp & 7;
+        if (force_state >= 0) state = force_state;
+        if (state == 0) ep.push(0, 1), --i, --j;
+        else if (state == 1 || state == 3) ep.push(2, 1), --i;
+        else ep.push(1, 1), --j;
+    }
+    if (i >= 0) ep.push(2, i + 1);
+    if (j >= 0) ep.push(1, j + 1);
+    if (ep.n > ep.cap) { atomicOr(err, TELR_ERR_CIGCAP); ep.n = 0; }
+    if (!(flag & KSW_REV_CIGAR))
+        for (int k = 0; k < ep.n >> 1; ++k) { uint32_t t = ep.c[k]; ep.c[k] = ep.c[ep.n - 1 - k]; ep.c[ep.n - 1 - k] = t; }
+    R.n_cigar = ep.n;
 }
 
 __device__ __forceinline__ void warp_extd2(const Opt &o, const DpTask &T, DpRes &R, DpScratch &S, unsigned long long *cells_acc, int32_t *err)
@@ -354,9 +378,59 @@ __device__ void warp_ll(const Opt &o, const DpTask &T, DpRes &R, DpScratch &S, u
     __syncwarp();
 }
 
+__global__ void k_unpack_reads(int n_reads, const uint32_t *seq2, const uint32_t *nmask, const int64_t *read_off, const int32_t *read_len,
+                               const int64_t *rbyte_off, uint8_t *out)
+{
+    for (int r = blockIdx.x; r < n_reads; r += gridDim.x) {
+        const int n = read_len[r];
+        const int64_t off = read_off[r];
+        uint8_t *fw = out + rbyte_off[r], *rc = fw + n;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            int64_t pp = off + i;
+            int c = (seq2[pp >> 4] >> (2 * (pp & 15))) & 3;
+            if ((nmask[pp >> 5] >> (pp & 31)) & 1) c = 4;
+            fw[i] = (uint8_t)c;
+            rc[n - 1 - i] = (uint8_t)(c < 4 ? 3 - c : 4);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_al_init(const __grid_constant__ AlignArgs A)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= A.n_work) return;
+    AlWork &W = A.work[w];
+    const int pidx = A.work_list[w];
+    const int read = A.prob_read[pidx], ls = A.prob_ls[pidx], l = ls >> 1, strand = ls & 1;
+    const int qlen = A.read_len[read], L = A.contig_len[l];
+    const int n_a = (int)(A.prob_aoff[pidx + 1] - A.prob_aoff[pidx]);
+    W.pidx = pidx; W.done = 0; W.pending = 0; W.has_task = 0; W.dir_off = 0;
+    AlnCtx &c = A.actx[w];
+    c.o = A.d_opt;
+    c.tseq = A.ctg_bytes + A.ctg_boff[l] + (strand ? L : 0); c.tlen = L;
+    c.qseq[0] = A.read_bytes + A.rbyte_off[read]; c.qseq[1] = c.qseq[0] + qlen; c.qlen = qlen;
+    c.a = A.anchors + A.prob_aoff[pidx]; c.n_a = A.prob_nca[pidx];
+    c.regs = A.regs + A.prob_roff[pidx]; c.n_regs = A.prob_nregs[pidx];
+    c.cap_regs = (int)(A.prob_roff[pidx + 1] - A.prob_roff[pidx]);
+    c.cig = A.cigs + W.cig_off; c.cig_top = 0; c.cig_cap = (uint32_t)W.cig_cap;
+    {   // the chaining scratch of this problem is free now: reuse its region-bookkeeping part and the candidate list
+        uint8_t *b = A.prob_scratch + A.prob_soff[pidx];
+        ChainScratch cs;
+        chain_scratch_carve(cs, b, (size_t)n_a + 1);
+        hit_scratch_carve(c.hs, b + chain_scratch_bytes((size_t)n_a + 1), (size_t)(2 * (n_a / 3) + 8));
+        c.K = cs.ord; c.capK = n_a;
+    }
+    c.err = 0; c.n_tasks = 0; c.defer_finish = 1;
+    c.phase = PH_START;
+    res_reset(A.res[w]);
+    A.res[w].cigar = A.cigs + W.ez_off;
+}
+
+// coroutine + DP + traceback for one problem per warp (persistent warps, dynamic queue, no global barriers).
+// The coroutine state lives in shared memory while the warp owns the problem and is written back for k_al_finish.
 struct AlWarpSmem { AlnCtx c; DpTask task; DpRes res; int more; };
 
-__global__ void __launch_bounds__(AL_THREADS) k_align(const __grid_constant__ AlignArgs A)
+__global__ void __launch_bounds__(AL_THREADS) k_al_fused(const __grid_constant__ AlignArgs A)
 {
     __shared__ AlWarpSmem WS[AL_WARPS];
     __shared__ DpWarpSmem DS[AL_WARPS];
@@ -364,120 +438,129 @@ __global__ void __launch_bounds__(AL_THREADS) k_align(const __grid_constant__ Al
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned FULL = 0xffffffffu;
     AlWarpSmem &W = WS[wid];
-    // carve the per-warp scratch
     uint8_t *base = A.warp_scratch + (size_t)(blockIdx.x * AL_WARPS + wid) * A.warp_scratch_stride;
-    const size_t maxQ = ((size_t)A.max_qlen + 64) & ~(size_t)15, maxT = ((size_t)A.max_tlen + 64) & ~(size_t)15;
-    uint8_t *qfw = base; base += maxQ;
-    uint8_t *qrc = base; base += maxQ;
+    const size_t maxT = ((size_t)A.max_tlen + 64) & ~(size_t)15;
     DpScratch S;
     S.u = (int8_t *)base; base += maxT; S.v = (int8_t *)base; base += maxT; S.x = (int8_t *)base; base += maxT;
     S.y = (int8_t *)base; base += maxT; S.x2 = (int8_t *)base; base += maxT; S.y2 = (int8_t *)base; base += maxT;
     S.H = (int32_t *)base; base += maxT * 4;
     S.ll = (int32_t *)base; base += maxT * 4 * 6;
-    S.ezcap = (int32_t)(maxQ + maxT); S.ezcig = (uint32_t *)base; base += (size_t)S.ezcap * 4;     // maxQ, maxT are multiples of 16
-    uint32_t *cig = (uint32_t *)base; base += ((size_t)A.cig_cap * 4 + 15) & ~(size_t)15;
-    int32_t *K = (int32_t *)base; base += (((size_t)A.max_na + 8) * 4 + 15) & ~(size_t)15;
-    uint8_t *hsb = base; base += hit_scratch_bytes((size_t)A.reg_cap_max + 1);
+    S.bnd = (uint32_t *)base; base += (((size_t)A.max_qlen + 64) & ~(size_t)15) * 6;
     base = (uint8_t *)(((uintptr_t)base + 255) & ~(uintptr_t)255);
-    S.dir = base; S.dir_cap = A.dir_cap;
-    S.big = A.big; S.big_cap = A.big_cap; S.n_big = A.n_big; S.big_lock = A.big_lock;
+    uint8_t *own_dir = base;
     S.s_state = &DS[wid].st[0][0]; S.s_H = DS[wid].H;
-
     for (;;) {
         int wi = 0;
-        if (lane == 0) wi = atomicAdd(A.work_counter, 1);
+        if (lane == 0) wi = (int)atomicAdd(&A.rc[2], 1ULL);
         wi = __shfl_sync(FULL, wi, 0);
         if (wi >= A.n_work) break;
-        const int pidx = A.work_list[wi];
-        const int read = A.prob_read[pidx], ls = A.prob_ls[pidx], l = ls >> 1, strand = ls & 1;
-        const int qlen = A.read_len[read], L = A.contig_len[l];
-        // unpack the read (forward + reverse complement)
-        {
-            const int64_t off = A.read_off[read];
-            for (int i = lane; i < qlen; i += 32) {
-                int64_t pp = off + i;
-                int c = (A.seq2[pp >> 4] >> (2 * (pp & 15))) & 3;
-                if ((A.nmask[pp >> 5] >> (pp & 31)) & 1) c = 4;
-                qfw[i] = (uint8_t)c;
-                qrc[qlen - 1 - i] = (uint8_t)(c < 4 ? 3 - c : 4);
-            }
+        {   // coroutine state: global -> shared
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(&A.actx[wi]);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(&W.c);
+            for (int i = lane; i < (int)(sizeof(AlnCtx) / 4); i += 32) dst[i] = src[i];
         }
-        if (lane == 0) {
-            AlnCtx &c = W.c;
-            c.o = &A.o;
-            c.tseq = A.ctg_bytes + A.ctg_boff[l] + (strand ? L : 0); c.tlen = L;
-            c.qseq[0] = qfw; c.qseq[1] = qrc; c.qlen = qlen;
-            c.a = A.anchors + A.prob_aoff[pidx]; c.n_a = A.prob_nca[pidx];
-            c.regs = A.regs + A.prob_roff[pidx]; c.n_regs = A.prob_nregs[pidx];
-            c.cap_regs = (int)(A.prob_roff[pidx + 1] - A.prob_roff[pidx]);
-            c.cig = cig; c.cig_top = 0; c.cig_cap = (uint32_t)A.cig_cap;
-            hit_scratch_carve(c.hs, hsb, (size_t)A.reg_cap_max + 1);
-            c.K = K; c.capK = A.max_na + 8;
-            c.err = 0; c.n_tasks = 0;
-            c.phase = PH_START;
-            res_reset(W.res);
-        }
+        if (lane == 0) { res_reset(W.res); W.res.cigar = A.cigs + A.work[wi].ez_off; }
+        S.ezcig = A.cigs + A.work[wi].ez_off; S.ezcap = A.work[wi].ez_cap;
         __syncwarp();
         for (;;) {
             if (lane == 0) W.more = aln_next(W.c, W.res, W.task) ? 1 : 0;
             __syncwarp();
             if (!W.more) break;
-            if (W.task.kind == 0) warp_extd2(o, W.task, W.res, S, A.stat_cells, A.err);
-            else warp_ll(o, W.task, W.res, S, A.stat_cells);
+            if (W.task.kind == 0) {
+                const bool fast = A.use_fast && fill_fast_ok(W.task);
+                const int64_t need = fast ? (int64_t)W.task.qlen * fill_stride(W.task.tlen) : dp_dir_bytes(W.task.qlen, W.task.tlen, W.task.w);
+                int big_slot = -1;
+                S.dir = own_dir; S.dir_cap = A.dir_cap;
+                if (need > A.dir_cap && need <= A.big_cap && A.n_big > 0) {
+                    if (lane == 0) {        // take one of the shared large traceback buffers (holders never wait on anything)
+                        unsigned ns = 64;
+                        for (int sl = (blockIdx.x * AL_WARPS + wid) % A.n_big;; sl = (sl + 1) % A.n_big) {
+                            if (atomicCAS(&A.big_lock[sl], 0, 1) == 0) { big_slot = sl; break; }
+                            __nanosleep(ns);
+                            if (ns < 4096) ns <<= 1;
+                        }
+                        __threadfence();
+                    }
+                    big_slot = __shfl_sync(FULL, big_slot, 0);
+                    S.dir = A.big + (int64_t)big_slot * A.big_cap; S.dir_cap = A.big_cap;
+                }
+                bool done_fast = false;
+                if (fast && need <= S.dir_cap) done_fast = warp_fill_fast(o, W.task, W.res, S.dir, S.bnd, A.stat_cells);
+                if (!done_fast) warp_extd2(o, W.task, W.res, S, A.stat_cells, A.err);
+                __syncwarp();
+                if (lane == 0) {
+                    if (done_fast) fill_traceback(W.task, W.res, S.dir, S.ezcig, S.ezcap, A.err);
+                    else extd2_traceback(W.task, W.res, S.dir, S.ezcig, S.ezcap, A.err);
+                    if (big_slot >= 0) { __threadfence(); atomicExch(&A.big_lock[big_slot], 0); }
+                }
+            } else warp_ll(o, W.task, W.res, S, A.stat_cells);
             __syncwarp();
         }
-        if (lane == 0) {
-            AlnCtx &c = W.c;
-            if (c.err) atomicOr(A.err, c.err);
-            atomicAdd(A.stat_tasks, (unsigned long long)c.n_tasks);
-            A.prob_nregs[pidx] = c.n_regs;
-            // M-blocks of every record samtools depth would count (everything but SECONDARY)
-            int nb = 0, ncg = 0;
-            for (int i = 0; i < c.n_regs; ++i) {
-                const Reg &r = c.regs[i];
-                ncg += r.n_cigar;
-                if (r.parent != r.id) continue;
-                const uint32_t *cg = c.cig + r.cig;
-                for (int k = 0; k < r.n_cigar; ++k) nb += (cg[k] & 0xf) == 0;
-            }
-            long long boff = (long long)atomicAdd(A.n_blocks, (unsigned long long)nb);
-            if (boff + nb > A.blocks_cap) { atomicOr(A.err, 32); nb = 0; boff = 0; }
-            A.prob_blk_off[pidx] = boff; A.prob_blk_cnt[pidx] = nb;
-            if (nb) {
-                int w = 0;
-                for (int i = 0; i < c.n_regs; ++i) {
-                    const Reg &r = c.regs[i];
-                    if (r.parent != r.id) continue;
-                    const uint32_t *cg = c.cig + r.cig;
-                    int pos = r.rs;
-                    for (int k = 0; k < r.n_cigar; ++k) {
-                        int op = cg[k] & 0xf, len = (int)(cg[k] >> 4);
-                        if (op == 0) { A.blocks[boff + w++] = make_int2(pos, len); pos += len; }
-                        else if (op == 2) pos += len;
-                    }
-                }
-            }
-            if (A.aln_out && c.n_regs > 0) {
-                long long ao = (long long)atomicAdd(A.n_aln, (unsigned long long)c.n_regs);
-                long long co = (long long)atomicAdd(A.n_cig, (unsigned long long)ncg);
-                if (ao + c.n_regs > A.aln_cap || co + ncg > A.cig_out_cap) atomicOr(A.err, 64);
-                else {
-                    for (int i = 0; i < c.n_regs; ++i) {
-                        const Reg &r = c.regs[i];
-                        int32_t *oo = A.aln_out + (ao + i) * 16;
-                        oo[0] = read + A.read_base; oo[1] = strand; oo[2] = r.rs; oo[3] = r.re; oo[4] = r.qs; oo[5] = r.qe; oo[6] = r.rev;
-                        oo[7] = (r.rev ? 0x10 : 0) | (r.parent != r.id ? 0x100 : !r.sam_pri ? 0x800 : 0);
-                        oo[8] = r.dp_max; oo[9] = r.mlen; oo[10] = r.blen; oo[11] = r.n_cigar;
-                        oo[12] = (int32_t)(co & 0xffffffffLL); oo[13] = (int32_t)(co >> 32);
-                        oo[14] = pidx + 2 * A.read_base; oo[15] = i;
-                        const uint32_t *cg = c.cig + r.cig;
-                        for (int k = 0; k < r.n_cigar; ++k) A.cig_out[co + k] = cg[k];
-                        co += r.n_cigar;
-                    }
-                }
-            }
+        {   // coroutine state: shared -> global (k_al_finish continues from PH_FINISH)
+            uint32_t *dst = reinterpret_cast<uint32_t *>(&A.actx[wi]);
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(&W.c);
+            for (int i = lane; i < (int)(sizeof(AlnCtx) / 4); i += 32) dst[i] = src[i];
         }
         __syncwarp();
+    }
+}
+
+// deferred statistics + final region pass + outputs, one thread per problem
+__global__ void __launch_bounds__(128) k_al_finish(const __grid_constant__ AlignArgs A)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= A.n_work) return;
+    AlnCtx &c = A.actx[w];
+    const int pidx = A.work[w].pidx;
+    const int read = A.prob_read[pidx], strand = A.prob_ls[pidx] & 1;
+    if (c.phase == PH_FINISH) aln_finish(c);
+    if (c.err) atomicOr(A.err, c.err);
+    atomicAdd(A.stat_tasks, (unsigned long long)c.n_tasks);
+    A.prob_nregs[pidx] = c.n_regs;
+    // M-blocks of every record samtools depth would count (everything but SECONDARY)
+    int nb = 0, ncg = 0;
+    for (int i = 0; i < c.n_regs; ++i) {
+        const Reg &r = c.regs[i];
+        ncg += r.n_cigar;
+        if (r.parent != r.id) continue;
+        const uint32_t *cg = c.cig + r.cig;
+        for (int k = 0; k < r.n_cigar; ++k) nb += (cg[k] & 0xf) == 0;
+    }
+    long long boff = (long long)atomicAdd(A.n_blocks, (unsigned long long)nb);
+    if (boff + nb > A.blocks_cap) { atomicOr(A.err, 32); nb = 0; boff = 0; }
+    A.prob_blk_off[pidx] = boff; A.prob_blk_cnt[pidx] = nb;
+    if (nb) {
+        int wq = 0;
+        for (int i = 0; i < c.n_regs; ++i) {
+            const Reg &r = c.regs[i];
+            if (r.parent != r.id) continue;
+            const uint32_t *cg = c.cig + r.cig;
+            int pos = r.rs;
+            for (int k = 0; k < r.n_cigar; ++k) {
+                int op = cg[k] & 0xf, len = (int)(cg[k] >> 4);
+                if (op == 0) { A.blocks[boff + wq++] = make_int2(pos, len); pos += len; }
+                else if (op == 2) pos += len;
+            }
+        }
+    }
+    if (A.aln_out && c.n_regs > 0) {
+        long long ao = (long long)atomicAdd(A.n_aln, (unsigned long long)c.n_regs);
+        long long co = (long long)atomicAdd(A.n_cig, (unsigned long long)ncg);
+        if (ao + c.n_regs > A.aln_cap || co + ncg > A.cig_out_cap) atomicOr(A.err, 64);
+        else {
+            for (int i = 0; i < c.n_regs; ++i) {
+                const Reg &r = c.regs[i];
+                int32_t *oo = A.aln_out + (ao + i) * 16;
+                oo[0] = read + A.read_base; oo[1] = strand; oo[2] = r.rs; oo[3] = r.re; oo[4] = r.qs; oo[5] = r.qe; oo[6] = r.rev;
+                oo[7] = (r.rev ? 0x10 : 0) | (r.parent != r.id ? 0x100 : !r.sam_pri ? 0x800 : 0);
+                oo[8] = r.dp_max; oo[9] = r.mlen; oo[10] = r.blen; oo[11] = r.n_cigar;
+                oo[12] = (int32_t)(co & 0xffffffffLL); oo[13] = (int32_t)(co >> 32);
+                oo[14] = pidx + 2 * A.read_base; oo[15] = i;
+                const uint32_t *cg = c.cig + r.cig;
+                for (int k = 0; k < r.n_cigar; ++k) A.cig_out[co + k] = cg[k];
+                co += r.n_cigar;
+            }
+        }
     }
 }
 

@@ -1,0 +1,209 @@
+// k_fill.cuh — fast path of kernel (d) for approximate-max GLOBAL gap fills (82 % of all DP cells on config 2):
+// `ksw_extd2_sse(..., w >= max(qlen,tlen), flag = KSW_EZ_APPROX_MAX)` as issued by mm_align1's gap-filling loop
+// (minimap2 align.c; reference call site TELR_te.py:505).
+//
+// Mapping.  The DP state never leaves registers.  Lane l owns FC = 8 consecutive target columns of a 256-column
+// pass; it walks the query two rows at a time (row pair m at step m + l, a systolic skew of one pair per lane).
+// Inside a lane-step the two rows are swept left to right with the second row one column behind the first, so the
+// two cells handled together are independent and sit in the two 16-bit halves of every register:
+//     lo half: cell (column k,   row j)      hi half: cell (column k-1, row j+1)
+// The difference recurrence (u,v,x,y,x2,y2) then runs on packed 16x2 integer SIMD ops.  Direction information is
+// 8 sign bits per cell (which of s,a,b,a2 is below the maximum; which gap states do not continue) gathered with
+// four PRMTs in sign-replicate mode; one 8-byte store per row per lane writes them row-major.
+// Left-to-right values (v,x,x2) travel between lanes by shuffle, between 256-column passes through a small
+// per-warp boundary array.  No tensor cores: this is not a dense contraction.
+#pragma once
+#include <cuda_runtime.h>
+#include "mm_align.cuh"
+
+namespace telr {
+
+constexpr int FC = 8;                 // columns per lane
+constexpr int FW = 32 * FC;           // columns per pass
+
+__device__ __forceinline__ uint32_t pk2(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
+__device__ __forceinline__ uint32_t pk1(int v) { return pk2(v, v); }
+__device__ __forceinline__ int lo16(uint32_t v) { return (int)(int16_t)(v & 0xffffu); }
+__device__ __forceinline__ int hi16(uint32_t v) { return (int)(int16_t)(v >> 16); }
+
+// sum of the first n boundary differences f(0..n-1) of ksw_extd2 (first row / first column)
+__device__ __forceinline__ int bnd_sum(int n, int qe, int e, int e2, int LT, int LD)
+{
+    if (n <= 0) return 0;
+    int s = -qe;                                           // r = 0
+    int n1 = (n - 1 < LT - 1 ? n - 1 : LT - 1);            // r = 1 .. LT-1
+    if (n1 > 0) s -= e * n1;
+    if (n - 1 >= LT && LT >= 1) s += LD;                    // r = LT
+    if (LT == 0 && n - 1 >= 0) { /* r == 0 already counted as -qe (r==0 wins) */ }
+    int n3 = n - 1 - (LT > 0 ? LT : 0);                     // r = LT+1 .. n-1
+    if (n3 > 0) s -= e2 * n3;
+    return s;
+}
+
+__host__ __device__ __forceinline__ int fill_stride(int tlen) { return (tlen + FC - 1) / FC * FC; }
+
+// true when the request can take the fast path (shape / flags); ambiguous bases are checked inside
+__device__ __forceinline__ bool fill_fast_ok(const DpTask &T)
+{
+    if (T.kind != 0 || T.flag != KSW_APPROX_MAX || T.qstep != 1 || T.tstep != 1 || T.qcomp) return false;
+    if (T.qlen < 1 || T.tlen < 1) return false;
+    int mx = T.qlen > T.tlen ? T.qlen : T.tlen;
+    return T.w < 0 || T.w >= mx;
+}
+
+// forward pass; returns false (nothing written) when an ambiguous base is present
+__device__ bool warp_fill_fast(const Opt &o, const DpTask &T, DpRes &R, uint8_t *dir, uint32_t *bnd, unsigned long long *cells_acc)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    const int qlen = T.qlen, tlen = T.tlen;
+    const uint8_t *__restrict__ Q = T.q, *__restrict__ Tg = T.t;
+    {   // ambiguous bases take the general path (their score is not match/mismatch)
+        bool n = false;
+        for (int i = lane; i < qlen; i += 32) n |= Q[i] > 3;
+        for (int i = lane; i < tlen; i += 32) n |= Tg[i] > 3;
+        if (__any_sync(FULL, n)) return false;
+    }
+    int q = o.q, e = o.e, q2 = o.q2, e2 = o.e2;
+    if (q2 + e2 < q + e) { int t = q; q = q2; q2 = t; t = e; e = e2; e2 = t; }
+    const int qe = q + e, qe2 = q2 + e2;
+    int LT = e != e2 ? (q2 - q) / (e - e2) - 1 : 0;
+    if (q2 + e2 + LT * e2 > q + e + LT * e) ++LT;
+    const int LD = LT * (e - e2) - (q2 - q) - e2;
+#define BNDF(r) ((r) == 0 ? -qe : (r) < LT ? -e : (r) == LT ? LD : -e2)
+    const uint32_t MAT = pk1(o.a), MIS = pk1(-o.b), NE1 = pk1(-e), NQE1 = pk1(-qe), NE2 = pk1(-e2), NQE2 = pk1(-qe2);
+    const uint32_t QM1 = pk1(q - 1), Q2M1 = pk1(q2 - 1);
+    const int stride = fill_stride(tlen);
+    const int npairs = (qlen + 1) >> 1, npass = (tlen + FW - 1) / FW;
+    int usum = 0;
+    if (lane == 0) { res_reset(R); }
+    for (int pass = 0; pass < npass; ++pass) {
+        const int t0 = pass * FW + lane * FC;
+        const bool live = t0 < tlen;
+        uint32_t tp[FC + 1], Uu[FC], Uy[FC], Uy2[FC];
+#pragma unroll
+        for (int k = 0; k <= FC; ++k) {
+            int lo = (k < FC && t0 + k < tlen) ? Tg[t0 + k] : 0;
+            int hi = (k >= 1 && t0 + k - 1 < tlen) ? Tg[t0 + k - 1] : 0;
+            tp[k] = pk2(lo, hi);
+        }
+#pragma unroll
+        for (int k = 0; k < FC; ++k) {              // top boundary sits in the hi halves (row "-1" of pair 0)
+            const int r = t0 + k;
+            Uu[k] = pk2(0, BNDF(r)); Uy[k] = pk2(0, -qe); Uy2[k] = pk2(0, -qe2);
+        }
+        uint32_t inV = 0, inX = 0, inX2 = 0, inQ = 0, Ufirst = 0;
+        const bool last_pass = pass == npass - 1;
+        for (int s = 0; s < npairs + 31; ++s) {
+            const int m = s - lane;
+            const bool active = live && m >= 0 && m < npairs;
+            if (lane == 0 && s < npairs) {
+                const int j = 2 * s;
+                inQ = pk2(Q[j], j + 1 < qlen ? Q[j + 1] : 0);
+                if (pass == 0) {
+                    inV = pk2(BNDF(j), BNDF(j + 1)); inX = NQE1; inX2 = NQE2;
+                } else { inV = bnd[3 * s]; inX = bnd[3 * s + 1]; inX2 = bnd[3 * s + 2]; }
+            }
+            uint32_t outV = 0, outX = 0, outX2 = 0;
+            if (active) {
+                const int j = 2 * m;
+                uint32_t Lv = inV, Lx = inX, Lx2 = inX2, pu = 0, py = 0, py2 = 0, kV = 0, kX = 0, kX2 = 0;
+                uint32_t rF0 = 0, rF1 = 0, rS0 = 0, rS1 = 0;
+#pragma unroll
+                for (int k = 0; k <= FC; ++k) {
+                    const int kk = k < FC ? k : FC - 1;
+                    // up inputs: lo <- previous row pair's second row (hi half of the saved register), hi <- cell above in this pair
+                    const uint32_t up_u = __byte_perm(Uu[kk], pu, 0x5432), up_y = __byte_perm(Uy[kk], py, 0x5432), up_y2 = __byte_perm(Uy2[kk], py2, 0x5432);
+                    if (k == 1) {                   // second row enters: its left neighbour is the previous lane's last column
+                        Lv = __byte_perm(Lv, inV, 0x7610); Lx = __byte_perm(Lx, inX, 0x7610); Lx2 = __byte_perm(Lx2, inX2, 0x7610);
+                    }
+                    const uint32_t ne = __vminu2(tp[k] ^ inQ, 0x00010001u);
+                    const uint32_t msk = ne * 0xffffu;
+                    const uint32_t S = (msk & MIS) | (~msk & MAT);
+                    const uint32_t A = __vadd2(Lx, Lv), A2 = __vadd2(Lx2, Lv), B = __vadd2(up_y, up_u), B2 = __vadd2(up_y2, up_u);
+                    uint32_t Z = __vimax3_s16x2(S, A, B);
+                    Z = __vimax3_s16x2(Z, A2, B2);
+                    const uint32_t DS = __vsub2(S, Z), DA = __vsub2(A, Z), DB = __vsub2(B, Z), DA2 = __vsub2(A2, Z), DB2 = __vsub2(B2, Z);
+                    const uint32_t nu = __vsub2(Z, Lv), nv = __vsub2(Z, up_u);
+                    const uint32_t nx = __viaddmax_s16x2(DA, NE1, NQE1), ny = __viaddmax_s16x2(DB, NE1, NQE1);
+                    const uint32_t nx2 = __viaddmax_s16x2(DA2, NE2, NQE2), ny2 = __viaddmax_s16x2(DB2, NE2, NQE2);
+                    const uint32_t cx = __vadd2(DA, QM1), cy = __vadd2(DB, QM1), cx2 = __vadd2(DA2, Q2M1), cy2 = __vadd2(DB2, Q2M1);
+                    // 8 sign bits per cell -> one byte per cell
+                    uint32_t acc = __byte_perm(DS, DA, 0xFDB9) & 0x02020101u;
+                    acc |= __byte_perm(DB, DA2, 0xFDB9) & 0x08080404u;
+                    acc |= __byte_perm(cx, cy, 0xFDB9) & 0x20201010u;
+                    acc |= __byte_perm(cx2, cy2, 0xFDB9) & 0x80804040u;
+                    const uint32_t f = acc | (acc >> 16);
+                    if (k < FC) {
+                        if (k < 4) rF0 |= (f & 0xffu) << (8 * (k & 3)); else rF1 |= (f & 0xffu) << (8 * (k & 3));
+                    }
+                    if (k >= 1) {
+                        const int c = k - 1;
+                        if (c < 4) rS0 |= ((f >> 8) & 0xffu) << (8 * (c & 3)); else rS1 |= ((f >> 8) & 0xffu) << (8 * (c & 3));
+                        Uu[c] = nu; Uy[c] = ny; Uy2[c] = ny2;          // hi halves: cell (c, j+1) = up input of the next row pair
+                    }
+                    if (k == 0) Ufirst = nu;
+                    if (k == FC - 1) { kV = nv; kX = nx; kX2 = nx2; }
+                    pu = nu; py = ny; py2 = ny2; Lv = nv; Lx = nx; Lx2 = nx2;
+                }
+                outV = __byte_perm(kV, Lv, 0x7610); outX = __byte_perm(kX, Lx, 0x7610); outX2 = __byte_perm(kX2, Lx2, 0x7610);
+                if (t0 < stride) {
+                    *reinterpret_cast<uint2 *>(dir + (int64_t)j * stride + t0) = make_uint2(rF0, rF1);
+                    if (j + 1 < qlen) *reinterpret_cast<uint2 *>(dir + (int64_t)(j + 1) * stride + t0) = make_uint2(rS0, rS1);
+                }
+                if (lane == 31 && !last_pass) { bnd[3 * m] = outV; bnd[3 * m + 1] = outX; bnd[3 * m + 2] = outX2; }
+            }
+            // systolic hand-over to the next lane (used by it in the next step)
+            const uint32_t sV = __shfl_up_sync(FULL, outV, 1), sX = __shfl_up_sync(FULL, outX, 1), sX2 = __shfl_up_sync(FULL, outX2, 1);
+            const uint32_t sQ = __shfl_up_sync(FULL, inQ, 1);
+            if (lane > 0) { inV = sV; inX = sX; inX2 = sX2; inQ = sQ; }
+        }
+        // u of the last query row for this lane's columns (score = boundary + sum of u along the last row)
+        if (live) {
+#pragma unroll
+            for (int k = 0; k < FC; ++k) {
+                if (t0 + k >= tlen) continue;
+                if (qlen & 1) usum += k == 0 ? lo16(Ufirst) : lo16(Uu[k - 1]);     // last real row = first row of the last pair
+                else usum += hi16(Uu[k]);
+            }
+        }
+        __syncwarp();       // bnd[] written by lane 31 is read by lane 0 in the next pass
+    }
+#undef BNDF
+#pragma unroll
+    for (int d = 16; d; d >>= 1) usum += __shfl_xor_sync(FULL, usum, d);
+    if (lane == 0) {
+        R.score = bnd_sum(qlen, qe, e, e2, LT, LD) + usum;
+        atomicAdd(cells_acc, (unsigned long long)qlen * (unsigned long long)tlen);
+    }
+    __syncwarp();
+    return true;
+}
+
+// ksw_backtrack over the fast path's row-major direction bytes (global alignment, no band); one thread
+__device__ void fill_traceback(const DpTask &T, DpRes &R, const uint8_t *dir, uint32_t *ezcig, int ezcap, int32_t *err)
+{
+    const int qlen = T.qlen, tlen = T.tlen, stride = fill_stride(tlen);
+    R.n_cigar = 0; R.cigar = ezcig; R.reach_end = 0;
+    uint32_t *c = ezcig; int n = 0;
+    int i = tlen - 1, j = qlen - 1, state = 0;
+#define PUSH(op, len) do { if (n == 0 || (uint32_t)(op) != (c[n - 1] & 0xf)) { if (n < ezcap) c[n] = (uint32_t)(len) << 4 | (op); ++n; } else c[n - 1] += (uint32_t)(len) << 4; } while (0)
+    while (i >= 0 && j >= 0) {
+        const uint32_t b = dir[(int64_t)j * stride + i];
+        const int d = !(b & 1) ? 0 : !(b & 2) ? 1 : !(b & 4) ? 2 : !(b & 8) ? 3 : 4;
+        if (state == 0) state = d;
+        else if ((b >> (3 + state)) & 1) state = 0;      // the gap does not continue here
+        if (state == 0) state = d;
+        if (state == 0) { PUSH(0, 1); --i; --j; }
+        else if (state == 1 || state == 3) { PUSH(2, 1); --i; }
+        else { PUSH(1, 1); --j; }
+    }
+    if (i >= 0) PUSH(2, i + 1);
+    if (j >= 0) PUSH(1, j + 1);
+#undef PUSH
+    if (n > ezcap) { atomicOr(err, TELR_ERR_CIGCAP); n = 0; }
+    for (int k = 0; k < n >> 1; ++k) { uint32_t t = c[k]; c[k] = c[n - 1 - k]; c[n - 1 - k] = t; }
+    R.n_cigar = n;
+}
+
+}  // namespace telr

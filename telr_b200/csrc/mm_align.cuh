@@ -27,6 +27,7 @@ struct AlnCtx {
     HitScratch hs;
     int32_t *K; int capK;
     int err;
+    int defer_finish;       // 1: leave reg_finish + the final region pass to aln_finish() (GPU rounds), 0: inline
     int64_t n_tasks;
     // ---- coroutine state ----
     int phase, ireg;
@@ -647,7 +648,11 @@ TELR_HDN bool aln_next(AlnCtx &c, const DpRes &in, DpTask &task)
             r.rs = c.rs1, r.re = c.re1;
             if (c.rev) r.qs = c.qlen - c.qe1, r.qe = c.qlen - c.qs1;
             else r.qs = c.qs1, r.qe = c.qe1;
-            if (r.has_p) reg_finish(c, r, &c.qseq[r.rev][c.qs1], &c.tseq[c.rs1]);
+            if (r.has_p) {
+                // statistics of the joined CIGAR are only needed right away when an inversion test follows
+                if (c.defer_finish && !r.split_inv && !(c.r2.cnt > 0 && c.r2.split_inv)) r.need_fin = 1, r.fin_q = c.qs1, r.fin_t = c.rs1;
+                else reg_finish(c, r, &c.qseq[r.rev][c.qs1], &c.tseq[c.rs1]);
+            }
             if (c.r2.cnt > 0) regs_insert(c, c.r2, c.ireg);
             c.phase = PH_NEXT_REG;
             if (c.ireg > 0 && c.regs[c.ireg].split_inv) {      // inversion between the two halves of a split?
@@ -713,6 +718,7 @@ TELR_HDN bool aln_next(AlnCtx &c, const DpRes &in, DpTask &task)
         }
         case PH_NEXT_REG: ++c.ireg; c.phase = PH_REG_BEGIN; break;
         case PH_FINISH: {
+            if (c.defer_finish) return false;        // the caller runs aln_finish() once every DP request is served
             regs_filter(o, c.qlen, &c.n_regs, c.regs);
             if (c.qlen >= o.rank_min_len) {
                 regs_update_dp_max(c);
@@ -728,6 +734,26 @@ TELR_HDN bool aln_next(AlnCtx &c, const DpRes &in, DpTask &task)
         default: return false;
         }
     }
+}
+
+// deferred tail of the coroutine: per-region statistics, then the final filter / sort / primary assignment
+TELR_HDN void aln_finish(AlnCtx &c)
+{
+    const Opt &o = *c.o;
+    for (int i = 0; i < c.n_regs; ++i) {
+        Reg &r = c.regs[i];
+        if (r.need_fin) { r.need_fin = 0; reg_finish(c, r, &c.qseq[r.rev][r.fin_q], &c.tseq[r.fin_t]); }
+    }
+    regs_filter(o, c.qlen, &c.n_regs, c.regs);
+    if (c.qlen >= o.rank_min_len) {
+        regs_update_dp_max(c);
+        regs_filter(o, c.qlen, &c.n_regs, c.regs);
+    }
+    regs_sort(&c.n_regs, c.regs, c.hs);
+    regs_set_parent(o, c.n_regs, c.regs, c.hs);
+    regs_select_sub(o, 0, &c.n_regs, c.regs, c.hs, c.cap_regs);
+    regs_set_sam_pri(c.n_regs, c.regs);
+    c.phase = PH_DONE;
 }
 
 }  // namespace telr

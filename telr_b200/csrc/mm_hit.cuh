@@ -60,7 +60,8 @@ TELR_HD void reg_clear(Reg &r)
 {
     r.id = r.cnt = r.score = r.qs = r.qe = r.rs = r.re = r.parent = r.subsc = r.as = r.mlen = r.blen = r.n_sub = r.score0 = 0;
     r.hash = 0;
-    r.rev = r.inv = r.sam_pri = r.split = r.split_inv = r.strand_retained = r.has_p = r.pad0 = 0;
+    r.rev = r.inv = r.sam_pri = r.split = r.split_inv = r.strand_retained = r.has_p = r.need_fin = 0;
+    r.fin_q = r.fin_t = 0;
     r.dp_score = r.dp_max = r.dp_max2 = r.n_ambi = r.n_cigar = 0;
     r.cig = 0;
 }

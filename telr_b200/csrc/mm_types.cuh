@@ -60,9 +60,10 @@ struct Opt {
 struct Reg {
     int32_t id, cnt, score, qs, qe, rs, re, parent, subsc, as, mlen, blen, n_sub, score0;
     uint32_t hash;
-    uint8_t rev, inv, sam_pri, split, split_inv, strand_retained, has_p, pad0;
+    uint8_t rev, inv, sam_pri, split, split_inv, strand_retained, has_p, need_fin;
     int32_t dp_score, dp_max, dp_max2, n_ambi, n_cigar;
     uint32_t cig;            // offset of this region's CIGAR in the problem's cigar arena
+    int32_t fin_q, fin_t;    // where the joined CIGAR starts on query/target (deferred reg_finish)
 };
 
 // result of one DP call (ksw_extz_t)

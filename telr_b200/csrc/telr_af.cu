@@ -50,6 +50,7 @@ struct telr_af_ctx {
     long long launches = 0;
     size_t ws_limit = 0;
     int depth_mode = 1;
+    int use_fast = 1;
     int64_t chunk_bases = 0;
     int64_t dir_cap = 8 << 20;
     // device buffers
@@ -58,6 +59,8 @@ struct telr_af_ctx {
     DevBuf b_lrb, b_cboff, b_ctg, b_descs, b_counts, b_mzoff, b_mzx, b_mzy, b_self, b_tabk, b_tabc, b_hpc, b_hpp, b_hpr;
     DevBuf b_pna, b_pread, b_pls, b_paoff, b_prcap, b_proff, b_pnregs, b_pnca, b_anch, b_regs, b_chws, b_alws, b_work;
     DevBuf b_psb, b_psoff, b_pscr, b_pnu, b_pm;
+    DevBuf b_rbytes, b_rboff, b_alwork, b_alctx, b_altask, b_alres, b_alsz, b_aloff, b_cigs, b_pool, b_tlist, b_rc, b_opt;
+    int64_t pool_cap = (int64_t)6144 << 20;
     DevBuf b_blk, b_pblkoff, b_pblkcnt, b_ctr, b_alnout, b_cigout, b_doff, b_big, b_biglock;
     int n_big = 8; int64_t big_cap = (int64_t)208 << 20;
     cudaEvent_t ev[10];
@@ -114,6 +117,24 @@ __global__ void k_worklist(int n, const int32_t *nregs, int32_t *list, int32_t *
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && nregs[i] > 0) list[atomicAdd(count, 1)] = i;
+}
+
+__global__ void k_al_sizes(AlignArgs A, int32_t *sizes)
+{
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= A.n_work) return;
+    const int pidx = A.work_list[w];
+    const int qlen = A.read_len[A.prob_read[pidx]], L = A.contig_len[A.prob_ls[pidx] >> 1];
+    sizes[w] = (2 * (qlen + L) + 256) + (qlen + L + 16);
+}
+__global__ void k_al_offsets(AlignArgs A, const int64_t *off)
+{
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= A.n_work) return;
+    const int pidx = A.work_list[w];
+    const int qlen = A.read_len[A.prob_read[pidx]], L = A.contig_len[A.prob_ls[pidx] >> 1];
+    A.work[w].cig_off = off[w]; A.work[w].cig_cap = 2 * (qlen + L) + 256;
+    A.work[w].ez_off = off[w] + A.work[w].cig_cap; A.work[w].ez_cap = qlen + L + 16;
 }
 
 struct HostMeta {       // host copies of the small per-read / per-locus arrays
@@ -217,7 +238,6 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
     CK(cudaMemcpyAsync(&max_na, ctr + C_MAXNA, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     ENS(ctx->b_anch, (tot_na + 1) * sizeof(Anchor)); ENS(ctx->b_regs, (tot_rcap + 1) * sizeof(Reg)); ENS(ctx->b_pscr, tot_scr + 256);
-    const int reg_cap_max = 2 * ((int)max_na / 3) + 8;
     const size_t ch_stride = (((size_t)max_qlen + 64) * 4 + 255) & ~(size_t)255;
     ENS(ctx->b_chws, ch_stride * (size_t)ch_grid * CH_WARPS);
     CK(cudaMemsetAsync(ctr + C_WORK_CHAIN, 0, 8, st));
@@ -243,6 +263,18 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
     CK(cudaMemcpyAsync(&n_work64, ctr + C_NWORK, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const int n_work = (int)(n_work64 & 0xffffffff);
+    if (n_work > 1) {   // longest problems first (LPT): the persistent warps drain the queue in this order
+        std::vector<int32_t> wl(n_work), pr(n_prob);
+        CK(cudaMemcpyAsync(wl.data(), ctx->b_work.p, (size_t)n_work * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(pr.data(), ctx->b_pread.p, (size_t)n_prob * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        std::sort(wl.begin(), wl.end(), [&](int32_t a, int32_t b) {
+            int la = hm.read_len[r0 + pr[a]], lb = hm.read_len[r0 + pr[b]];
+            return la != lb ? la > lb : a < b;
+        });
+        CK(cudaMemcpyAsync(ctx->b_work.p, wl.data(), (size_t)n_work * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+    }
     int64_t chunk_bases = 0;
     for (int r = r0; r < r1; ++r) chunk_bases += hm.read_len[r];
     int64_t blocks_cap = chunk_bases / 2 + (int64_t)n_prob * 8 + 1024;
@@ -250,26 +282,43 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
     CK(cudaMemsetAsync(ctx->b_pblkcnt.p, 0, (size_t)(n_prob + 1) * 4, st));
     CK(cudaMemsetAsync(ctx->b_pblkoff.p, 0, (size_t)(n_prob + 1) * 8, st));
     AlignArgs aa; memset(&aa, 0, sizeof(aa));
-    aa.o = o; aa.n_prob = n_prob; aa.read_base = r0; aa.seq2 = db->seq2; aa.nmask = db->nmask; aa.read_off = read_off; aa.read_len = read_len;
+    ENS(ctx->b_opt, sizeof(Opt));
+    CK(cudaMemcpyAsync(ctx->b_opt.p, &o, sizeof(Opt), cudaMemcpyHostToDevice, st));
+    aa.o = o; aa.d_opt = ctx->b_opt.as<Opt>(); aa.n_prob = n_prob; aa.read_base = r0; aa.n_work = n_work; aa.read_len = read_len;
     aa.contig_len = contig_len; aa.ctg_boff = ctx->b_cboff.as<int64_t>(); aa.ctg_bytes = ctx->b_ctg.as<uint8_t>();
     aa.prob_read = ctx->b_pread.as<int32_t>(); aa.prob_ls = ctx->b_pls.as<int32_t>(); aa.prob_nca = ctx->b_pnca.as<int32_t>();
     aa.prob_nregs = ctx->b_pnregs.as<int32_t>(); aa.prob_aoff = ctx->b_paoff.as<int64_t>(); aa.prob_roff = ctx->b_proff.as<int64_t>();
     aa.anchors = ctx->b_anch.as<Anchor>(); aa.regs = ctx->b_regs.as<Reg>();
-    aa.max_qlen = max_qlen; aa.max_tlen = max_tlen; aa.max_na = (int)max_na; aa.reg_cap_max = reg_cap_max;
-    aa.cig_cap = 4 * (max_qlen + max_tlen) + 1024; aa.dir_cap = ctx->dir_cap;
-    ENS(ctx->b_big, (size_t)ctx->n_big * ctx->big_cap); ENS(ctx->b_biglock, 256);
-    CK(cudaMemsetAsync(ctx->b_biglock.p, 0, 256, st));
-    aa.big = ctx->b_big.as<uint8_t>(); aa.big_cap = ctx->big_cap; aa.n_big = ctx->n_big; aa.big_lock = ctx->b_biglock.as<int32_t>();
-    {
-        size_t maxQ = ((size_t)max_qlen + 64) & ~(size_t)15, maxT = ((size_t)max_tlen + 64) & ~(size_t)15;
-        size_t s = 2 * maxQ + 6 * maxT + maxT * 4 + maxT * 24 + (maxQ + maxT) * 4 + (size_t)aa.cig_cap * 4 + ((size_t)max_na + 8) * 4 +
-                   hit_scratch_bytes((size_t)reg_cap_max + 1) + 512 + (size_t)aa.dir_cap;
-        aa.warp_scratch_stride = (s + 255) & ~(size_t)255;
+    aa.prob_scratch = ctx->b_pscr.as<uint8_t>(); aa.prob_soff = ctx->b_psoff.as<int64_t>();
+    aa.work_list = ctx->b_work.as<int32_t>();
+    {   // nt4 bytes of every read of the chunk (forward + reverse complement)
+        std::vector<int64_t> rbo(n_reads + 1);
+        int64_t acc = 0;
+        for (int r = 0; r < n_reads; ++r) { rbo[r] = acc; acc += 2 * (((int64_t)hm.read_len[r0 + r] + 15) & ~15LL); }
+        rbo[n_reads] = acc;
+        ENS(ctx->b_rboff, (size_t)(n_reads + 1) * 8); ENS(ctx->b_rbytes, acc + 64);
+        CK(cudaMemcpyAsync(ctx->b_rboff.p, rbo.data(), (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        k_unpack_reads<<<std::max(1, std::min(n_reads, sm * 16)), 128, 0, st>>>(n_reads, db->seq2, db->nmask, read_off, read_len, ctx->b_rboff.as<int64_t>(), ctx->b_rbytes.as<uint8_t>());
+        aa.read_bytes = ctx->b_rbytes.as<uint8_t>(); aa.rbyte_off = ctx->b_rboff.as<int64_t>();
     }
+    const int nwk = std::max(n_work, 1);
+    ENS(ctx->b_alwork, (size_t)nwk * sizeof(AlWork)); ENS(ctx->b_alctx, (size_t)nwk * sizeof(AlnCtx)); ENS(ctx->b_altask, (size_t)nwk * sizeof(DpTask));
+    ENS(ctx->b_alres, (size_t)nwk * sizeof(DpRes)); ENS(ctx->b_alsz, (size_t)(nwk + 1) * 4); ENS(ctx->b_aloff, (size_t)(nwk + 2) * 8);
+    ENS(ctx->b_rc, 64);
     const int al_grid = std::max(1, std::min((n_work + AL_WARPS - 1) / AL_WARPS, sm * 4));
-    ENS(ctx->b_alws, aa.warp_scratch_stride * (size_t)al_grid * AL_WARPS);
-    aa.warp_scratch = ctx->b_alws.as<uint8_t>();
-    aa.work_counter = (int32_t *)(ctr + C_WORK_ALIGN); aa.work_list = ctx->b_work.as<int32_t>(); aa.n_work = n_work;
+    {
+        size_t maxT = ((size_t)max_tlen + 64) & ~(size_t)15;
+        aa.max_tlen = max_tlen; aa.max_qlen = max_qlen; aa.dir_cap = ctx->dir_cap; aa.use_fast = ctx->use_fast;
+        aa.warp_scratch_stride = (maxT * (6 + 4 + 24) + (((size_t)max_qlen + 64) & ~(size_t)15) * 6 + 512 + (size_t)ctx->dir_cap + 255) & ~(size_t)255;
+        ENS(ctx->b_alws, aa.warp_scratch_stride * (size_t)al_grid * AL_WARPS);
+        aa.warp_scratch = ctx->b_alws.as<uint8_t>();
+        ENS(ctx->b_big, (size_t)ctx->n_big * ctx->big_cap); ENS(ctx->b_biglock, 256);
+        CK(cudaMemsetAsync(ctx->b_biglock.p, 0, 256, st));
+        aa.big = ctx->b_big.as<uint8_t>(); aa.big_cap = ctx->big_cap; aa.n_big = ctx->n_big; aa.big_lock = ctx->b_biglock.as<int32_t>();
+    }
+    aa.work = ctx->b_alwork.as<AlWork>(); aa.actx = ctx->b_alctx.as<AlnCtx>(); aa.tasks = ctx->b_altask.as<DpTask>(); aa.res = ctx->b_alres.as<DpRes>();
+    aa.rc = ctx->b_rc.as<unsigned long long>();
     aa.err = (int32_t *)(ctr + C_ERR); aa.stat_cells = (unsigned long long *)(ctr + C_CELLS); aa.stat_tasks = (unsigned long long *)(ctr + C_TASKS);
     aa.blocks = ctx->b_blk.as<int2>(); aa.n_blocks = (unsigned long long *)(ctr + C_NBLK); aa.blocks_cap = blocks_cap;
     aa.prob_blk_off = ctx->b_pblkoff.as<int64_t>(); aa.prob_blk_cnt = ctx->b_pblkcnt.as<int32_t>();
@@ -280,7 +329,21 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
         CK(cudaMemcpyAsync(ctr + C_NALN, init, 16, cudaMemcpyHostToDevice, st));
     }
     CK(cudaEventRecord(ctx->ev[3], st));
-    if (n_work > 0) k_align<<<al_grid, AL_THREADS, 0, st>>>(aa);
+    if (n_work > 0) {
+        const int tb = (n_work + 127) / 128;
+        k_al_sizes<<<tb, 128, 0, st>>>(aa, ctx->b_alsz.as<int32_t>());
+        k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_alsz.as<int32_t>(), ctx->b_aloff.as<int64_t>(), n_work, nullptr);
+        int64_t cig_total = 0;
+        CK(cudaMemcpyAsync(&cig_total, ctx->b_aloff.as<int64_t>() + n_work, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        ENS(ctx->b_cigs, (size_t)(cig_total + 16) * 4);
+        aa.cigs = ctx->b_cigs.as<uint32_t>();
+        CK(cudaMemsetAsync(ctx->b_rc.p, 0, 64, st));
+        k_al_offsets<<<tb, 128, 0, st>>>(aa, ctx->b_aloff.as<int64_t>());
+        k_al_init<<<tb, 128, 0, st>>>(aa);
+        k_al_fused<<<al_grid, AL_THREADS, 0, st>>>(aa);
+        k_al_finish<<<tb, 128, 0, st>>>(aa);
+    }
     CK(cudaEventRecord(ctx->ev[4], st));
     // ---- (e)+(f) depth, medians, AF ----
     DepthArgs da; memset(&da, 0, sizeof(da));
@@ -312,7 +375,7 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
     }
     stats->dp_cells += hc[C_CELLS]; stats->n_dp_tasks += hc[C_TASKS]; stats->n_anchors += hc[C_ANCH]; stats->n_minimizers += n_mz;
     stats->n_aln_blocks += hc[C_NBLK];
-    ctx->launches += 20 + (n_work > 0 ? 1 : 0);   // unpack, descs, sketch x2, scan x4, self_count, chain x2 + sort/dp/bt/rmq/regs, reg_caps, worklist, align, depth_af
+    ctx->launches += 22 + (n_work > 0 ? 6 : 0);   // unpack, descs, sketch x2, scan x4, self_count, chain x2 + sort/dp/bt/rmq/regs, reg_caps, worklist, align, depth_af
     if (d_aln_out) { stats->n_aln = hc[C_NALN]; stats->n_cigar = hc[C_NCIG]; }
     float ms;
     static const int pairs[5][3] = {{0, 1, 0}, {1, 2, 1}, {2, 3, 2}, {3, 4, 3}, {4, 5, 6}};
@@ -398,6 +461,10 @@ int telr_af_create(telr_af_ctx **out, int device, size_t workspace_bytes)
     if (dm) ctx->depth_mode = atoi(dm) ? 1 : 0;
     const char *cb = getenv("TELR_CHUNK_MBASES");
     if (cb) ctx->chunk_bases = (int64_t)atoll(cb) << 20;
+    const char *uf = getenv("TELR_FAST_FILL");
+    if (uf) ctx->use_fast = atoi(uf) ? 1 : 0;
+    const char *pm = getenv("TELR_POOL_MB");
+    if (pm) ctx->pool_cap = (int64_t)atoll(pm) << 20;
     const char *dc = getenv("TELR_DIR_MB");
     if (dc) ctx->dir_cap = (int64_t)atoll(dc) << 20;
     *out = ctx;
@@ -413,7 +480,8 @@ int telr_af_destroy(telr_af_ctx *ctx)
                      &ctx->b_mzx, &ctx->b_mzy, &ctx->b_self, &ctx->b_tabk, &ctx->b_tabc, &ctx->b_hpc, &ctx->b_hpp, &ctx->b_hpr, &ctx->b_pna, &ctx->b_pread,
                      &ctx->b_pls, &ctx->b_paoff, &ctx->b_prcap, &ctx->b_proff, &ctx->b_pnregs, &ctx->b_pnca, &ctx->b_anch, &ctx->b_regs, &ctx->b_chws,
                      &ctx->b_alws, &ctx->b_work, &ctx->b_blk, &ctx->b_pblkoff, &ctx->b_pblkcnt, &ctx->b_ctr, &ctx->b_alnout, &ctx->b_cigout, &ctx->b_doff,
-                     &ctx->b_big, &ctx->b_biglock, &ctx->b_psb, &ctx->b_psoff, &ctx->b_pscr, &ctx->b_pnu, &ctx->b_pm};
+                     &ctx->b_big, &ctx->b_biglock, &ctx->b_rbytes, &ctx->b_rboff, &ctx->b_alwork, &ctx->b_alctx, &ctx->b_altask, &ctx->b_alres, &ctx->b_alsz, &ctx->b_aloff,
+                     &ctx->b_cigs, &ctx->b_pool, &ctx->b_tlist, &ctx->b_rc, &ctx->b_opt, &ctx->b_psb, &ctx->b_psoff, &ctx->b_pscr, &ctx->b_pnu, &ctx->b_pm};
     for (auto *b : all) b->release();
     for (auto &b : ctx->b_in) b.release();
     for (auto &e : ctx->ev) cudaEventDestroy(e);
@@ -610,8 +678,7 @@ int telr_af_depth_af(telr_af_ctx *ctx, int32_t n_loci, const int32_t *contig_len
 struct DpStageArgs {
     Opt o; int32_t n_tasks; const telr_dp_task *tasks; const uint8_t *q, *t; telr_dp_out *out;
     uint32_t *cig; unsigned long long *n_cig; int64_t cig_cap;
-    uint8_t *warp_scratch; size_t stride; int32_t maxQ, maxT; int64_t dir_cap;
-    uint8_t *big; int64_t big_cap; int32_t n_big; int32_t *big_lock;
+    uint8_t *warp_scratch; size_t stride; int32_t maxQ, maxT, use_fast; int64_t dir_cap;
     int32_t *work_counter, *err; unsigned long long *cells;
 };
 
@@ -630,9 +697,9 @@ __global__ void __launch_bounds__(AL_THREADS) k_dp_stage(const __grid_constant__
     S.H = (int32_t *)base; base += maxT * 4;
     S.ll = (int32_t *)base; base += maxT * 24;
     S.ezcap = (int32_t)(maxQ + maxT); S.ezcig = (uint32_t *)base; base += (size_t)S.ezcap * 4;
+    S.bnd = (uint32_t *)base; base += maxQ * 6;
     base = (uint8_t *)(((uintptr_t)base + 255) & ~(uintptr_t)255);
     S.dir = base; S.dir_cap = A.dir_cap;
-    S.big = A.big; S.big_cap = A.big_cap; S.n_big = A.n_big; S.big_lock = A.big_lock;
     S.s_state = &DS[wid].st[0][0]; S.s_H = DS[wid].H;
     for (;;) {
         int i = 0;
@@ -647,7 +714,15 @@ __global__ void __launch_bounds__(AL_THREADS) k_dp_stage(const __grid_constant__
             CS[wid] = 0;
         }
         __syncwarp();
-        warp_extd2(A.o, TS[wid], RS[wid], S, &CS[wid], A.err);
+        bool done_fast = false;
+        if (A.use_fast && fill_fast_ok(TS[wid]) && (int64_t)TS[wid].qlen * fill_stride(TS[wid].tlen) <= S.dir_cap)
+            done_fast = warp_fill_fast(A.o, TS[wid], RS[wid], S.dir, S.bnd, &CS[wid]);
+        if (!done_fast) warp_extd2(A.o, TS[wid], RS[wid], S, &CS[wid], A.err);
+        __syncwarp();
+        if (lane == 0) {
+            if (done_fast) fill_traceback(TS[wid], RS[wid], S.dir, S.ezcig, S.ezcap, A.err);
+            else extd2_traceback(TS[wid], RS[wid], S.dir, S.ezcig, S.ezcap, A.err);
+        }
         __syncwarp();
         if (lane == 0) {
             const DpRes &R = RS[wid];
@@ -676,7 +751,8 @@ extern "C" int telr_af_dp(telr_af_ctx *ctx, int32_t preset, int32_t n_tasks, con
     int maxQ = 0, maxT = 0;
     for (int i = 0; i < n_tasks; ++i) { maxQ = std::max(maxQ, tasks[i].qlen); maxT = std::max(maxT, tasks[i].tlen); }
     A.maxQ = (maxQ + 64) & ~15; A.maxT = (maxT + 64) & ~15; A.dir_cap = ctx->dir_cap;
-    A.stride = ((size_t)A.maxT * (6 + 4 + 24) + (size_t)(A.maxQ + A.maxT) * 4 + 512 + (size_t)A.dir_cap + 255) & ~(size_t)255;
+    A.use_fast = ctx->use_fast;
+    A.stride = ((size_t)A.maxT * (6 + 4 + 24) + (size_t)(A.maxQ + A.maxT) * 4 + (size_t)A.maxQ * 6 + 512 + (size_t)A.dir_cap + 255) & ~(size_t)255;
     const int grid = std::max(1, std::min((n_tasks + AL_WARPS - 1) / AL_WARPS, ctx->sm_count * 4));
     ENS(ctx->b_alws, A.stride * (size_t)grid * AL_WARPS);
     ENS(ctx->b_in[0], qbytes + 64); ENS(ctx->b_in[1], tbytes + 64); ENS(ctx->b_in[2], (size_t)n_tasks * sizeof(telr_dp_task));
@@ -690,9 +766,6 @@ extern "C" int telr_af_dp(telr_af_ctx *ctx, int32_t preset, int32_t n_tasks, con
     A.out = ctx->b_in[3].as<telr_dp_out>(); A.cig = ctx->b_cigout.as<uint32_t>(); A.n_cig = (unsigned long long *)(ctr + C_NCIG); A.cig_cap = cigar_cap;
     A.warp_scratch = ctx->b_alws.as<uint8_t>(); A.work_counter = (int32_t *)(ctr + C_WORK_ALIGN); A.err = (int32_t *)(ctr + C_ERR);
     A.cells = (unsigned long long *)(ctr + C_CELLS);
-    ENS(ctx->b_big, (size_t)ctx->n_big * ctx->big_cap); ENS(ctx->b_biglock, 256);
-    CK(cudaMemsetAsync(ctx->b_biglock.p, 0, 256, st));
-    A.big = ctx->b_big.as<uint8_t>(); A.big_cap = ctx->big_cap; A.n_big = ctx->n_big; A.big_lock = ctx->b_biglock.as<int32_t>();
     k_dp_stage<<<grid, AL_THREADS, 0, st>>>(A);
     int64_t hc[C_SLOTS];
     CK(cudaMemcpyAsync(hc, ctr, sizeof(hc), cudaMemcpyDeviceToHost, st));
