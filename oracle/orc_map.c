@@ -838,6 +838,7 @@ static void append_cigar(actx_t *c, reg_t *r, uint32_t n_cigar, const uint32_t *
 
 int64_t orc_cell_stats[8];   /* debugging: cells by task class */
 int64_t orc_size_hist[4][16];
+int64_t orc_tlen_hist[64], orc_qlen_hist[64];
 static void align_pair(actx_t *c, int qlen, const uint8_t *qseq, int tlen, const uint8_t *tseq, int w, int end_bonus,
                        int zdrop, int flag)
 {
@@ -863,6 +864,13 @@ static void align_pair(actx_t *c, int qlen, const uint8_t *qseq, int tlen, const
         orc_cell_stats[4 + cls] += 1;
 #pragma omp atomic
         orc_size_hist[cls][b] += ez->cells;
+        if (cls == 0) {
+            int tb = tlen / 32 < 63 ? tlen / 32 : 63, qb = qlen / 32 < 63 ? qlen / 32 : 63;
+#pragma omp atomic
+            orc_tlen_hist[tb] += ez->cells;
+#pragma omp atomic
+            orc_qlen_hist[qb] += ez->cells;
+        }
     }
 }
 

@@ -488,9 +488,9 @@ __global__ void __launch_bounds__(AL_THREADS) k_al_fused(const __grid_constant__
                 if (fast && need <= S.dir_cap) done_fast = warp_fill_fast(o, W.task, W.res, S.dir, S.bnd, A.stat_cells);
                 if (!done_fast) warp_extd2(o, W.task, W.res, S, A.stat_cells, A.err);
                 __syncwarp();
+                if (done_fast) fill_traceback(W.task, W.res, S.dir, S.ezcig, S.ezcap, A.err, *reinterpret_cast<TbSmem *>(DS[wid].H));     // the DP state window is idle during traceback
                 if (lane == 0) {
-                    if (done_fast) fill_traceback(W.task, W.res, S.dir, S.ezcig, S.ezcap, A.err);
-                    else extd2_traceback(W.task, W.res, S.dir, S.ezcig, S.ezcap, A.err);
+                    if (!done_fast) extd2_traceback(W.task, W.res, S.dir, S.ezcig, S.ezcap, A.err);
                     if (big_slot >= 0) { __threadfence(); atomicExch(&A.big_lock[big_slot], 0); }
                 }
             } else warp_ll(o, W.task, W.res, S, A.stat_cells);

@@ -180,30 +180,59 @@ __device__ bool warp_fill_fast(const Opt &o, const DpTask &T, DpRes &R, uint8_t 
     return true;
 }
 
-// ksw_backtrack over the fast path's row-major direction bytes (global alignment, no band); one thread
-__device__ void fill_traceback(const DpTask &T, DpRes &R, const uint8_t *dir, uint32_t *ezcig, int ezcap, int32_t *err)
+// ksw_backtrack over the fast path's row-major direction bytes (global alignment, no band).
+// Warp-cooperative: the lanes stage a window of 32 rows x 64 columns that ends at the current cell into shared
+// memory with coalesced 8-byte loads (one row per lane); lane 0 then walks the path inside the window with
+// shared-memory latency instead of one dependent global load per step, and asks for the next window when it leaves.
+constexpr int TBW = 64, TBR = 32;
+struct TbSmem { uint2 w[TBR][TBW / 8]; };
+
+__device__ void fill_traceback(const DpTask &T, DpRes &R, const uint8_t *dir, uint32_t *ezcig, int ezcap, int32_t *err, TbSmem &tb)
 {
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
     const int qlen = T.qlen, tlen = T.tlen, stride = fill_stride(tlen);
-    R.n_cigar = 0; R.cigar = ezcig; R.reach_end = 0;
     uint32_t *c = ezcig; int n = 0;
     int i = tlen - 1, j = qlen - 1, state = 0;
 #define PUSH(op, len) do { if (n == 0 || (uint32_t)(op) != (c[n - 1] & 0xf)) { if (n < ezcap) c[n] = (uint32_t)(len) << 4 | (op); ++n; } else c[n - 1] += (uint32_t)(len) << 4; } while (0)
-    while (i >= 0 && j >= 0) {
-        const uint32_t b = dir[(int64_t)j * stride + i];
-        const int d = !(b & 1) ? 0 : !(b & 2) ? 1 : !(b & 4) ? 2 : !(b & 8) ? 3 : 4;
-        if (state == 0) state = d;
-        else if ((b >> (3 + state)) & 1) state = 0;      // the gap does not continue here
-        if (state == 0) state = d;
-        if (state == 0) { PUSH(0, 1); --i; --j; }
-        else if (state == 1 || state == 3) { PUSH(2, 1); --i; }
-        else { PUSH(1, 1); --j; }
+    while (i >= 0 && j >= 0) {          // i, j are kept uniform across the warp
+        const int c0 = (i - (TBW - 8)) > 0 ? ((i - (TBW - 8)) & ~7) : 0;      // window columns [c0, c0+64), rows [j-31, j]
+        {
+            const int row = j - lane;
+            if (row >= 0) {
+                const uint8_t *src = dir + (int64_t)row * stride + c0;
+#pragma unroll
+                for (int k = 0; k < TBW / 8; ++k)
+                    if (c0 + 8 * k < stride) tb.w[lane][k] = *reinterpret_cast<const uint2 *>(src + 8 * k);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            const uint8_t *wb = reinterpret_cast<const uint8_t *>(&tb.w[0][0]);
+            const int jtop = j - (TBR - 1) > 0 ? j - (TBR - 1) : 0, j0 = j;
+            while (i >= c0 && j >= jtop && i >= 0 && j >= 0) {
+                const uint32_t b = wb[(j0 - j) * TBW + (i - c0)];
+                const int d = !(b & 1) ? 0 : !(b & 2) ? 1 : !(b & 4) ? 2 : !(b & 8) ? 3 : 4;
+                if (state == 0) state = d;
+                else if ((b >> (3 + state)) & 1) state = 0;      // the gap does not continue here
+                if (state == 0) state = d;
+                if (state == 0) { PUSH(0, 1); --i; --j; }
+                else if (state == 1 || state == 3) { PUSH(2, 1); --i; }
+                else { PUSH(1, 1); --j; }
+            }
+        }
+        i = __shfl_sync(FULL, i, 0); j = __shfl_sync(FULL, j, 0);
+        __syncwarp();
     }
-    if (i >= 0) PUSH(2, i + 1);
-    if (j >= 0) PUSH(1, j + 1);
+    if (lane == 0) {
+        if (i >= 0) PUSH(2, i + 1);
+        if (j >= 0) PUSH(1, j + 1);
+        if (n > ezcap) { atomicOr(err, TELR_ERR_CIGCAP); n = 0; }
+        for (int k = 0; k < n >> 1; ++k) { uint32_t t = c[k]; c[k] = c[n - 1 - k]; c[n - 1 - k] = t; }
+        R.n_cigar = n; R.cigar = ezcig; R.reach_end = 0;
+    }
 #undef PUSH
-    if (n > ezcap) { atomicOr(err, TELR_ERR_CIGCAP); n = 0; }
-    for (int k = 0; k < n >> 1; ++k) { uint32_t t = c[k]; c[k] = c[n - 1 - k]; c[n - 1 - k] = t; }
-    R.n_cigar = n;
+    __syncwarp();
 }
 
 }  // namespace telr

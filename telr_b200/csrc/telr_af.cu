@@ -719,10 +719,8 @@ __global__ void __launch_bounds__(AL_THREADS) k_dp_stage(const __grid_constant__
             done_fast = warp_fill_fast(A.o, TS[wid], RS[wid], S.dir, S.bnd, &CS[wid]);
         if (!done_fast) warp_extd2(A.o, TS[wid], RS[wid], S, &CS[wid], A.err);
         __syncwarp();
-        if (lane == 0) {
-            if (done_fast) fill_traceback(TS[wid], RS[wid], S.dir, S.ezcig, S.ezcap, A.err);
-            else extd2_traceback(TS[wid], RS[wid], S.dir, S.ezcig, S.ezcap, A.err);
-        }
+        if (done_fast) fill_traceback(TS[wid], RS[wid], S.dir, S.ezcig, S.ezcap, A.err, *reinterpret_cast<TbSmem *>(DS[wid].H));     // the DP state window is idle during traceback
+        else if (lane == 0) extd2_traceback(TS[wid], RS[wid], S.dir, S.ezcig, S.ezcap, A.err);
         __syncwarp();
         if (lane == 0) {
             const DpRes &R = RS[wid];
