@@ -20,7 +20,7 @@ constexpr int AL_THREADS = 128;
 constexpr int AL_WARPS = AL_THREADS / 32;
 constexpr int DPU = 4;                 // independent 32-cell chunks per lane per DP iteration
 constexpr int DP_SCOLS = 1024;         // columns of DP state kept in shared memory per warp (power of two)
-struct DpWarpSmem { int8_t st[6][DP_SCOLS]; int32_t H[DP_SCOLS]; };
+struct VecSmem;
 
 struct DpScratch {
     int8_t *u, *v, *x, *y, *x2, *y2;   // [maxT] each
@@ -31,6 +31,7 @@ struct DpScratch {
     uint32_t *bnd;                     // fast fill path: pass-boundary values, 3 words per query row pair
     // shared-memory circular window of DP_SCOLS columns (used when the live band fits)
     int8_t *s_state; int32_t *s_H;
+    VecSmem *vsm;                      // same window plus staged sequence codes (vectorised path)
 };
 
 // ---- round-based alignment (BSP): plan (thread/problem) -> dp (warp/task) -> traceback (thread/task) ----
@@ -56,7 +57,7 @@ struct AlignArgs {
     const int32_t *work_list;
     AlWork *work; AlnCtx *actx; DpTask *tasks; DpRes *res;
     uint32_t *cigs;
-    uint8_t *warp_scratch; size_t warp_scratch_stride; int32_t max_tlen, max_qlen, use_fast; int64_t dir_cap;    // per resident warp: spilled DP state + traceback bytes
+    uint8_t *warp_scratch; size_t warp_scratch_stride; int32_t max_tlen, max_qlen, use_fast, use_vec, census; int64_t dir_cap;    // per resident warp: spilled DP state + traceback bytes
     uint8_t *big; int64_t big_cap; int32_t n_big; int32_t *big_lock;                          // shared large traceback buffers
     unsigned long long *rc;      // [2] work queue head
     int32_t *err;
@@ -72,6 +73,11 @@ __device__ __forceinline__ int dp_base(const uint8_t *p, int step, int comp, int
     int b = p[(ptrdiff_t)i * step];
     return comp ? (b >= 4 ? 4 : 3 - b) : b;
 }
+
+}  // namespace telr
+#include "k_extv.cuh"
+namespace telr {
+static_assert(VSC == DP_SCOLS, "shared-memory window size");
 
 struct EzPush {
     uint32_t *c; int n, cap;
@@ -323,13 +329,18 @@ __device__ void extd2_traceback(const DpTask &T, DpRes &R, const uint8_t *p, uin
     R.n_cigar = ep.n;
 }
 
-__device__ __forceinline__ void warp_extd2(const Opt &o, const DpTask &T, DpRes &R, DpScratch &S, unsigned long long *cells_acc, int32_t *err)
+// returns 1 when the vectorised path produced the direction bytes (sign-bit format, vec_stride rows), 0 for the scalar path
+__device__ __forceinline__ int warp_extd2(const Opt &o, const DpTask &T, DpRes &R, DpScratch &S, unsigned long long *cells_acc, int32_t *err)
 {
-    int w = T.w < 0 ? (T.tlen > T.qlen ? T.tlen : T.qlen) : T.w;
-    int ncol = T.qlen < T.tlen ? T.qlen : T.tlen;
-    if (ncol > w + 1) ncol = w + 1;
+    const int ncol = vec_ncol(T.qlen, T.tlen, T.w);
+    if (S.vsm && T.qlen > 0 && T.tlen > 0 && ncol + 40 <= VSC && vec_dir_bytes(T.qlen, T.tlen, T.w) <= S.dir_cap) {
+        bool ok = (T.flag & KSW_RIGHT) ? warp_extd2_vec<true>(o, T, R, *S.vsm, S.dir, cells_acc)
+                                       : warp_extd2_vec<false>(o, T, R, *S.vsm, S.dir, cells_acc);
+        if (ok) return 1;
+    }
     if (S.s_state && ncol + 2 <= DP_SCOLS) warp_extd2_impl<true>(o, T, R, S, cells_acc, err);
     else warp_extd2_impl<false>(o, T, R, S, cells_acc, err);
+    return 0;
 }
 
 // local affine Smith-Waterman score probe with end coordinates (first maximum in target-major order)
@@ -433,7 +444,8 @@ struct AlWarpSmem { AlnCtx c; DpTask task; DpRes res; int more; };
 __global__ void __launch_bounds__(AL_THREADS) k_al_fused(const __grid_constant__ AlignArgs A)
 {
     __shared__ AlWarpSmem WS[AL_WARPS];
-    __shared__ DpWarpSmem DS[AL_WARPS];
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    VecSmem *DS = reinterpret_cast<VecSmem *>(dyn_smem);
     const Opt &o = A.o;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned FULL = 0xffffffffu;
@@ -448,7 +460,7 @@ __global__ void __launch_bounds__(AL_THREADS) k_al_fused(const __grid_constant__
     S.bnd = (uint32_t *)base; base += (((size_t)A.max_qlen + 64) & ~(size_t)15) * 6;
     base = (uint8_t *)(((uintptr_t)base + 255) & ~(uintptr_t)255);
     uint8_t *own_dir = base;
-    S.s_state = &DS[wid].st[0][0]; S.s_H = DS[wid].H;
+    S.s_state = &DS[wid].st[0][0]; S.s_H = DS[wid].H; S.vsm = A.use_vec ? &DS[wid] : nullptr;
     for (;;) {
         int wi = 0;
         if (lane == 0) wi = (int)atomicAdd(&A.rc[2], 1ULL);
@@ -463,12 +475,18 @@ __global__ void __launch_bounds__(AL_THREADS) k_al_fused(const __grid_constant__
         S.ezcig = A.cigs + A.work[wi].ez_off; S.ezcap = A.work[wi].ez_cap;
         __syncwarp();
         for (;;) {
-            if (lane == 0) W.more = aln_next(W.c, W.res, W.task) ? 1 : 0;
+            long long t0 = 0;
+            if (lane == 0) {
+                if (A.census) t0 = clock64();
+                W.more = aln_next(W.c, W.res, W.task) ? 1 : 0;
+                if (A.census) atomicAdd(&A.rc[4], (unsigned long long)(clock64() - t0));
+            }
             __syncwarp();
             if (!W.more) break;
+            if (A.census) t0 = clock64();
             if (W.task.kind == 0) {
                 const bool fast = A.use_fast && fill_fast_ok(W.task);
-                const int64_t need = fast ? (int64_t)W.task.qlen * fill_stride(W.task.tlen) : dp_dir_bytes(W.task.qlen, W.task.tlen, W.task.w);
+                const int64_t need = fast ? (int64_t)W.task.qlen * fill_stride(W.task.tlen) : vec_dir_bytes(W.task.qlen, W.task.tlen, W.task.w);
                 int big_slot = -1;
                 S.dir = own_dir; S.dir_cap = A.dir_cap;
                 if (need > A.dir_cap && need <= A.big_cap && A.n_big > 0) {
@@ -486,14 +504,27 @@ __global__ void __launch_bounds__(AL_THREADS) k_al_fused(const __grid_constant__
                 }
                 bool done_fast = false;
                 if (fast && need <= S.dir_cap) done_fast = warp_fill_fast(o, W.task, W.res, S.dir, S.bnd, A.stat_cells);
-                if (!done_fast) warp_extd2(o, W.task, W.res, S, A.stat_cells, A.err);
+                int vec = 0;
+                if (!done_fast) vec = warp_extd2(o, W.task, W.res, S, A.stat_cells, A.err);
                 __syncwarp();
+                const int path = done_fast ? 0 : vec ? 1 : 2;
+                if (A.census && lane == 0) {
+                    long long t1 = clock64();
+                    atomicAdd(&A.rc[5 + path], (unsigned long long)(t1 - t0));
+                    atomicAdd(&A.rc[12 + path], 1ULL);
+                    atomicAdd(&A.rc[16 + path], (unsigned long long)W.task.qlen * (unsigned long long)W.task.tlen);
+                    t0 = t1;
+                }
                 if (done_fast) fill_traceback(W.task, W.res, S.dir, S.ezcig, S.ezcap, A.err, *reinterpret_cast<TbSmem *>(DS[wid].H));     // the DP state window is idle during traceback
                 if (lane == 0) {
-                    if (!done_fast) extd2_traceback(W.task, W.res, S.dir, S.ezcig, S.ezcap, A.err);
+                    if (!done_fast) { if (vec) extd2_traceback_vec(W.task, W.res, S.dir, S.ezcig, S.ezcap, A.err); else extd2_traceback(W.task, W.res, S.dir, S.ezcig, S.ezcap, A.err); }
                     if (big_slot >= 0) { __threadfence(); atomicExch(&A.big_lock[big_slot], 0); }
+                    if (A.census) atomicAdd(&A.rc[8 + path], (unsigned long long)(clock64() - t0));
                 }
-            } else warp_ll(o, W.task, W.res, S, A.stat_cells);
+            } else {
+                warp_ll(o, W.task, W.res, S, A.stat_cells);
+                if (A.census && lane == 0) { atomicAdd(&A.rc[11], (unsigned long long)(clock64() - t0)); atomicAdd(&A.rc[15], 1ULL); }
+            }
             __syncwarp();
         }
         {   // coroutine state: shared -> global (k_al_finish continues from PH_FINISH)

@@ -1,0 +1,267 @@
+// k_extv.cuh — vectorised form of the general two-piece-affine DP (kernel (d)): extensions with exact max tracking and
+// z-drop, banded or not, left- or right-aligned gaps.  Same anti-diagonal sweep and shared-memory circular state window as
+// warp_extd2_impl<true>, but every lane owns a group of 4 consecutive columns per step: state arrays are read/written
+// as 32-bit words (4 x int8), unpacked to two 16x2 registers and run through the packed recurrence of k_fill.cuh;
+// target/query codes are staged in shared memory in chunks of 32.  Direction bytes use the sign-bit format:
+//   bits 0-3: "below the maximum" for (s,a,b,a2) [left-aligned gaps] or (a,b,a2,b2) [right-aligned]
+//   bits 4-7: "gap does not continue" for x,y,x2,y2
+// Requests that contain an ambiguous base, or whose band does not fit the window, return false and take the scalar path.
+#pragma once
+#include "k_fill.cuh"
+
+namespace telr {
+
+constexpr int VSC = 1024;             // shared-memory window (columns / rows), power of two
+struct VecSmem { int8_t st[6][VSC]; int32_t H[VSC]; uint8_t tb[VSC]; uint8_t qb[VSC]; };
+
+__host__ __device__ __forceinline__ int vec_ncol(int qlen, int tlen, int w_in)
+{
+    int w = w_in < 0 ? (tlen > qlen ? tlen : qlen) : w_in;
+    int ncol = qlen < tlen ? qlen : tlen;
+    if (ncol > w + 1) ncol = w + 1;
+    return ncol;
+}
+__host__ __device__ __forceinline__ int vec_stride(int qlen, int tlen, int w_in) { return (vec_ncol(qlen, tlen, w_in) + 11) & ~3; }
+__host__ __device__ __forceinline__ int64_t vec_dir_bytes(int qlen, int tlen, int w_in)
+{
+    if (qlen <= 0 || tlen <= 0) return 0;
+    return (int64_t)(qlen + tlen - 1) * vec_stride(qlen, tlen, w_in);
+}
+
+template <bool RIGHT>
+__device__ bool warp_extd2_vec(const Opt &o, const DpTask &T, DpRes &R, VecSmem &M, uint8_t *p, unsigned long long *cells_acc)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    constexpr int CM = VSC - 1;
+    const int qlen = T.qlen, tlen = T.tlen, flag = T.flag;
+    int q = o.q, e = o.e, q2 = o.q2, e2 = o.e2;
+    if (q2 + e2 < q + e) { int t = q; q = q2; q2 = t; t = e; e = e2; e2 = t; }
+    const int qe = q + e, qe2 = q2 + e2;
+    const int w = T.w < 0 ? (tlen > qlen ? tlen : qlen) : T.w;
+    const int ncol = vec_ncol(qlen, tlen, T.w), vstride = vec_stride(qlen, tlen, T.w);
+    int LT = e != e2 ? (q2 - q) / (e - e2) - 1 : 0;
+    if (q2 + e2 + LT * e2 > q + e + LT * e) ++LT;
+    const int LD = LT * (e - e2) - (q2 - q) - e2;
+    const bool approx = flag & KSW_APPROX_MAX;
+    const uint32_t MAT = pk1(o.a), MIS = pk1(-o.b), NE1 = pk1(-e), NQE1 = pk1(-qe), NE2 = pk1(-e2), NQE2 = pk1(-qe2);
+    const uint32_t QC1 = pk1(q - 1 + (RIGHT ? 1 : 0)), QC2 = pk1(q2 - 1 + (RIGHT ? 1 : 0));
+    int8_t *u = M.st[0], *v = M.st[1], *x = M.st[2], *y = M.st[3], *x2 = M.st[4], *y2 = M.st[5];
+    int32_t *H = M.H;
+    (void)ncol;
+    int pst = -1, pen = -1, t_loaded = 0, q_loaded = 0;
+    int32_t ez_max = 0, ez_max_t = -1, ez_max_q = -1, ez_mqe = KSW_NEG_INF, ez_mqe_t = -1, ez_mte = KSW_NEG_INF, ez_mte_q = -1;
+    int32_t ez_score = KSW_NEG_INF, zdropped = 0, H0 = 0, last_H0_t = 0;
+    unsigned long long cells = 0;
+    const int nr = qlen + tlen - 1;
+    bool bail = false;
+    for (int r = 0; r < nr; ++r) {
+        int st = 0, en = tlen - 1;
+        if (st < r - qlen + 1) st = r - qlen + 1;
+        if (en > r) en = r;
+        if (st < (r - w + 1) >> 1) st = (r - w + 1) >> 1;
+        if (en > (r + w) >> 1) en = (r + w) >> 1;
+        if (st > en) { zdropped = 1; break; }
+        cells += (unsigned long long)(en - st + 1);
+        // ---- stage sequence codes 32 at a time (columns up to en, rows up to r - st) ----
+        while (t_loaded <= en) {
+            int i = t_loaded + lane, c = i < tlen ? dp_base(T.t, T.tstep, 0, i) : 0;
+            if (__any_sync(FULL, c > 3)) { bail = true; break; }
+            M.tb[i & CM] = (uint8_t)c;
+            t_loaded += 32;
+        }
+        while (!bail && q_loaded <= r - st) {
+            int i = q_loaded + lane, c = i < qlen ? dp_base(T.q, T.qstep, T.qcomp, i) : 0;
+            if (__any_sync(FULL, c > 3)) { bail = true; break; }
+            M.qb[i & CM] = (uint8_t)c;
+            q_loaded += 32;
+        }
+        if (bail) break;
+        // ---- seeds: entering column, top boundary, left neighbour of the first cell ----
+        const int bnd = r == 0 ? -q - e : r < LT ? -e : r == LT ? LD : -e2;
+        if (lane == 0) {
+            if (en > pen) {
+                const int se = en & CM;
+                u[se] = v[se] = x[se] = y[se] = (int8_t)(-q - e);
+                x2[se] = y2[se] = (int8_t)(-q2 - e2);
+            }
+            if (en == r) { y[r & CM] = (int8_t)(-q - e); y2[r & CM] = (int8_t)(-q2 - e2); u[r & CM] = (int8_t)bnd; }
+            const int sl = (st - 1) & CM;
+            if (st == 0) { x[sl] = (int8_t)(-q - e); x2[sl] = (int8_t)(-q2 - e2); v[sl] = (int8_t)bnd; }
+            else if (!(st - 1 >= pst && st - 1 <= pen)) { x[sl] = (int8_t)(-q - e); x2[sl] = (int8_t)(-q2 - e2); v[sl] = (int8_t)(-q - e); }
+        }
+        __syncwarp();
+        const int gs = st >> 2, ge = en >> 2, nchunk = ((ge - gs) >> 5) + 1;
+        uint8_t *pr = p + (int64_t)r * vstride - (gs << 2);
+        for (int cb = nchunk - 1; cb >= 0; --cb) {
+            const int g = gs + (cb << 5) + lane;
+            const bool act = g <= ge;
+            uint32_t Wu = 0, Wv = 0, Wx = 0, Wy = 0, Wx2 = 0, Wy2 = 0, Lv4 = 0, Lx4 = 0, Lx24 = 0, X4 = 0;
+            if (act) {
+                const int gw = (g << 2) & CM, gl = ((g << 2) - 4) & CM;
+                Wu = *reinterpret_cast<const uint32_t *>(u + gw); Wy = *reinterpret_cast<const uint32_t *>(y + gw); Wy2 = *reinterpret_cast<const uint32_t *>(y2 + gw);
+                Wv = *reinterpret_cast<const uint32_t *>(v + gw); Wx = *reinterpret_cast<const uint32_t *>(x + gw); Wx2 = *reinterpret_cast<const uint32_t *>(x2 + gw);
+                Lv4 = __byte_perm(*reinterpret_cast<const uint32_t *>(v + gl), Wv, 0x6543);
+                Lx4 = __byte_perm(*reinterpret_cast<const uint32_t *>(x + gl), Wx, 0x6543);
+                Lx24 = __byte_perm(*reinterpret_cast<const uint32_t *>(x2 + gl), Wx2, 0x6543);
+                const uint32_t TW = *reinterpret_cast<const uint32_t *>(M.tb + gw);
+                const int j0 = r - (g << 2);       // row of the group's first column; next columns are one row up each
+                const uint32_t QW = (uint32_t)M.qb[j0 & CM] | (uint32_t)M.qb[(j0 - 1) & CM] << 8 | (uint32_t)M.qb[(j0 - 2) & CM] << 16 | (uint32_t)M.qb[(j0 - 3) & CM] << 24;
+                X4 = TW ^ QW;
+            }
+            __syncwarp();
+            if (act) {
+                uint32_t nU[2], nV[2], nX[2], nY[2], nX2[2], nY2[2], F[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t sxl = h ? 0xB3A2 : 0x9180, zxl = h ? 0x4342 : 0x4140;
+                    const uint32_t up_u = prmt(Wu, Wu, sxl), up_y = prmt(Wy, Wy, sxl), up_y2 = prmt(Wy2, Wy2, sxl);
+                    const uint32_t Lv = prmt(Lv4, Lv4, sxl), Lx = prmt(Lx4, Lx4, sxl), Lx2 = prmt(Lx24, Lx24, sxl);
+                    const uint32_t ne = __vminu2(__byte_perm(X4, 0, zxl), 0x00010001u);
+                    const uint32_t msk = ne * 0xffffu;
+                    const uint32_t S = (msk & MIS) | (~msk & MAT);
+                    const uint32_t A = __vadd2(Lx, Lv), A2 = __vadd2(Lx2, Lv), B = __vadd2(up_y, up_u), B2 = __vadd2(up_y2, up_u);
+                    uint32_t Z = __vimax3_s16x2(S, A, B);
+                    Z = __vimax3_s16x2(Z, A2, B2);
+                    const uint32_t DS = __vsub2(S, Z), DA = __vsub2(A, Z), DB = __vsub2(B, Z), DA2 = __vsub2(A2, Z), DB2 = __vsub2(B2, Z);
+                    nU[h] = __vsub2(Z, Lv); nV[h] = __vsub2(Z, up_u);
+                    nX[h] = __viaddmax_s16x2(DA, NE1, NQE1); nY[h] = __viaddmax_s16x2(DB, NE1, NQE1);
+                    nX2[h] = __viaddmax_s16x2(DA2, NE2, NQE2); nY2[h] = __viaddmax_s16x2(DB2, NE2, NQE2);
+                    const uint32_t cx = __vadd2(DA, QC1), cy = __vadd2(DB, QC1), cx2 = __vadd2(DA2, QC2), cy2 = __vadd2(DB2, QC2);
+                    uint32_t acc;
+                    if (!RIGHT) { acc = prmt(DS, DA, 0xFDB9) & 0x02020101u; acc |= prmt(DB, DA2, 0xFDB9) & 0x08080404u; }
+                    else        { acc = prmt(DA, DB, 0xFDB9) & 0x02020101u; acc |= prmt(DA2, DB2, 0xFDB9) & 0x08080404u; }
+                    acc |= prmt(cx, cy, 0xFDB9) & 0x20201010u;
+                    acc |= prmt(cx2, cy2, 0xFDB9) & 0x80804040u;
+                    F[h] = acc | (acc >> 16);
+                }
+                // in-band byte mask of this group (columns outside [st,en] keep their old state)
+                const int c0 = g << 2;
+                uint32_t BM = 0xffffffffu;
+                if (c0 < st) BM &= 0xffffffffu << (8 * (st - c0));
+                if (c0 + 3 > en) BM &= 0xffffffffu >> (8 * (c0 + 3 - en));
+                const int gw = c0 & CM;
+#define PACK8(a) __byte_perm((a)[0], (a)[1], 0x6420)
+                *reinterpret_cast<uint32_t *>(u + gw) = (PACK8(nU) & BM) | (Wu & ~BM);
+                *reinterpret_cast<uint32_t *>(v + gw) = (PACK8(nV) & BM) | (Wv & ~BM);
+                *reinterpret_cast<uint32_t *>(x + gw) = (PACK8(nX) & BM) | (Wx & ~BM);
+                *reinterpret_cast<uint32_t *>(y + gw) = (PACK8(nY) & BM) | (Wy & ~BM);
+                *reinterpret_cast<uint32_t *>(x2 + gw) = (PACK8(nX2) & BM) | (Wx2 & ~BM);
+                *reinterpret_cast<uint32_t *>(y2 + gw) = (PACK8(nY2) & BM) | (Wy2 & ~BM);
+#undef PACK8
+                *reinterpret_cast<uint32_t *>(pr + c0) = __byte_perm(F[0], F[1], 0x5410);
+            }
+            __syncwarp();
+        }
+        if (!approx) {
+            int32_t max_H, max_t, Hen, Hst;
+            if (r > 0) {
+                Hen = en > 0 ? H[(en - 1) & CM] + u[en & CM] : H[en & CM] + v[en & CM];
+                __syncwarp();
+                const int en1 = st + (en - st) / 4 * 4;
+                int32_t bh = KSW_NEG_INF * 2; int brank = 0x7fffffff, bt = -1, hst = 0;
+                for (int t = st + lane; t < en; t += 32) {
+                    int32_t h = H[t & CM] + v[t & CM];
+                    H[t & CM] = h;
+                    if (t == st) hst = h;
+                    int rank = t < en1 ? 1 + (((t - st) & 3) << 20) + ((t - st) >> 2) : 1 + (4 << 20) + (t - en1);
+                    if (h > bh || (h == bh && rank < brank)) bh = h, brank = rank, bt = t;
+                }
+                if (lane == 0) { H[en & CM] = Hen; if (Hen >= bh) bh = Hen, brank = 0, bt = en; }
+#pragma unroll
+                for (int d = 16; d; d >>= 1) {
+                    int32_t oh = __shfl_xor_sync(FULL, bh, d); int orank = __shfl_xor_sync(FULL, brank, d), ot = __shfl_xor_sync(FULL, bt, d);
+                    if (oh > bh || (oh == bh && orank < brank)) bh = oh, brank = orank, bt = ot;
+                }
+                max_H = bh, max_t = bt;
+                Hst = st == en ? Hen : __shfl_sync(FULL, hst, 0);
+                __syncwarp();
+            } else {
+                Hen = Hst = (int32_t)v[0] - qe;
+                if (lane == 0) H[0] = Hen;
+                max_H = Hen, max_t = 0;
+                __syncwarp();
+            }
+            if (en == tlen - 1 && Hen > ez_mte) ez_mte = Hen, ez_mte_q = r - en;
+            if (r - st == qlen - 1 && Hst > ez_mqe) ez_mqe = Hst, ez_mqe_t = st;
+            bool stop = false;
+            if (max_H > ez_max) ez_max = max_H, ez_max_t = max_t, ez_max_q = r - max_t;
+            else if (max_t >= ez_max_t && r - max_t >= ez_max_q) {
+                int tl = max_t - ez_max_t, ql = (r - max_t) - ez_max_q, l = tl > ql ? tl - ql : ql - tl;
+                if (T.zdrop >= 0 && ez_max - max_H > T.zdrop + l * e2) zdropped = 1, stop = true;
+            }
+            if (stop) break;
+            if (r == nr - 1 && en == tlen - 1) ez_score = Hen;
+        } else {
+            if (r > 0) {
+                if (last_H0_t >= st && last_H0_t <= en && last_H0_t + 1 >= st && last_H0_t + 1 <= en) {
+                    int d0 = v[last_H0_t & CM], d1 = u[(last_H0_t + 1) & CM];
+                    if (d0 > d1) H0 += d0; else H0 += d1, ++last_H0_t;
+                } else if (last_H0_t >= st && last_H0_t <= en) H0 += v[last_H0_t & CM];
+                else ++last_H0_t, H0 += u[last_H0_t & CM];
+            } else H0 = (int32_t)v[0] - qe, last_H0_t = 0;
+            if (r == nr - 1 && en == tlen - 1) ez_score = H0;
+        }
+        pst = st, pen = en;
+    }
+    if (bail) return false;
+    if (lane == 0) {
+        atomicAdd(cells_acc, cells);
+        res_reset(R);
+        R.max = ez_max; R.max_t = ez_max_t; R.max_q = ez_max_q; R.mqe = ez_mqe; R.mqe_t = ez_mqe_t;
+        R.mte = ez_mte; R.mte_q = ez_mte_q; R.score = ez_score; R.zdropped = zdropped;
+    }
+    __syncwarp();
+    return true;
+}
+
+// ksw_backtrack over the sign-bit direction bytes of warp_extd2_vec; sequential, one thread
+__device__ void extd2_traceback_vec(const DpTask &T, DpRes &R, const uint8_t *p, uint32_t *ezcig, int ezcap, int32_t *err)
+{
+    const int qlen = T.qlen, tlen = T.tlen, flag = T.flag;
+    const bool right = flag & KSW_RIGHT;
+    R.n_cigar = 0; R.cigar = ezcig; R.reach_end = 0;
+    if (qlen <= 0 || tlen <= 0) return;
+    const int w = T.w < 0 ? (tlen > qlen ? tlen : qlen) : T.w;
+    const int vstride = vec_stride(qlen, tlen, T.w);
+    int i0 = -1, j0 = -1;
+    if (!R.zdropped && !(flag & KSW_EXTZ_ONLY)) i0 = tlen - 1, j0 = qlen - 1;
+    else if (!R.zdropped && (flag & KSW_EXTZ_ONLY) && R.mqe + T.end_bonus > R.max) R.reach_end = 1, i0 = R.mqe_t, j0 = qlen - 1;
+    else if (R.max_t >= 0 && R.max_q >= 0) i0 = R.max_t, j0 = R.max_q;
+    if (i0 < 0 || j0 < 0) return;
+    uint32_t *c = ezcig; int n = 0;
+#define PUSH(op, len) do { if (n == 0 || (uint32_t)(op) != (c[n - 1] & 0xf)) { if (n < ezcap) c[n] = (uint32_t)(len) << 4 | (op); ++n; } else c[n - 1] += (uint32_t)(len) << 4; } while (0)
+    int i = i0, j = j0, state = 0;
+    while (i >= 0 && j >= 0) {
+        int r = i + j, force_state = -1;
+        int st = 0, en = tlen - 1;
+        if (st < r - qlen + 1) st = r - qlen + 1;
+        if (en > r) en = r;
+        if (st < (r - w + 1) >> 1) st = (r - w + 1) >> 1;
+        if (en > (r + w) >> 1) en = (r + w) >> 1;
+        if (i < st) force_state = 2;
+        if (i > en) force_state = 1;
+        int d = 0; uint32_t b = 0;
+        if (force_state < 0) {
+            b = p[(int64_t)r * vstride + (i - (st & ~3))];
+            if (!right) d = !(b & 1) ? 0 : !(b & 2) ? 1 : !(b & 4) ? 2 : !(b & 8) ? 3 : 4;
+            else d = !(b & 8) ? 4 : !(b & 4) ? 3 : !(b & 2) ? 2 : !(b & 1) ? 1 : 0;
+        }
+        if (state == 0) state = d;
+        else if (force_state >= 0 || ((b >> (3 + state)) & 1)) state = 0;
+        if (state == 0) state = d;
+        if (force_state >= 0) state = force_state;
+        if (state == 0) { PUSH(0, 1); --i; --j; }
+        else if (state == 1 || state == 3) { PUSH(2, 1); --i; }
+        else { PUSH(1, 1); --j; }
+    }
+    if (i >= 0) PUSH(2, i + 1);
+    if (j >= 0) PUSH(1, j + 1);
+#undef PUSH
+    if (n > ezcap) { atomicOr(err, TELR_ERR_CIGCAP); n = 0; }
+    if (!(flag & KSW_REV_CIGAR))
+        for (int k = 0; k < n >> 1; ++k) { uint32_t t = c[k]; c[k] = c[n - 1 - k]; c[n - 1 - k] = t; }
+    R.n_cigar = n;
+}
+
+}  // namespace telr

@@ -21,6 +21,13 @@ namespace telr {
 constexpr int FC = 8;                 // columns per lane
 constexpr int FW = 32 * FC;           // columns per pass
 
+// prmt.b32 in default mode: selector nibble bit 3 replicates the sign of the selected byte (__byte_perm drops that bit)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
 __device__ __forceinline__ uint32_t pk2(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
 __device__ __forceinline__ uint32_t pk1(int v) { return pk2(v, v); }
 __device__ __forceinline__ int lo16(uint32_t v) { return (int)(int16_t)(v & 0xffffu); }
@@ -129,10 +136,10 @@ __device__ bool warp_fill_fast(const Opt &o, const DpTask &T, DpRes &R, uint8_t 
                     const uint32_t nx2 = __viaddmax_s16x2(DA2, NE2, NQE2), ny2 = __viaddmax_s16x2(DB2, NE2, NQE2);
                     const uint32_t cx = __vadd2(DA, QM1), cy = __vadd2(DB, QM1), cx2 = __vadd2(DA2, Q2M1), cy2 = __vadd2(DB2, Q2M1);
                     // 8 sign bits per cell -> one byte per cell
-                    uint32_t acc = __byte_perm(DS, DA, 0xFDB9) & 0x02020101u;
-                    acc |= __byte_perm(DB, DA2, 0xFDB9) & 0x08080404u;
-                    acc |= __byte_perm(cx, cy, 0xFDB9) & 0x20201010u;
-                    acc |= __byte_perm(cx2, cy2, 0xFDB9) & 0x80804040u;
+                    uint32_t acc = prmt(DS, DA, 0xFDB9) & 0x02020101u;
+                    acc |= prmt(DB, DA2, 0xFDB9) & 0x08080404u;
+                    acc |= prmt(cx, cy, 0xFDB9) & 0x20201010u;
+                    acc |= prmt(cx2, cy2, 0xFDB9) & 0x80804040u;
                     const uint32_t f = acc | (acc >> 16);
                     if (k < FC) {
                         if (k < 4) rF0 |= (f & 0xffu) << (8 * (k & 3)); else rF1 |= (f & 0xffu) << (8 * (k & 3));

@@ -50,7 +50,7 @@ struct telr_af_ctx {
     long long launches = 0;
     size_t ws_limit = 0;
     int depth_mode = 1;
-    int use_fast = 1;
+    int use_fast = 1, use_vec = 1, census = 0;
     int64_t chunk_bases = 0;
     int64_t dir_cap = 8 << 20;
     // device buffers
@@ -305,11 +305,11 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
     const int nwk = std::max(n_work, 1);
     ENS(ctx->b_alwork, (size_t)nwk * sizeof(AlWork)); ENS(ctx->b_alctx, (size_t)nwk * sizeof(AlnCtx)); ENS(ctx->b_altask, (size_t)nwk * sizeof(DpTask));
     ENS(ctx->b_alres, (size_t)nwk * sizeof(DpRes)); ENS(ctx->b_alsz, (size_t)(nwk + 1) * 4); ENS(ctx->b_aloff, (size_t)(nwk + 2) * 8);
-    ENS(ctx->b_rc, 64);
+    ENS(ctx->b_rc, 256);
     const int al_grid = std::max(1, std::min((n_work + AL_WARPS - 1) / AL_WARPS, sm * 4));
     {
         size_t maxT = ((size_t)max_tlen + 64) & ~(size_t)15;
-        aa.max_tlen = max_tlen; aa.max_qlen = max_qlen; aa.dir_cap = ctx->dir_cap; aa.use_fast = ctx->use_fast;
+        aa.max_tlen = max_tlen; aa.max_qlen = max_qlen; aa.dir_cap = ctx->dir_cap; aa.use_fast = ctx->use_fast; aa.use_vec = ctx->use_vec; aa.census = ctx->census;
         aa.warp_scratch_stride = (maxT * (6 + 4 + 24) + (((size_t)max_qlen + 64) & ~(size_t)15) * 6 + 512 + (size_t)ctx->dir_cap + 255) & ~(size_t)255;
         ENS(ctx->b_alws, aa.warp_scratch_stride * (size_t)al_grid * AL_WARPS);
         aa.warp_scratch = ctx->b_alws.as<uint8_t>();
@@ -338,10 +338,11 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
         CK(cudaStreamSynchronize(st));
         ENS(ctx->b_cigs, (size_t)(cig_total + 16) * 4);
         aa.cigs = ctx->b_cigs.as<uint32_t>();
-        CK(cudaMemsetAsync(ctx->b_rc.p, 0, 64, st));
+        CK(cudaMemsetAsync(ctx->b_rc.p, 0, 256, st));
         k_al_offsets<<<tb, 128, 0, st>>>(aa, ctx->b_aloff.as<int64_t>());
         k_al_init<<<tb, 128, 0, st>>>(aa);
-        k_al_fused<<<al_grid, AL_THREADS, 0, st>>>(aa);
+        CK(cudaFuncSetAttribute(k_al_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(AL_WARPS * sizeof(VecSmem))));
+        k_al_fused<<<al_grid, AL_THREADS, AL_WARPS * sizeof(VecSmem), st>>>(aa);
         k_al_finish<<<tb, 128, 0, st>>>(aa);
     }
     CK(cudaEventRecord(ctx->ev[4], st));
@@ -372,6 +373,14 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
     if (err) {
         fprintf(stderr, "[telr_af] device pipeline flagged error mask 0x%x (1 regcap 2 cigcap 4 kcap 8 dircap 16 idxcap 32 blkcap 64 alncap)\n", err);
         return (err & 16) ? TELR_EUNSUPPORTED : TELR_ECAP;
+    }
+    if (ctx->census && n_work > 0) {     // where the alignment kernel's warp cycles go (diagnostic, TELR_CENSUS=1)
+        unsigned long long rc[32];
+        CK(cudaMemcpy(rc, ctx->b_rc.p, sizeof(rc), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[census] cycles(M): coroutine %.1f | fill dp %.1f tb %.1f | vec dp %.1f tb %.1f | scalar dp %.1f tb %.1f | ll %.1f\n",
+                rc[4] / 1e6, rc[5] / 1e6, rc[8] / 1e6, rc[6] / 1e6, rc[9] / 1e6, rc[7] / 1e6, rc[10] / 1e6, rc[11] / 1e6);
+        fprintf(stderr, "[census] tasks: fill %llu vec %llu scalar %llu ll %llu | q*t (M): fill %.1f vec %.1f scalar %.1f\n",
+                rc[12], rc[13], rc[14], rc[15], rc[16] / 1e6, rc[17] / 1e6, rc[18] / 1e6);
     }
     stats->dp_cells += hc[C_CELLS]; stats->n_dp_tasks += hc[C_TASKS]; stats->n_anchors += hc[C_ANCH]; stats->n_minimizers += n_mz;
     stats->n_aln_blocks += hc[C_NBLK];
@@ -463,6 +472,10 @@ int telr_af_create(telr_af_ctx **out, int device, size_t workspace_bytes)
     if (cb) ctx->chunk_bases = (int64_t)atoll(cb) << 20;
     const char *uf = getenv("TELR_FAST_FILL");
     if (uf) ctx->use_fast = atoi(uf) ? 1 : 0;
+    const char *uv = getenv("TELR_VEC_EXT");
+    if (uv) ctx->use_vec = atoi(uv) ? 1 : 0;
+    const char *cs = getenv("TELR_CENSUS");
+    if (cs) ctx->census = atoi(cs) ? 1 : 0;
     const char *pm = getenv("TELR_POOL_MB");
     if (pm) ctx->pool_cap = (int64_t)atoll(pm) << 20;
     const char *dc = getenv("TELR_DIR_MB");
@@ -678,7 +691,7 @@ int telr_af_depth_af(telr_af_ctx *ctx, int32_t n_loci, const int32_t *contig_len
 struct DpStageArgs {
     Opt o; int32_t n_tasks; const telr_dp_task *tasks; const uint8_t *q, *t; telr_dp_out *out;
     uint32_t *cig; unsigned long long *n_cig; int64_t cig_cap;
-    uint8_t *warp_scratch; size_t stride; int32_t maxQ, maxT, use_fast; int64_t dir_cap;
+    uint8_t *warp_scratch; size_t stride; int32_t maxQ, maxT, use_fast, use_vec; int64_t dir_cap;
     int32_t *work_counter, *err; unsigned long long *cells;
 };
 
@@ -687,7 +700,8 @@ __global__ void __launch_bounds__(AL_THREADS) k_dp_stage(const __grid_constant__
     __shared__ DpRes RS[AL_WARPS];
     __shared__ DpTask TS[AL_WARPS];
     __shared__ unsigned long long CS[AL_WARPS];
-    __shared__ DpWarpSmem DS[AL_WARPS];
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    VecSmem *DS = reinterpret_cast<VecSmem *>(dyn_smem);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint8_t *base = A.warp_scratch + (size_t)(blockIdx.x * AL_WARPS + wid) * A.stride;
     const size_t maxT = (size_t)A.maxT, maxQ = (size_t)A.maxQ;
@@ -700,7 +714,7 @@ __global__ void __launch_bounds__(AL_THREADS) k_dp_stage(const __grid_constant__
     S.bnd = (uint32_t *)base; base += maxQ * 6;
     base = (uint8_t *)(((uintptr_t)base + 255) & ~(uintptr_t)255);
     S.dir = base; S.dir_cap = A.dir_cap;
-    S.s_state = &DS[wid].st[0][0]; S.s_H = DS[wid].H;
+    S.s_state = &DS[wid].st[0][0]; S.s_H = DS[wid].H; S.vsm = A.use_vec ? &DS[wid] : nullptr;
     for (;;) {
         int i = 0;
         if (lane == 0) i = atomicAdd(A.work_counter, 1);
@@ -717,10 +731,11 @@ __global__ void __launch_bounds__(AL_THREADS) k_dp_stage(const __grid_constant__
         bool done_fast = false;
         if (A.use_fast && fill_fast_ok(TS[wid]) && (int64_t)TS[wid].qlen * fill_stride(TS[wid].tlen) <= S.dir_cap)
             done_fast = warp_fill_fast(A.o, TS[wid], RS[wid], S.dir, S.bnd, &CS[wid]);
-        if (!done_fast) warp_extd2(A.o, TS[wid], RS[wid], S, &CS[wid], A.err);
+        int vec = 0;
+        if (!done_fast) vec = warp_extd2(A.o, TS[wid], RS[wid], S, &CS[wid], A.err);
         __syncwarp();
         if (done_fast) fill_traceback(TS[wid], RS[wid], S.dir, S.ezcig, S.ezcap, A.err, *reinterpret_cast<TbSmem *>(DS[wid].H));     // the DP state window is idle during traceback
-        else if (lane == 0) extd2_traceback(TS[wid], RS[wid], S.dir, S.ezcig, S.ezcap, A.err);
+        else if (lane == 0) { if (vec) extd2_traceback_vec(TS[wid], RS[wid], S.dir, S.ezcig, S.ezcap, A.err); else extd2_traceback(TS[wid], RS[wid], S.dir, S.ezcig, S.ezcap, A.err); }
         __syncwarp();
         if (lane == 0) {
             const DpRes &R = RS[wid];
@@ -749,7 +764,7 @@ extern "C" int telr_af_dp(telr_af_ctx *ctx, int32_t preset, int32_t n_tasks, con
     int maxQ = 0, maxT = 0;
     for (int i = 0; i < n_tasks; ++i) { maxQ = std::max(maxQ, tasks[i].qlen); maxT = std::max(maxT, tasks[i].tlen); }
     A.maxQ = (maxQ + 64) & ~15; A.maxT = (maxT + 64) & ~15; A.dir_cap = ctx->dir_cap;
-    A.use_fast = ctx->use_fast;
+    A.use_fast = ctx->use_fast; A.use_vec = ctx->use_vec;
     A.stride = ((size_t)A.maxT * (6 + 4 + 24) + (size_t)(A.maxQ + A.maxT) * 4 + (size_t)A.maxQ * 6 + 512 + (size_t)A.dir_cap + 255) & ~(size_t)255;
     const int grid = std::max(1, std::min((n_tasks + AL_WARPS - 1) / AL_WARPS, ctx->sm_count * 4));
     ENS(ctx->b_alws, A.stride * (size_t)grid * AL_WARPS);
@@ -764,7 +779,8 @@ extern "C" int telr_af_dp(telr_af_ctx *ctx, int32_t preset, int32_t n_tasks, con
     A.out = ctx->b_in[3].as<telr_dp_out>(); A.cig = ctx->b_cigout.as<uint32_t>(); A.n_cig = (unsigned long long *)(ctr + C_NCIG); A.cig_cap = cigar_cap;
     A.warp_scratch = ctx->b_alws.as<uint8_t>(); A.work_counter = (int32_t *)(ctr + C_WORK_ALIGN); A.err = (int32_t *)(ctr + C_ERR);
     A.cells = (unsigned long long *)(ctr + C_CELLS);
-    k_dp_stage<<<grid, AL_THREADS, 0, st>>>(A);
+    CK(cudaFuncSetAttribute(k_dp_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(AL_WARPS * sizeof(VecSmem))));
+    k_dp_stage<<<grid, AL_THREADS, AL_WARPS * sizeof(VecSmem), st>>>(A);
     int64_t hc[C_SLOTS];
     CK(cudaMemcpyAsync(hc, ctr, sizeof(hc), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(out, ctx->b_in[3].p, (size_t)n_tasks * sizeof(telr_dp_out), cudaMemcpyDeviceToHost, st));
