@@ -18,6 +18,7 @@ namespace telr {
 
 constexpr int AL_THREADS = 128;
 constexpr int AL_WARPS = AL_THREADS / 32;
+constexpr int AL_BLOCKS_PER_SM = 4;     // 16 resident warps per SM: the kernel is issue-bound (profiles/), more warps only add spills
 constexpr int DPU = 4;                 // independent 32-cell chunks per lane per DP iteration
 constexpr int DP_SCOLS = 1024;         // columns of DP state kept in shared memory per warp (power of two)
 struct VecSmem;
@@ -30,7 +31,7 @@ struct DpScratch {
     uint32_t *ezcig; int32_t ezcap;
     uint32_t *bnd;                     // fast fill path: pass-boundary values, 3 words per query row pair
     // shared-memory circular window of DP_SCOLS columns (used when the live band fits)
-    int8_t *s_state; int32_t *s_H;
+    int8_t *s_state; int32_t *s_H; const uint2 *stab;
     VecSmem *vsm;                      // same window plus staged sequence codes (vectorised path)
 };
 
@@ -77,7 +78,7 @@ __device__ __forceinline__ int dp_base(const uint8_t *p, int step, int comp, int
 }  // namespace telr
 #include "k_extv.cuh"
 namespace telr {
-static_assert(VSC == DP_SCOLS, "shared-memory window size");
+static_assert(sizeof(TbSmem) <= sizeof(((VecSmem *)0)->H), "fill traceback window aliases the idle H window");
 
 struct EzPush {
     uint32_t *c; int n, cap;
@@ -333,13 +334,12 @@ __device__ void extd2_traceback(const DpTask &T, DpRes &R, const uint8_t *p, uin
 __device__ __forceinline__ int warp_extd2(const Opt &o, const DpTask &T, DpRes &R, DpScratch &S, unsigned long long *cells_acc, int32_t *err)
 {
     const int ncol = vec_ncol(T.qlen, T.tlen, T.w);
-    if (S.vsm && T.qlen > 0 && T.tlen > 0 && ncol + 40 <= VSC && vec_dir_bytes(T.qlen, T.tlen, T.w) <= S.dir_cap) {
-        bool ok = (T.flag & KSW_RIGHT) ? warp_extd2_vec<true>(o, T, R, *S.vsm, S.dir, cells_acc)
-                                       : warp_extd2_vec<false>(o, T, R, *S.vsm, S.dir, cells_acc);
+    if (S.vsm && T.qlen > 0 && T.tlen > 0 && ncol + 12 <= VSC && vec_dir_bytes(T.qlen, T.tlen, T.w) <= S.dir_cap) {
+        bool ok = (T.flag & KSW_RIGHT) ? warp_extd2_vec<true>(o, T, R, *S.vsm, S.stab, S.dir, cells_acc)
+                                       : warp_extd2_vec<false>(o, T, R, *S.vsm, S.stab, S.dir, cells_acc);
         if (ok) return 1;
     }
-    if (S.s_state && ncol + 2 <= DP_SCOLS) warp_extd2_impl<true>(o, T, R, S, cells_acc, err);
-    else warp_extd2_impl<false>(o, T, R, S, cells_acc, err);
+    warp_extd2_impl<false>(o, T, R, S, cells_acc, err);      // ambiguous bases or a band wider than the window: state arrays in global memory
     return 0;
 }
 
@@ -441,9 +441,10 @@ __global__ void __launch_bounds__(128) k_al_init(const __grid_constant__ AlignAr
 // The coroutine state lives in shared memory while the warp owns the problem and is written back for k_al_finish.
 struct AlWarpSmem { AlnCtx c; DpTask task; DpRes res; int more; };
 
-__global__ void __launch_bounds__(AL_THREADS) k_al_fused(const __grid_constant__ AlignArgs A)
+__global__ void __launch_bounds__(AL_THREADS, AL_BLOCKS_PER_SM) k_al_fused(const __grid_constant__ AlignArgs A)
 {
     __shared__ AlWarpSmem WS[AL_WARPS];
+    __shared__ uint2 stab[256];
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     VecSmem *DS = reinterpret_cast<VecSmem *>(dyn_smem);
     const Opt &o = A.o;
@@ -460,7 +461,8 @@ __global__ void __launch_bounds__(AL_THREADS) k_al_fused(const __grid_constant__
     S.bnd = (uint32_t *)base; base += (((size_t)A.max_qlen + 64) & ~(size_t)15) * 6;
     base = (uint8_t *)(((uintptr_t)base + 255) & ~(uintptr_t)255);
     uint8_t *own_dir = base;
-    S.s_state = &DS[wid].st[0][0]; S.s_H = DS[wid].H; S.vsm = A.use_vec ? &DS[wid] : nullptr;
+    S.s_state = nullptr; S.s_H = nullptr; S.vsm = A.use_vec ? &DS[wid] : nullptr; S.stab = stab;
+    vec_fill_stab(stab, o);
     for (;;) {
         int wi = 0;
         if (lane == 0) wi = (int)atomicAdd(&A.rc[2], 1ULL);

@@ -11,8 +11,20 @@
 
 namespace telr {
 
-constexpr int VSC = 1024;             // shared-memory window (columns / rows), power of two
-struct VecSmem { int8_t st[6][VSC]; int32_t H[VSC]; uint8_t tb[VSC]; uint8_t qb[VSC]; };
+constexpr int VSC = 1024;             // shared-memory state window (columns); covers the default alignment band (1.5 * 500 + 1) + group slack
+constexpr int VCW = 1024;             // window of staged sequence codes (2 bits each), power of two
+__device__ __forceinline__ int vwr(int i) { return (VSC & (VSC - 1)) ? (int)((unsigned)(i + VSC) % (unsigned)VSC) : (i & (VSC - 1)); }   // window slot of column i (i >= -VSC)
+struct VecSmem { int8_t st[6][VSC]; int32_t H[VSC]; uint8_t tb[VCW / 4]; uint8_t qb[VCW / 4]; };
+// Score lookup: index = XOR of four packed 2-bit target codes with the four query codes they meet; value = the packed
+// match/mismatch scores of cells (0,1) and (2,3).  256 entries per CTA, filled once at kernel start.
+__device__ __forceinline__ void vec_fill_stab(uint2 *stab, const Opt &o)
+{
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        const int s0 = (i & 3) ? -o.b : o.a, s1 = ((i >> 2) & 3) ? -o.b : o.a, s2 = ((i >> 4) & 3) ? -o.b : o.a, s3 = ((i >> 6) & 3) ? -o.b : o.a;
+        stab[i] = make_uint2(((uint32_t)s0 & 0xffffu) | ((uint32_t)s1 << 16), ((uint32_t)s2 & 0xffffu) | ((uint32_t)s3 << 16));
+    }
+    __syncthreads();
+}
 
 __host__ __device__ __forceinline__ int vec_ncol(int qlen, int tlen, int w_in)
 {
@@ -29,11 +41,10 @@ __host__ __device__ __forceinline__ int64_t vec_dir_bytes(int qlen, int tlen, in
 }
 
 template <bool RIGHT>
-__device__ bool warp_extd2_vec(const Opt &o, const DpTask &T, DpRes &R, VecSmem &M, uint8_t *p, unsigned long long *cells_acc)
+__device__ bool warp_extd2_vec(const Opt &o, const DpTask &T, DpRes &R, VecSmem &M, const uint2 *stab, uint8_t *p, unsigned long long *cells_acc)
 {
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
-    constexpr int CM = VSC - 1;
     const int qlen = T.qlen, tlen = T.tlen, flag = T.flag;
     int q = o.q, e = o.e, q2 = o.q2, e2 = o.e2;
     if (q2 + e2 < q + e) { int t = q; q = q2; q2 = t; t = e; e = e2; e2 = t; }
@@ -44,7 +55,7 @@ __device__ bool warp_extd2_vec(const Opt &o, const DpTask &T, DpRes &R, VecSmem 
     if (q2 + e2 + LT * e2 > q + e + LT * e) ++LT;
     const int LD = LT * (e - e2) - (q2 - q) - e2;
     const bool approx = flag & KSW_APPROX_MAX;
-    const uint32_t MAT = pk1(o.a), MIS = pk1(-o.b), NE1 = pk1(-e), NQE1 = pk1(-qe), NE2 = pk1(-e2), NQE2 = pk1(-qe2);
+    const uint32_t NE1 = pk1(-e), NQE1 = pk1(-qe), NE2 = pk1(-e2), NQE2 = pk1(-qe2);
     const uint32_t QC1 = pk1(q - 1 + (RIGHT ? 1 : 0)), QC2 = pk1(q2 - 1 + (RIGHT ? 1 : 0));
     int8_t *u = M.st[0], *v = M.st[1], *x = M.st[2], *y = M.st[3], *x2 = M.st[4], *y2 = M.st[5];
     int32_t *H = M.H;
@@ -67,13 +78,17 @@ __device__ bool warp_extd2_vec(const Opt &o, const DpTask &T, DpRes &R, VecSmem 
         while (t_loaded <= en) {
             int i = t_loaded + lane, c = i < tlen ? dp_base(T.t, T.tstep, 0, i) : 0;
             if (__any_sync(FULL, c > 3)) { bail = true; break; }
-            M.tb[i & CM] = (uint8_t)c;
+            uint32_t pk = (uint32_t)c << (2 * (lane & 3));
+            pk |= __shfl_xor_sync(FULL, pk, 1); pk |= __shfl_xor_sync(FULL, pk, 2);
+            if (!(lane & 3)) M.tb[(i >> 2) & (VCW / 4 - 1)] = (uint8_t)pk;
             t_loaded += 32;
         }
         while (!bail && q_loaded <= r - st) {
             int i = q_loaded + lane, c = i < qlen ? dp_base(T.q, T.qstep, T.qcomp, i) : 0;
             if (__any_sync(FULL, c > 3)) { bail = true; break; }
-            M.qb[i & CM] = (uint8_t)c;
+            uint32_t pk = (uint32_t)c << (2 * (3 - (lane & 3)));      // the query runs backwards along an anti-diagonal: row i sits at stream position 3 - i
+            pk |= __shfl_xor_sync(FULL, pk, 1); pk |= __shfl_xor_sync(FULL, pk, 2);
+            if (!(lane & 3)) M.qb[(-(i >> 2)) & (VCW / 4 - 1)] = (uint8_t)pk;
             q_loaded += 32;
         }
         if (bail) break;
@@ -81,12 +96,12 @@ __device__ bool warp_extd2_vec(const Opt &o, const DpTask &T, DpRes &R, VecSmem 
         const int bnd = r == 0 ? -q - e : r < LT ? -e : r == LT ? LD : -e2;
         if (lane == 0) {
             if (en > pen) {
-                const int se = en & CM;
+                const int se = vwr(en);
                 u[se] = v[se] = x[se] = y[se] = (int8_t)(-q - e);
                 x2[se] = y2[se] = (int8_t)(-q2 - e2);
             }
-            if (en == r) { y[r & CM] = (int8_t)(-q - e); y2[r & CM] = (int8_t)(-q2 - e2); u[r & CM] = (int8_t)bnd; }
-            const int sl = (st - 1) & CM;
+            if (en == r) { y[vwr(r)] = (int8_t)(-q - e); y2[vwr(r)] = (int8_t)(-q2 - e2); u[vwr(r)] = (int8_t)bnd; }
+            const int sl = vwr(st - 1);
             if (st == 0) { x[sl] = (int8_t)(-q - e); x2[sl] = (int8_t)(-q2 - e2); v[sl] = (int8_t)bnd; }
             else if (!(st - 1 >= pst && st - 1 <= pen)) { x[sl] = (int8_t)(-q - e); x2[sl] = (int8_t)(-q2 - e2); v[sl] = (int8_t)(-q - e); }
         }
@@ -98,28 +113,26 @@ __device__ bool warp_extd2_vec(const Opt &o, const DpTask &T, DpRes &R, VecSmem 
             const bool act = g <= ge;
             uint32_t Wu = 0, Wv = 0, Wx = 0, Wy = 0, Wx2 = 0, Wy2 = 0, Lv4 = 0, Lx4 = 0, Lx24 = 0, X4 = 0;
             if (act) {
-                const int gw = (g << 2) & CM, gl = ((g << 2) - 4) & CM;
+                const int gw = vwr(g << 2), gl = vwr((g << 2) - 4);
                 Wu = *reinterpret_cast<const uint32_t *>(u + gw); Wy = *reinterpret_cast<const uint32_t *>(y + gw); Wy2 = *reinterpret_cast<const uint32_t *>(y2 + gw);
                 Wv = *reinterpret_cast<const uint32_t *>(v + gw); Wx = *reinterpret_cast<const uint32_t *>(x + gw); Wx2 = *reinterpret_cast<const uint32_t *>(x2 + gw);
                 Lv4 = __byte_perm(*reinterpret_cast<const uint32_t *>(v + gl), Wv, 0x6543);
                 Lx4 = __byte_perm(*reinterpret_cast<const uint32_t *>(x + gl), Wx, 0x6543);
                 Lx24 = __byte_perm(*reinterpret_cast<const uint32_t *>(x2 + gl), Wx2, 0x6543);
-                const uint32_t TW = *reinterpret_cast<const uint32_t *>(M.tb + gw);
-                const int j0 = r - (g << 2);       // row of the group's first column; next columns are one row up each
-                const uint32_t QW = (uint32_t)M.qb[j0 & CM] | (uint32_t)M.qb[(j0 - 1) & CM] << 8 | (uint32_t)M.qb[(j0 - 2) & CM] << 16 | (uint32_t)M.qb[(j0 - 3) & CM] << 24;
-                X4 = TW ^ QW;
+                const int p0 = ((g << 2) + 3 - r) & (VCW - 1);      // stream position of the query row that meets the group's first column
+                const uint32_t qh = (uint32_t)M.qb[p0 >> 2] | (uint32_t)M.qb[((p0 >> 2) + 1) & (VCW / 4 - 1)] << 8;
+                X4 = ((uint32_t)M.tb[g & (VCW / 4 - 1)] ^ (qh >> (2 * (p0 & 3)))) & 0xffu;
             }
             __syncwarp();
             if (act) {
                 uint32_t nU[2], nV[2], nX[2], nY[2], nX2[2], nY2[2], F[2];
+                const uint2 SS = stab[X4];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const uint32_t sxl = h ? 0xB3A2 : 0x9180, zxl = h ? 0x4342 : 0x4140;
+                    const uint32_t sxl = h ? 0xB3A2 : 0x9180;
                     const uint32_t up_u = prmt(Wu, Wu, sxl), up_y = prmt(Wy, Wy, sxl), up_y2 = prmt(Wy2, Wy2, sxl);
                     const uint32_t Lv = prmt(Lv4, Lv4, sxl), Lx = prmt(Lx4, Lx4, sxl), Lx2 = prmt(Lx24, Lx24, sxl);
-                    const uint32_t ne = __vminu2(__byte_perm(X4, 0, zxl), 0x00010001u);
-                    const uint32_t msk = ne * 0xffffu;
-                    const uint32_t S = (msk & MIS) | (~msk & MAT);
+                    const uint32_t S = h ? SS.y : SS.x;
                     const uint32_t A = __vadd2(Lx, Lv), A2 = __vadd2(Lx2, Lv), B = __vadd2(up_y, up_u), B2 = __vadd2(up_y2, up_u);
                     uint32_t Z = __vimax3_s16x2(S, A, B);
                     Z = __vimax3_s16x2(Z, A2, B2);
@@ -140,7 +153,7 @@ __device__ bool warp_extd2_vec(const Opt &o, const DpTask &T, DpRes &R, VecSmem 
                 uint32_t BM = 0xffffffffu;
                 if (c0 < st) BM &= 0xffffffffu << (8 * (st - c0));
                 if (c0 + 3 > en) BM &= 0xffffffffu >> (8 * (c0 + 3 - en));
-                const int gw = c0 & CM;
+                const int gw = vwr(c0);
 #define PACK8(a) __byte_perm((a)[0], (a)[1], 0x6420)
                 *reinterpret_cast<uint32_t *>(u + gw) = (PACK8(nU) & BM) | (Wu & ~BM);
                 *reinterpret_cast<uint32_t *>(v + gw) = (PACK8(nV) & BM) | (Wv & ~BM);
@@ -156,18 +169,18 @@ __device__ bool warp_extd2_vec(const Opt &o, const DpTask &T, DpRes &R, VecSmem 
         if (!approx) {
             int32_t max_H, max_t, Hen, Hst;
             if (r > 0) {
-                Hen = en > 0 ? H[(en - 1) & CM] + u[en & CM] : H[en & CM] + v[en & CM];
+                Hen = en > 0 ? H[vwr(en - 1)] + u[vwr(en)] : H[vwr(en)] + v[vwr(en)];
                 __syncwarp();
                 const int en1 = st + (en - st) / 4 * 4;
                 int32_t bh = KSW_NEG_INF * 2; int brank = 0x7fffffff, bt = -1, hst = 0;
                 for (int t = st + lane; t < en; t += 32) {
-                    int32_t h = H[t & CM] + v[t & CM];
-                    H[t & CM] = h;
+                    int32_t h = H[vwr(t)] + v[vwr(t)];
+                    H[vwr(t)] = h;
                     if (t == st) hst = h;
                     int rank = t < en1 ? 1 + (((t - st) & 3) << 20) + ((t - st) >> 2) : 1 + (4 << 20) + (t - en1);
                     if (h > bh || (h == bh && rank < brank)) bh = h, brank = rank, bt = t;
                 }
-                if (lane == 0) { H[en & CM] = Hen; if (Hen >= bh) bh = Hen, brank = 0, bt = en; }
+                if (lane == 0) { H[vwr(en)] = Hen; if (Hen >= bh) bh = Hen, brank = 0, bt = en; }
 #pragma unroll
                 for (int d = 16; d; d >>= 1) {
                     int32_t oh = __shfl_xor_sync(FULL, bh, d); int orank = __shfl_xor_sync(FULL, brank, d), ot = __shfl_xor_sync(FULL, bt, d);
@@ -195,10 +208,10 @@ __device__ bool warp_extd2_vec(const Opt &o, const DpTask &T, DpRes &R, VecSmem 
         } else {
             if (r > 0) {
                 if (last_H0_t >= st && last_H0_t <= en && last_H0_t + 1 >= st && last_H0_t + 1 <= en) {
-                    int d0 = v[last_H0_t & CM], d1 = u[(last_H0_t + 1) & CM];
+                    int d0 = v[vwr(last_H0_t)], d1 = u[vwr(last_H0_t + 1)];
                     if (d0 > d1) H0 += d0; else H0 += d1, ++last_H0_t;
-                } else if (last_H0_t >= st && last_H0_t <= en) H0 += v[last_H0_t & CM];
-                else ++last_H0_t, H0 += u[last_H0_t & CM];
+                } else if (last_H0_t >= st && last_H0_t <= en) H0 += v[vwr(last_H0_t)];
+                else ++last_H0_t, H0 += u[vwr(last_H0_t)];
             } else H0 = (int32_t)v[0] - qe, last_H0_t = 0;
             if (r == nr - 1 && en == tlen - 1) ez_score = H0;
         }

@@ -306,7 +306,7 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
     ENS(ctx->b_alwork, (size_t)nwk * sizeof(AlWork)); ENS(ctx->b_alctx, (size_t)nwk * sizeof(AlnCtx)); ENS(ctx->b_altask, (size_t)nwk * sizeof(DpTask));
     ENS(ctx->b_alres, (size_t)nwk * sizeof(DpRes)); ENS(ctx->b_alsz, (size_t)(nwk + 1) * 4); ENS(ctx->b_aloff, (size_t)(nwk + 2) * 8);
     ENS(ctx->b_rc, 256);
-    const int al_grid = std::max(1, std::min((n_work + AL_WARPS - 1) / AL_WARPS, sm * 4));
+    const int al_grid = std::max(1, std::min((n_work + AL_WARPS - 1) / AL_WARPS, sm * AL_BLOCKS_PER_SM));
     {
         size_t maxT = ((size_t)max_tlen + 64) & ~(size_t)15;
         aa.max_tlen = max_tlen; aa.max_qlen = max_qlen; aa.dir_cap = ctx->dir_cap; aa.use_fast = ctx->use_fast; aa.use_vec = ctx->use_vec; aa.census = ctx->census;
@@ -695,11 +695,12 @@ struct DpStageArgs {
     int32_t *work_counter, *err; unsigned long long *cells;
 };
 
-__global__ void __launch_bounds__(AL_THREADS) k_dp_stage(const __grid_constant__ DpStageArgs A)
+__global__ void __launch_bounds__(AL_THREADS, AL_BLOCKS_PER_SM) k_dp_stage(const __grid_constant__ DpStageArgs A)
 {
     __shared__ DpRes RS[AL_WARPS];
     __shared__ DpTask TS[AL_WARPS];
     __shared__ unsigned long long CS[AL_WARPS];
+    __shared__ uint2 stab[256];
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     VecSmem *DS = reinterpret_cast<VecSmem *>(dyn_smem);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -714,7 +715,8 @@ __global__ void __launch_bounds__(AL_THREADS) k_dp_stage(const __grid_constant__
     S.bnd = (uint32_t *)base; base += maxQ * 6;
     base = (uint8_t *)(((uintptr_t)base + 255) & ~(uintptr_t)255);
     S.dir = base; S.dir_cap = A.dir_cap;
-    S.s_state = &DS[wid].st[0][0]; S.s_H = DS[wid].H; S.vsm = A.use_vec ? &DS[wid] : nullptr;
+    S.s_state = nullptr; S.s_H = nullptr; S.vsm = A.use_vec ? &DS[wid] : nullptr; S.stab = stab;
+    telr::vec_fill_stab(stab, A.o);
     for (;;) {
         int i = 0;
         if (lane == 0) i = atomicAdd(A.work_counter, 1);
@@ -766,7 +768,7 @@ extern "C" int telr_af_dp(telr_af_ctx *ctx, int32_t preset, int32_t n_tasks, con
     A.maxQ = (maxQ + 64) & ~15; A.maxT = (maxT + 64) & ~15; A.dir_cap = ctx->dir_cap;
     A.use_fast = ctx->use_fast; A.use_vec = ctx->use_vec;
     A.stride = ((size_t)A.maxT * (6 + 4 + 24) + (size_t)(A.maxQ + A.maxT) * 4 + (size_t)A.maxQ * 6 + 512 + (size_t)A.dir_cap + 255) & ~(size_t)255;
-    const int grid = std::max(1, std::min((n_tasks + AL_WARPS - 1) / AL_WARPS, ctx->sm_count * 4));
+    const int grid = std::max(1, std::min((n_tasks + AL_WARPS - 1) / AL_WARPS, ctx->sm_count * AL_BLOCKS_PER_SM));
     ENS(ctx->b_alws, A.stride * (size_t)grid * AL_WARPS);
     ENS(ctx->b_in[0], qbytes + 64); ENS(ctx->b_in[1], tbytes + 64); ENS(ctx->b_in[2], (size_t)n_tasks * sizeof(telr_dp_task));
     ENS(ctx->b_in[3], (size_t)n_tasks * sizeof(telr_dp_out)); ENS(ctx->b_cigout, (size_t)cigar_cap * 4 + 64); ENS(ctx->b_ctr, C_SLOTS * 8);
