@@ -243,7 +243,9 @@ __device__ void extd2_traceback_vec(const DpTask &T, DpRes &R, const uint8_t *p,
     else if (R.max_t >= 0 && R.max_q >= 0) i0 = R.max_t, j0 = R.max_q;
     if (i0 < 0 || j0 < 0) return;
     uint32_t *c = ezcig; int n = 0;
-#define PUSH(op, len) do { if (n == 0 || (uint32_t)(op) != (c[n - 1] & 0xf)) { if (n < ezcap) c[n] = (uint32_t)(len) << 4 | (op); ++n; } else c[n - 1] += (uint32_t)(len) << 4; } while (0)
+    int run_op = -1; uint32_t run_len = 0;          // the open CIGAR run lives in registers
+#define FLUSH() do { if (run_len) { if (n < ezcap) c[n] = run_len << 4 | (uint32_t)run_op; ++n; } } while (0)
+#define PUSH(op, len) do { if ((op) == run_op) run_len += (uint32_t)(len); else { FLUSH(); run_op = (op); run_len = (uint32_t)(len); } } while (0)
     int i = i0, j = j0, state = 0;
     while (i >= 0 && j >= 0) {
         int r = i + j, force_state = -1;
@@ -270,7 +272,9 @@ __device__ void extd2_traceback_vec(const DpTask &T, DpRes &R, const uint8_t *p,
     }
     if (i >= 0) PUSH(2, i + 1);
     if (j >= 0) PUSH(1, j + 1);
+    FLUSH();
 #undef PUSH
+#undef FLUSH
     if (n > ezcap) { atomicOr(err, TELR_ERR_CIGCAP); n = 0; }
     if (!(flag & KSW_REV_CIGAR))
         for (int k = 0; k < n >> 1; ++k) { uint32_t t = c[k]; c[k] = c[n - 1 - k]; c[n - 1 - k] = t; }

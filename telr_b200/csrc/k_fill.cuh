@@ -101,7 +101,8 @@ __device__ bool warp_fill_fast(const Opt &o, const DpTask &T, DpRes &R, uint8_t 
         }
         uint32_t inV = 0, inX = 0, inX2 = 0, inQ = 0, Ufirst = 0;
         const bool last_pass = pass == npass - 1;
-        for (int s = 0; s < npairs + 31; ++s) {
+        const int nlive = tlen - pass * FW >= FW ? 32 : (tlen - pass * FW + FC - 1) / FC;      // lanes that own columns in this pass
+        for (int s = 0; s < npairs + nlive - 1; ++s) {
             const int m = s - lane;
             const bool active = live && m >= 0 && m < npairs;
             if (lane == 0 && s < npairs) {
@@ -201,7 +202,9 @@ __device__ void fill_traceback(const DpTask &T, DpRes &R, const uint8_t *dir, ui
     const int qlen = T.qlen, tlen = T.tlen, stride = fill_stride(tlen);
     uint32_t *c = ezcig; int n = 0;
     int i = tlen - 1, j = qlen - 1, state = 0;
-#define PUSH(op, len) do { if (n == 0 || (uint32_t)(op) != (c[n - 1] & 0xf)) { if (n < ezcap) c[n] = (uint32_t)(len) << 4 | (op); ++n; } else c[n - 1] += (uint32_t)(len) << 4; } while (0)
+    int run_op = -1; uint32_t run_len = 0;          // the open CIGAR run lives in registers; memory is touched once per run
+#define FLUSH() do { if (run_len) { if (n < ezcap) c[n] = run_len << 4 | (uint32_t)run_op; ++n; } } while (0)
+#define PUSH(op, len) do { if ((op) == run_op) run_len += (uint32_t)(len); else { FLUSH(); run_op = (op); run_len = (uint32_t)(len); } } while (0)
     while (i >= 0 && j >= 0) {          // i, j are kept uniform across the warp
         const int c0 = (i - (TBW - 8)) > 0 ? ((i - (TBW - 8)) & ~7) : 0;      // window columns [c0, c0+64), rows [j-31, j]
         {
@@ -217,7 +220,7 @@ __device__ void fill_traceback(const DpTask &T, DpRes &R, const uint8_t *dir, ui
         if (lane == 0) {
             const uint8_t *wb = reinterpret_cast<const uint8_t *>(&tb.w[0][0]);
             const int jtop = j - (TBR - 1) > 0 ? j - (TBR - 1) : 0, j0 = j;
-            while (i >= c0 && j >= jtop && i >= 0 && j >= 0) {
+            while (i >= c0 && j >= jtop) {
                 const uint32_t b = wb[(j0 - j) * TBW + (i - c0)];
                 const int d = !(b & 1) ? 0 : !(b & 2) ? 1 : !(b & 4) ? 2 : !(b & 8) ? 3 : 4;
                 if (state == 0) state = d;
@@ -234,10 +237,13 @@ __device__ void fill_traceback(const DpTask &T, DpRes &R, const uint8_t *dir, ui
     if (lane == 0) {
         if (i >= 0) PUSH(2, i + 1);
         if (j >= 0) PUSH(1, j + 1);
+        FLUSH();
         if (n > ezcap) { atomicOr(err, TELR_ERR_CIGCAP); n = 0; }
         for (int k = 0; k < n >> 1; ++k) { uint32_t t = c[k]; c[k] = c[n - 1 - k]; c[n - 1 - k] = t; }
         R.n_cigar = n; R.cigar = ezcig; R.reach_end = 0;
     }
+#undef PUSH
+#undef FLUSH
 #undef PUSH
     __syncwarp();
 }

@@ -239,6 +239,30 @@ TELR_HDN void scan_zdrop(AlnCtx &c, const uint8_t *qseq, const uint8_t *tseq, in
     c.max_zdrop = max_zdrop;
 }
 
+// Upper bound on everything scan_zdrop could report, from the CIGAR and the fill's DP score alone (no sequence access).
+// With D diagonal cells, m mismatches, n ambiguous pairs and gap runs costing G2 under the DP's two-piece model:
+//   score = a(D - m - n) - b m - sc_ambi n - G2   =>   (a+b) m + (a+sc_ambi) n = a D - score - G2 <= a D - score - G2min
+// and no drop along the path can exceed the single-affine loss  b m + sc_ambi n + G1 <= floor(b X / (a+b)) + G1
+// (valid while b/(a+b) >= sc_ambi/(a+sc_ambi)).  Returns INT32_MAX when no bound is available.
+TELR_HDN int32_t zdrop_bound(const Opt &o, int n_cigar, const uint32_t *cigar, int32_t score)
+{
+    if (n_cigar <= 0 || score <= KSW_NEG_INF / 2) return INT32_MAX;
+    if ((long long)o.b * (o.a + o.sc_ambi) < (long long)o.sc_ambi * (o.a + o.b)) return INT32_MAX;
+    long long D = 0, G1 = 0, G2 = 0;
+    for (int k = 0; k < n_cigar; ++k) {
+        const int op = cigar[k] & 0xf; const long long len = cigar[k] >> 4;
+        if (op == 0) D += len;
+        else {
+            const long long c1 = o.q + o.e * len, c2 = o.q2 + o.e2 * len;
+            G1 += c1; G2 += c1 < c2 ? c1 : c2;
+        }
+    }
+    const long long X = o.a * D - score - G2;
+    if (X < 0) return INT32_MAX;
+    const long long N = o.b * X / (o.a + o.b) + G1;
+    return N < INT32_MAX ? (int32_t)N : INT32_MAX;
+}
+
 // CIGAR clean-up after all pieces are joined: indel left-alignment, I/D merging, leading I/D removal
 TELR_HDN void fix_cigar(AlnCtx &c, Reg &r, const uint8_t *qseq, const uint8_t *tseq, int *qshift, int *tshift)
 {
@@ -554,6 +578,10 @@ TELR_HDN bool aln_next(AlnCtx &c, const DpRes &in, DpTask &task)
         }
         case PH_FILL1_DONE + 100: c.res = in; c.phase = PH_FILL1_DONE; break;
         case PH_FILL1_DONE: {
+            {   // the common case: the whole path loses less than either threshold, so the per-base rescan cannot fire
+                const int32_t lim = o.zdrop < o.zdrop_inv ? o.zdrop : o.zdrop_inv;
+                if (zdrop_bound(o, c.res.n_cigar, c.res.cigar, c.res.score) <= lim) { c.max_zdrop = 0; c.zdrop_code = 0; c.phase = PH_FILL_DECIDE; break; }
+            }
             scan_zdrop(c, &c.qseq[c.rev][c.qs], &c.tseq[c.rs], c.res.n_cigar, c.res.cigar);
             int q_len = c.zpos[1][1] - c.zpos[0][1], t_len = c.zpos[1][0] - c.zpos[0][0];
             if (c.max_zdrop > o.zdrop_inv && q_len < o.max_gap && t_len < o.max_gap) {
