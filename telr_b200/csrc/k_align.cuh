@@ -335,9 +335,7 @@ __device__ __forceinline__ int warp_extd2(const Opt &o, const DpTask &T, DpRes &
 {
     const int ncol = vec_ncol(T.qlen, T.tlen, T.w);
     if (S.vsm && T.qlen > 0 && T.tlen > 0 && ncol + 12 <= VSC && vec_dir_bytes(T.qlen, T.tlen, T.w) <= S.dir_cap) {
-        bool ok = (T.flag & KSW_RIGHT) ? warp_extd2_vec<true>(o, T, R, *S.vsm, S.stab, S.dir, cells_acc)
-                                       : warp_extd2_vec<false>(o, T, R, *S.vsm, S.stab, S.dir, cells_acc);
-        if (ok) return 1;
+        if (warp_extd2_vec(o, T, R, *S.vsm, S.stab, S.dir, cells_acc)) return 1;
     }
     warp_extd2_impl<false>(o, T, R, S, cells_acc, err);      // ambiguous bases or a band wider than the window: state arrays in global memory
     return 0;

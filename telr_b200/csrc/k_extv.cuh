@@ -3,7 +3,7 @@
 // warp_extd2_impl<true>, but every lane owns a group of 4 consecutive columns per step: state arrays are read/written
 // as 32-bit words (4 x int8), unpacked to two 16x2 registers and run through the packed recurrence of k_fill.cuh;
 // target/query codes are staged in shared memory in chunks of 32.  Direction bytes use the sign-bit format:
-//   bits 0-3: "below the maximum" for (s,a,b,a2) [left-aligned gaps] or (a,b,a2,b2) [right-aligned]
+//   bits 0-3: "below the maximum" for (s,a,b,a2) [left-aligned gaps] or (b2,a,b,a2) [right-aligned]
 //   bits 4-7: "gap does not continue" for x,y,x2,y2
 // Requests that contain an ambiguous base, or whose band does not fit the window, return false and take the scalar path.
 #pragma once
@@ -40,12 +40,12 @@ __host__ __device__ __forceinline__ int64_t vec_dir_bytes(int qlen, int tlen, in
     return (int64_t)(qlen + tlen - 1) * vec_stride(qlen, tlen, w_in);
 }
 
-template <bool RIGHT>
 __device__ bool warp_extd2_vec(const Opt &o, const DpTask &T, DpRes &R, VecSmem &M, const uint2 *stab, uint8_t *p, unsigned long long *cells_acc)
 {
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
     const int qlen = T.qlen, tlen = T.tlen, flag = T.flag;
+    const bool RIGHT = flag & KSW_RIGHT;
     int q = o.q, e = o.e, q2 = o.q2, e2 = o.e2;
     if (q2 + e2 < q + e) { int t = q; q = q2; q2 = t; t = e; e = e2; e2 = t; }
     const int qe = q + e, qe2 = q2 + e2;
@@ -125,7 +125,7 @@ __device__ bool warp_extd2_vec(const Opt &o, const DpTask &T, DpRes &R, VecSmem 
             }
             __syncwarp();
             if (act) {
-                uint32_t nU[2], nV[2], nX[2], nY[2], nX2[2], nY2[2], F[2];
+                uint32_t nU[2], nV[2], nX[2], nY[2], nX2[2], nY2[2], fO[2], fA[2], fB[2], fA2[2], fX[2], fY[2], fX2[2], fY2[2];
                 const uint2 SS = stab[X4];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -136,33 +136,36 @@ __device__ bool warp_extd2_vec(const Opt &o, const DpTask &T, DpRes &R, VecSmem 
                     const uint32_t A = __vadd2(Lx, Lv), A2 = __vadd2(Lx2, Lv), B = __vadd2(up_y, up_u), B2 = __vadd2(up_y2, up_u);
                     uint32_t Z = __vimax3_s16x2(S, A, B);
                     Z = __vimax3_s16x2(Z, A2, B2);
-                    const uint32_t DS = __vsub2(S, Z), DA = __vsub2(A, Z), DB = __vsub2(B, Z), DA2 = __vsub2(A2, Z), DB2 = __vsub2(B2, Z);
+                    const uint32_t DA = __vsub2(A, Z), DB = __vsub2(B, Z), DA2 = __vsub2(A2, Z);
+                    const uint32_t DB2 = __vsub2(B2, Z);
+                    fO[h] = __vsub2(RIGHT ? B2 : S, Z);          // the one candidate the two tie-break orders do not share
                     nU[h] = __vsub2(Z, Lv); nV[h] = __vsub2(Z, up_u);
                     nX[h] = __viaddmax_s16x2(DA, NE1, NQE1); nY[h] = __viaddmax_s16x2(DB, NE1, NQE1);
                     nX2[h] = __viaddmax_s16x2(DA2, NE2, NQE2); nY2[h] = __viaddmax_s16x2(DB2, NE2, NQE2);
-                    const uint32_t cx = __vadd2(DA, QC1), cy = __vadd2(DB, QC1), cx2 = __vadd2(DA2, QC2), cy2 = __vadd2(DB2, QC2);
-                    uint32_t acc;
-                    if (!RIGHT) { acc = prmt(DS, DA, 0xFDB9) & 0x02020101u; acc |= prmt(DB, DA2, 0xFDB9) & 0x08080404u; }
-                    else        { acc = prmt(DA, DB, 0xFDB9) & 0x02020101u; acc |= prmt(DA2, DB2, 0xFDB9) & 0x08080404u; }
-                    acc |= prmt(cx, cy, 0xFDB9) & 0x20201010u;
-                    acc |= prmt(cx2, cy2, 0xFDB9) & 0x80804040u;
-                    F[h] = acc | (acc >> 16);
+                    fA[h] = DA; fB[h] = DB; fA2[h] = DA2;
+                    fX[h] = __vadd2(DA, QC1); fY[h] = __vadd2(DB, QC1); fX2[h] = __vadd2(DA2, QC2); fY2[h] = __vadd2(DB2, QC2);
                 }
-                // in-band byte mask of this group (columns outside [st,en] keep their old state)
-                const int c0 = g << 2;
-                uint32_t BM = 0xffffffffu;
-                if (c0 < st) BM &= 0xffffffffu << (8 * (st - c0));
-                if (c0 + 3 > en) BM &= 0xffffffffu >> (8 * (c0 + 3 - en));
-                const int gw = vwr(c0);
+                // 8 sign bits per cell: one PRMT per flag gathers the four cells of the group (bytes = columns c0..c0+3)
+                uint32_t dw = prmt(fO[0], fO[1], 0xFDB9) & 0x01010101u;
+                dw |= prmt(fA[0], fA[1], 0xFDB9) & 0x02020202u;
+                dw |= prmt(fB[0], fB[1], 0xFDB9) & 0x04040404u;
+                dw |= prmt(fA2[0], fA2[1], 0xFDB9) & 0x08080808u;
+                dw |= prmt(fX[0], fX[1], 0xFDB9) & 0x10101010u;
+                dw |= prmt(fY[0], fY[1], 0xFDB9) & 0x20202020u;
+                dw |= prmt(fX2[0], fX2[1], 0xFDB9) & 0x40404040u;
+                dw |= prmt(fY2[0], fY2[1], 0xFDB9) & 0x80808080u;
+                // Whole words are written back: cells outside [st, en] hold garbage, which is never read (a column is
+                // re-seeded when it enters the band, and the left neighbour of st is either last row's cell or a constant).
+                const int c0 = g << 2, gw = vwr(c0);
 #define PACK8(a) __byte_perm((a)[0], (a)[1], 0x6420)
-                *reinterpret_cast<uint32_t *>(u + gw) = (PACK8(nU) & BM) | (Wu & ~BM);
-                *reinterpret_cast<uint32_t *>(v + gw) = (PACK8(nV) & BM) | (Wv & ~BM);
-                *reinterpret_cast<uint32_t *>(x + gw) = (PACK8(nX) & BM) | (Wx & ~BM);
-                *reinterpret_cast<uint32_t *>(y + gw) = (PACK8(nY) & BM) | (Wy & ~BM);
-                *reinterpret_cast<uint32_t *>(x2 + gw) = (PACK8(nX2) & BM) | (Wx2 & ~BM);
-                *reinterpret_cast<uint32_t *>(y2 + gw) = (PACK8(nY2) & BM) | (Wy2 & ~BM);
+                *reinterpret_cast<uint32_t *>(u + gw) = PACK8(nU);
+                *reinterpret_cast<uint32_t *>(v + gw) = PACK8(nV);
+                *reinterpret_cast<uint32_t *>(x + gw) = PACK8(nX);
+                *reinterpret_cast<uint32_t *>(y + gw) = PACK8(nY);
+                *reinterpret_cast<uint32_t *>(x2 + gw) = PACK8(nX2);
+                *reinterpret_cast<uint32_t *>(y2 + gw) = PACK8(nY2);
 #undef PACK8
-                *reinterpret_cast<uint32_t *>(pr + c0) = __byte_perm(F[0], F[1], 0x5410);
+                *reinterpret_cast<uint32_t *>(pr + c0) = dw;
             }
             __syncwarp();
         }
@@ -260,7 +263,7 @@ __device__ void extd2_traceback_vec(const DpTask &T, DpRes &R, const uint8_t *p,
         if (force_state < 0) {
             b = p[(int64_t)r * vstride + (i - (st & ~3))];
             if (!right) d = !(b & 1) ? 0 : !(b & 2) ? 1 : !(b & 4) ? 2 : !(b & 8) ? 3 : 4;
-            else d = !(b & 8) ? 4 : !(b & 4) ? 3 : !(b & 2) ? 2 : !(b & 1) ? 1 : 0;
+            else d = !(b & 1) ? 4 : !(b & 8) ? 3 : !(b & 4) ? 2 : !(b & 2) ? 1 : 0;
         }
         if (state == 0) state = d;
         else if (force_state >= 0 || ((b >> (3 + state)) & 1)) state = 0;

@@ -18,8 +18,7 @@
 
 namespace telr {
 
-constexpr int FC = 8;                 // columns per lane
-constexpr int FW = 32 * FC;           // columns per pass
+constexpr int FC_MAX = 12;            // columns per lane: 8 (256-column passes) or 12 (384-column passes)
 
 // prmt.b32 in default mode: selector nibble bit 3 replicates the sign of the selected byte (__byte_perm drops that bit)
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
@@ -41,13 +40,13 @@ __device__ __forceinline__ int bnd_sum(int n, int qe, int e, int e2, int LT, int
     int n1 = (n - 1 < LT - 1 ? n - 1 : LT - 1);            // r = 1 .. LT-1
     if (n1 > 0) s -= e * n1;
     if (n - 1 >= LT && LT >= 1) s += LD;                    // r = LT
-    if (LT == 0 && n - 1 >= 0) { /* r == 0 already counted as -qe (r==0 wins) */ }
     int n3 = n - 1 - (LT > 0 ? LT : 0);                     // r = LT+1 .. n-1
     if (n3 > 0) s -= e2 * n3;
     return s;
 }
 
-__host__ __device__ __forceinline__ int fill_stride(int tlen) { return (tlen + FC - 1) / FC * FC; }
+// direction rows are padded to a multiple of 24 bytes so that both lane widths store whole lanes
+__host__ __device__ __forceinline__ int fill_stride(int tlen) { return (tlen + 23) / 24 * 24; }
 
 // true when the request can take the fast path (shape / flags); ambiguous bases are checked inside
 __device__ __forceinline__ bool fill_fast_ok(const DpTask &T)
@@ -58,19 +57,22 @@ __device__ __forceinline__ bool fill_fast_ok(const DpTask &T)
     return T.w < 0 || T.w >= mx;
 }
 
-// forward pass; returns false (nothing written) when an ambiguous base is present
-__device__ bool warp_fill_fast(const Opt &o, const DpTask &T, DpRes &R, uint8_t *dir, uint32_t *bnd, unsigned long long *cells_acc)
+// 12 columns per lane when that saves a pass (e.g. 257..384 target bases: one pass instead of two)
+__host__ __device__ __forceinline__ int fill_width(int tlen)
 {
+    const int p8 = (tlen + 255) / 256, p12 = (tlen + 383) / 384;
+    return p12 * 13 < p8 * 9 ? 12 : 8;
+}
+
+// forward pass for one lane width; the caller has excluded ambiguous bases
+template <int FC>
+__device__ void warp_fill_fwd(const Opt &o, const DpTask &T, DpRes &R, uint8_t *dir, uint32_t *bnd, unsigned long long *cells_acc)
+{
+    constexpr int FW = 32 * FC;
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
     const int qlen = T.qlen, tlen = T.tlen;
     const uint8_t *__restrict__ Q = T.q, *__restrict__ Tg = T.t;
-    {   // ambiguous bases take the general path (their score is not match/mismatch)
-        bool n = false;
-        for (int i = lane; i < qlen; i += 32) n |= Q[i] > 3;
-        for (int i = lane; i < tlen; i += 32) n |= Tg[i] > 3;
-        if (__any_sync(FULL, n)) return false;
-    }
     int q = o.q, e = o.e, q2 = o.q2, e2 = o.e2;
     if (q2 + e2 < q + e) { int t = q; q = q2; q2 = t; t = e; e = e2; e2 = t; }
     const int qe = q + e, qe2 = q2 + e2;
@@ -78,8 +80,10 @@ __device__ bool warp_fill_fast(const Opt &o, const DpTask &T, DpRes &R, uint8_t 
     if (q2 + e2 + LT * e2 > q + e + LT * e) ++LT;
     const int LD = LT * (e - e2) - (q2 - q) - e2;
 #define BNDF(r) ((r) == 0 ? -qe : (r) < LT ? -e : (r) == LT ? LD : -e2)
-    const uint32_t MAT = pk1(o.a), MIS = pk1(-o.b), NE1 = pk1(-e), NQE1 = pk1(-qe), NE2 = pk1(-e2), NQE2 = pk1(-qe2);
+    const uint32_t NE1 = pk1(-e), NQE1 = pk1(-qe), NE2 = pk1(-e2), NQE2 = pk1(-qe2);
     const uint32_t QM1 = pk1(q - 1), Q2M1 = pk1(q2 - 1);
+    // score table of one target base: byte c = score against query base c (int8)
+    const uint32_t TS_MIS = 0x01010101u * ((uint32_t)(-o.b) & 0xffu), TS_FLIP = ((uint32_t)o.a ^ (uint32_t)(-o.b)) & 0xffu;
     const int stride = fill_stride(tlen);
     const int npairs = (qlen + 1) >> 1, npass = (tlen + FW - 1) / FW;
     int usum = 0;
@@ -87,12 +91,11 @@ __device__ bool warp_fill_fast(const Opt &o, const DpTask &T, DpRes &R, uint8_t 
     for (int pass = 0; pass < npass; ++pass) {
         const int t0 = pass * FW + lane * FC;
         const bool live = t0 < tlen;
-        uint32_t tp[FC + 1], Uu[FC], Uy[FC], Uy2[FC];
+        uint32_t TS[FC], Uu[FC], Uy[FC], Uy2[FC];
 #pragma unroll
-        for (int k = 0; k <= FC; ++k) {
-            int lo = (k < FC && t0 + k < tlen) ? Tg[t0 + k] : 0;
-            int hi = (k >= 1 && t0 + k - 1 < tlen) ? Tg[t0 + k - 1] : 0;
-            tp[k] = pk2(lo, hi);
+        for (int k = 0; k < FC; ++k) {
+            const int tc = t0 + k < tlen ? Tg[t0 + k] : 0;
+            TS[k] = TS_MIS ^ (TS_FLIP << (8 * tc));
         }
 #pragma unroll
         for (int k = 0; k < FC; ++k) {              // top boundary sits in the hi halves (row "-1" of pair 0)
@@ -107,7 +110,10 @@ __device__ bool warp_fill_fast(const Opt &o, const DpTask &T, DpRes &R, uint8_t 
             const bool active = live && m >= 0 && m < npairs;
             if (lane == 0 && s < npairs) {
                 const int j = 2 * s;
-                inQ = pk2(Q[j], j + 1 < qlen ? Q[j + 1] : 0);
+                // the two query bases of this row pair travel as the PRMT selector that looks them up in the score tables:
+                // lo half <- sign-extended byte q[j] of the first table, hi half <- byte q[j+1] of the second
+                const uint32_t q0 = Q[j], q1 = j + 1 < qlen ? Q[j + 1] : 0;
+                inQ = q0 | (q0 | 8u) << 4 | (q1 + 4u) << 8 | (q1 + 12u) << 12;
                 if (pass == 0) {
                     inV = pk2(BNDF(j), BNDF(j + 1)); inX = NQE1; inX2 = NQE2;
                 } else { inV = bnd[3 * s]; inX = bnd[3 * s + 1]; inX2 = bnd[3 * s + 2]; }
@@ -116,18 +122,17 @@ __device__ bool warp_fill_fast(const Opt &o, const DpTask &T, DpRes &R, uint8_t 
             if (active) {
                 const int j = 2 * m;
                 uint32_t Lv = inV, Lx = inX, Lx2 = inX2, pu = 0, py = 0, py2 = 0, kV = 0, kX = 0, kX2 = 0;
-                uint32_t rF0 = 0, rF1 = 0, rS0 = 0, rS1 = 0;
+                uint32_t W[FC / 2 + 1];             // W[p]: flag bytes of cells (2p, j), (2p-1, j+1), (2p+1, j), (2p, j+1)
+                uint32_t eDS = 0, eDA = 0, eDB = 0, eDA2 = 0, eCX = 0, eCY = 0, eCX2 = 0, eCY2 = 0;   // even iteration, waiting for its partner
 #pragma unroll
                 for (int k = 0; k <= FC; ++k) {
-                    const int kk = k < FC ? k : FC - 1;
+                    const int kk = k < FC ? k : FC - 1, kh = k > 0 ? k - 1 : 0;
                     // up inputs: lo <- previous row pair's second row (hi half of the saved register), hi <- cell above in this pair
                     const uint32_t up_u = __byte_perm(Uu[kk], pu, 0x5432), up_y = __byte_perm(Uy[kk], py, 0x5432), up_y2 = __byte_perm(Uy2[kk], py2, 0x5432);
                     if (k == 1) {                   // second row enters: its left neighbour is the previous lane's last column
                         Lv = __byte_perm(Lv, inV, 0x7610); Lx = __byte_perm(Lx, inX, 0x7610); Lx2 = __byte_perm(Lx2, inX2, 0x7610);
                     }
-                    const uint32_t ne = __vminu2(tp[k] ^ inQ, 0x00010001u);
-                    const uint32_t msk = ne * 0xffffu;
-                    const uint32_t S = (msk & MIS) | (~msk & MAT);
+                    const uint32_t S = prmt(TS[kk], TS[kh], inQ);
                     const uint32_t A = __vadd2(Lx, Lv), A2 = __vadd2(Lx2, Lv), B = __vadd2(up_y, up_u), B2 = __vadd2(up_y2, up_u);
                     uint32_t Z = __vimax3_s16x2(S, A, B);
                     Z = __vimax3_s16x2(Z, A2, B2);
@@ -136,28 +141,51 @@ __device__ bool warp_fill_fast(const Opt &o, const DpTask &T, DpRes &R, uint8_t 
                     const uint32_t nx = __viaddmax_s16x2(DA, NE1, NQE1), ny = __viaddmax_s16x2(DB, NE1, NQE1);
                     const uint32_t nx2 = __viaddmax_s16x2(DA2, NE2, NQE2), ny2 = __viaddmax_s16x2(DB2, NE2, NQE2);
                     const uint32_t cx = __vadd2(DA, QM1), cy = __vadd2(DB, QM1), cx2 = __vadd2(DA2, Q2M1), cy2 = __vadd2(DB2, Q2M1);
-                    // 8 sign bits per cell -> one byte per cell
-                    uint32_t acc = prmt(DS, DA, 0xFDB9) & 0x02020101u;
-                    acc |= prmt(DB, DA2, 0xFDB9) & 0x08080404u;
-                    acc |= prmt(cx, cy, 0xFDB9) & 0x20201010u;
-                    acc |= prmt(cx2, cy2, 0xFDB9) & 0x80804040u;
-                    const uint32_t f = acc | (acc >> 16);
-                    if (k < FC) {
-                        if (k < 4) rF0 |= (f & 0xffu) << (8 * (k & 3)); else rF1 |= (f & 0xffu) << (8 * (k & 3));
+                    // 8 sign bits per cell -> one byte per cell.  Two iterations are gathered together, one PRMT per flag:
+                    // bytes (k lo, k hi, k+1 lo, k+1 hi) of flag f land on bit f of the four cell bytes.
+                    if (k == FC) {                  // last iteration (even): only its hi cell (FC-1, j+1) exists
+                        uint32_t acc = prmt(DS, DA, 0xFDB9) & 0x02020101u;
+                        acc |= prmt(DB, DA2, 0xFDB9) & 0x08080404u;
+                        acc |= prmt(cx, cy, 0xFDB9) & 0x20201010u;
+                        acc |= prmt(cx2, cy2, 0xFDB9) & 0x80804040u;
+                        W[FC / 2] = acc | (acc >> 16);          // byte 1
+                    } else if (!(k & 1)) {
+                        eDS = DS; eDA = DA; eDB = DB; eDA2 = DA2; eCX = cx; eCY = cy; eCX2 = cx2; eCY2 = cy2;
+                    } else {
+                        uint32_t acc = prmt(eDS, DS, 0xFDB9) & 0x01010101u;
+                        acc |= prmt(eDA, DA, 0xFDB9) & 0x02020202u;
+                        acc |= prmt(eDB, DB, 0xFDB9) & 0x04040404u;
+                        acc |= prmt(eDA2, DA2, 0xFDB9) & 0x08080808u;
+                        acc |= prmt(eCX, cx, 0xFDB9) & 0x10101010u;
+                        acc |= prmt(eCY, cy, 0xFDB9) & 0x20202020u;
+                        acc |= prmt(eCX2, cx2, 0xFDB9) & 0x40404040u;
+                        acc |= prmt(eCY2, cy2, 0xFDB9) & 0x80808080u;
+                        W[k >> 1] = acc;
                     }
-                    if (k >= 1) {
-                        const int c = k - 1;
-                        if (c < 4) rS0 |= ((f >> 8) & 0xffu) << (8 * (c & 3)); else rS1 |= ((f >> 8) & 0xffu) << (8 * (c & 3));
-                        Uu[c] = nu; Uy[c] = ny; Uy2[c] = ny2;          // hi halves: cell (c, j+1) = up input of the next row pair
-                    }
+                    if (k >= 1) { Uu[k - 1] = nu; Uy[k - 1] = ny; Uy2[k - 1] = ny2; }      // hi halves: cell (k-1, j+1) = up input of the next row pair
                     if (k == 0) Ufirst = nu;
                     if (k == FC - 1) { kV = nv; kX = nx; kX2 = nx2; }
                     pu = nu; py = ny; py2 = ny2; Lv = nv; Lx = nx; Lx2 = nx2;
                 }
                 outV = __byte_perm(kV, Lv, 0x7610); outX = __byte_perm(kX, Lx, 0x7610); outX2 = __byte_perm(kX2, Lx2, 0x7610);
                 if (t0 < stride) {
-                    *reinterpret_cast<uint2 *>(dir + (int64_t)j * stride + t0) = make_uint2(rF0, rF1);
-                    if (j + 1 < qlen) *reinterpret_cast<uint2 *>(dir + (int64_t)(j + 1) * stride + t0) = make_uint2(rS0, rS1);
+                    uint8_t *r0 = dir + (int64_t)j * stride + t0, *r1 = r0 + stride;
+                    uint32_t w0[FC / 4], w1[FC / 4];
+#pragma unroll
+                    for (int w = 0; w < FC / 4; ++w) {
+                        w0[w] = __byte_perm(W[2 * w], W[2 * w + 1], 0x6420);                                        // row j: cells (4w .. 4w+3, j)
+                        w1[w] = __byte_perm(__byte_perm(W[2 * w], W[2 * w + 1], 0x0753), W[2 * w + 2], 0x5210);      // row j+1
+                    }
+                    if (FC == 8) {
+                        *reinterpret_cast<uint2 *>(r0) = make_uint2(w0[0], w0[1]);
+                        if (j + 1 < qlen) *reinterpret_cast<uint2 *>(r1) = make_uint2(w1[0], w1[1]);
+                    } else {
+#pragma unroll
+                        for (int w = 0; w < FC / 4; ++w) {
+                            reinterpret_cast<uint32_t *>(r0)[w] = w0[w];
+                            if (j + 1 < qlen) reinterpret_cast<uint32_t *>(r1)[w] = w1[w];
+                        }
+                    }
                 }
                 if (lane == 31 && !last_pass) { bnd[3 * m] = outV; bnd[3 * m + 1] = outX; bnd[3 * m + 2] = outX2; }
             }
@@ -185,15 +213,31 @@ __device__ bool warp_fill_fast(const Opt &o, const DpTask &T, DpRes &R, uint8_t 
         atomicAdd(cells_acc, (unsigned long long)qlen * (unsigned long long)tlen);
     }
     __syncwarp();
+}
+
+// forward pass; returns false (nothing written) when an ambiguous base is present
+__device__ bool warp_fill_fast(const Opt &o, const DpTask &T, DpRes &R, uint8_t *dir, uint32_t *bnd, unsigned long long *cells_acc)
+{
+    const int lane = threadIdx.x & 31;
+    {   // ambiguous bases take the general path (their score is not match/mismatch)
+        bool n = false;
+        for (int i = lane; i < T.qlen; i += 32) n |= T.q[i] > 3;
+        for (int i = lane; i < T.tlen; i += 32) n |= T.t[i] > 3;
+        if (__any_sync(0xffffffffu, n)) return false;
+    }
+    if (o.a > 127 || o.b > 127) return false;            // score tables are int8
+    warp_fill_fwd<8>(o, T, R, dir, bnd, cells_acc);     // a second instantiation (12 columns per lane) halves the passes of 257..384-column fills but
+                                                         // doubles the hot code: measured 35 % slower end to end (instruction-cache misses), so it stays off
     return true;
 }
 
 // ksw_backtrack over the fast path's row-major direction bytes (global alignment, no band).
-// Warp-cooperative: the lanes stage a window of 32 rows x 64 columns that ends at the current cell into shared
-// memory with coalesced 8-byte loads (one row per lane); lane 0 then walks the path inside the window with
-// shared-memory latency instead of one dependent global load per step, and asks for the next window when it leaves.
-constexpr int TBW = 64, TBR = 32;
-struct TbSmem { uint2 w[TBR][TBW / 8]; };
+// Warp-cooperative and run-at-a-time: the lanes stage a window of 56 rows x 64 columns that ends at the current cell
+// into shared memory (coalesced 8-byte loads, two rows per lane); then every step resolves a whole CIGAR run: lane k
+// looks at the k-th cell ahead along the current direction (diagonal, left or up), one ballot finds where the run stops.
+// All lanes carry the same (i, j, state, open run); only lane 0 writes CIGAR words.
+constexpr int TBW = 64, TBR = 56, TBP = 72;        // window columns, rows, row pitch in bytes (72: column walks hit 16 banks)
+struct TbSmem { uint2 w[TBR][TBP / 8]; };
 
 __device__ void fill_traceback(const DpTask &T, DpRes &R, const uint8_t *dir, uint32_t *ezcig, int ezcap, int32_t *err, TbSmem &tb)
 {
@@ -203,48 +247,56 @@ __device__ void fill_traceback(const DpTask &T, DpRes &R, const uint8_t *dir, ui
     uint32_t *c = ezcig; int n = 0;
     int i = tlen - 1, j = qlen - 1, state = 0;
     int run_op = -1; uint32_t run_len = 0;          // the open CIGAR run lives in registers; memory is touched once per run
-#define FLUSH() do { if (run_len) { if (n < ezcap) c[n] = run_len << 4 | (uint32_t)run_op; ++n; } } while (0)
+#define FLUSH() do { if (run_len) { if (n < ezcap && lane == 0) c[n] = run_len << 4 | (uint32_t)run_op; ++n; } } while (0)
 #define PUSH(op, len) do { if ((op) == run_op) run_len += (uint32_t)(len); else { FLUSH(); run_op = (op); run_len = (uint32_t)(len); } } while (0)
-    while (i >= 0 && j >= 0) {          // i, j are kept uniform across the warp
-        const int c0 = (i - (TBW - 8)) > 0 ? ((i - (TBW - 8)) & ~7) : 0;      // window columns [c0, c0+64), rows [j-31, j]
-        {
-            const int row = j - lane;
+    const uint8_t *wb = reinterpret_cast<const uint8_t *>(&tb.w[0][0]);
+    while (i >= 0 && j >= 0) {
+        const int c0 = (i - (TBW - 8)) > 0 ? ((i - (TBW - 8)) & ~7) : 0;      // window columns [c0, c0+64), rows [jtop, j0]
+        const int j0 = j, jtop = j - (TBR - 1) > 0 ? j - (TBR - 1) : 0;
+        for (int rr = lane; rr < TBR; rr += 32) {
+            const int row = j0 - rr;
             if (row >= 0) {
                 const uint8_t *src = dir + (int64_t)row * stride + c0;
 #pragma unroll
                 for (int k = 0; k < TBW / 8; ++k)
-                    if (c0 + 8 * k < stride) tb.w[lane][k] = *reinterpret_cast<const uint2 *>(src + 8 * k);
+                    if (c0 + 8 * k < stride) tb.w[rr][k] = *reinterpret_cast<const uint2 *>(src + 8 * k);
             }
         }
         __syncwarp();
-        if (lane == 0) {
-            const uint8_t *wb = reinterpret_cast<const uint8_t *>(&tb.w[0][0]);
-            const int jtop = j - (TBR - 1) > 0 ? j - (TBR - 1) : 0, j0 = j;
-            while (i >= c0 && j >= jtop) {
-                const uint32_t b = wb[(j0 - j) * TBW + (i - c0)];
-                const int d = !(b & 1) ? 0 : !(b & 2) ? 1 : !(b & 4) ? 2 : !(b & 8) ? 3 : 4;
-                if (state == 0) state = d;
-                else if ((b >> (3 + state)) & 1) state = 0;      // the gap does not continue here
-                if (state == 0) state = d;
-                if (state == 0) { PUSH(0, 1); --i; --j; }
-                else if (state == 1 || state == 3) { PUSH(2, 1); --i; }
-                else { PUSH(1, 1); --j; }
+        while (i >= c0 && j >= jtop) {
+            if (state == 0) {           // diagonal run: cells (i-k, j-k) while "s is the maximum"
+                const int ii = i - lane, jj = j - lane;
+                const bool ok = ii >= c0 && jj >= jtop;
+                const uint32_t b = ok ? wb[(j0 - jj) * TBP + (ii - c0)] : 1u;
+                const unsigned m = __ballot_sync(FULL, b & 1u);
+                const int L = m ? __ffs(m) - 1 : 32;
+                if (L > 0) { PUSH(0, L); i -= L; j -= L; continue; }
+                const uint32_t b0 = __shfl_sync(FULL, b, 0);      // a gap opens here
+                state = !(b0 & 2) ? 1 : !(b0 & 4) ? 2 : !(b0 & 8) ? 3 : 4;
+                if (state == 1 || state == 3) { PUSH(2, 1); --i; } else { PUSH(1, 1); --j; }
+            } else {                    // gap run: cells to the left (deletion) or above (insertion) while the gap state continues
+                const bool del = state == 1 || state == 3;
+                const int ii = del ? i - lane : i, jj = del ? j : j - lane;
+                const bool ok = ii >= c0 && jj >= jtop;
+                const uint32_t b = ok ? wb[(j0 - jj) * TBP + (ii - c0)] : 0xffu;
+                const unsigned m = __ballot_sync(FULL, (b >> (3 + state)) & 1u);
+                const unsigned okm = __ballot_sync(FULL, ok);
+                const int L = m ? __ffs(m) - 1 : 32;
+                if (L > 0) { PUSH(del ? 2 : 1, L); if (del) i -= L; else j -= L; }
+                if (L < 32 && ((okm >> L) & 1u)) state = 0;       // the gap ends on a cell inside the window; its own direction is read next
             }
         }
-        i = __shfl_sync(FULL, i, 0); j = __shfl_sync(FULL, j, 0);
         __syncwarp();
     }
-    if (lane == 0) {
-        if (i >= 0) PUSH(2, i + 1);
-        if (j >= 0) PUSH(1, j + 1);
-        FLUSH();
-        if (n > ezcap) { atomicOr(err, TELR_ERR_CIGCAP); n = 0; }
-        for (int k = 0; k < n >> 1; ++k) { uint32_t t = c[k]; c[k] = c[n - 1 - k]; c[n - 1 - k] = t; }
-        R.n_cigar = n; R.cigar = ezcig; R.reach_end = 0;
-    }
+    if (i >= 0) PUSH(2, i + 1);
+    if (j >= 0) PUSH(1, j + 1);
+    FLUSH();
 #undef PUSH
 #undef FLUSH
-#undef PUSH
+    __syncwarp();
+    if (n > ezcap) { if (lane == 0) atomicOr(err, TELR_ERR_CIGCAP); n = 0; }
+    for (int k = lane; k < n >> 1; k += 32) { uint32_t t = c[k]; c[k] = c[n - 1 - k]; c[n - 1 - k] = t; }
+    if (lane == 0) { R.n_cigar = n; R.cigar = ezcig; R.reach_end = 0; }
     __syncwarp();
 }
 
