@@ -18,7 +18,10 @@ namespace telr {
 
 constexpr int AL_THREADS = 128;
 constexpr int AL_WARPS = AL_THREADS / 32;
-constexpr int AL_BLOCKS_PER_SM = 4;     // 16 resident warps per SM: the kernel is issue-bound (profiles/), more warps only add spills
+#ifndef TELR_AL_BLOCKS
+#define TELR_AL_BLOCKS 4
+#endif
+constexpr int AL_BLOCKS_PER_SM = TELR_AL_BLOCKS;     // 16 resident warps per SM: the kernel is issue-bound (profiles/), more warps only add spills
 constexpr int DPU = 4;                 // independent 32-cell chunks per lane per DP iteration
 constexpr int DP_SCOLS = 1024;         // columns of DP state kept in shared memory per warp (power of two)
 struct VecSmem;
@@ -333,8 +336,7 @@ __device__ void extd2_traceback(const DpTask &T, DpRes &R, const uint8_t *p, uin
 // returns 1 when the vectorised path produced the direction bytes (sign-bit format, vec_stride rows), 0 for the scalar path
 __device__ __forceinline__ int warp_extd2(const Opt &o, const DpTask &T, DpRes &R, DpScratch &S, unsigned long long *cells_acc, int32_t *err)
 {
-    const int ncol = vec_ncol(T.qlen, T.tlen, T.w);
-    if (S.vsm && T.qlen > 0 && T.tlen > 0 && ncol + 12 <= VSC && vec_dir_bytes(T.qlen, T.tlen, T.w) <= S.dir_cap) {
+    if (S.vsm && vec_ok(o, T.qlen, T.tlen, T.w) && vec_dir_bytes(T.qlen, T.tlen, T.w) <= S.dir_cap) {
         if (warp_extd2_vec(o, T, R, *S.vsm, S.stab, S.dir, cells_acc)) return 1;
     }
     warp_extd2_impl<false>(o, T, R, S, cells_acc, err);      // ambiguous bases or a band wider than the window: state arrays in global memory

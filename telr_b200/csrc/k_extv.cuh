@@ -1,8 +1,13 @@
 // k_extv.cuh — vectorised form of the general two-piece-affine DP (kernel (d)): extensions with exact max tracking and
-// z-drop, banded or not, left- or right-aligned gaps.  Same anti-diagonal sweep and shared-memory circular state window as
-// warp_extd2_impl<true>, but every lane owns a group of 4 consecutive columns per step: state arrays are read/written
-// as 32-bit words (4 x int8), unpacked to two 16x2 registers and run through the packed recurrence of k_fill.cuh;
-// target/query codes are staged in shared memory in chunks of 32.  Direction bytes use the sign-bit format:
+// z-drop, banded or not, left- or right-aligned gaps (ksw_extd2_sse as called by mm_align1; reference call site
+// TELR_te.py:505).  Anti-diagonal sweep over a shared-memory circular window of the six difference arrays.  Every lane
+// owns a group of 4 consecutive columns per step: state is moved as 32-bit words (4 x int8), unpacked to two 16x2
+// registers and run through the packed recurrence of k_fill.cuh.  Sequence codes are staged 128 at a time as packed
+// 2-bit streams (the query reversed, so that an anti-diagonal reads both forwards); the XOR of 4+4 codes indexes a
+// shared table of packed match/mismatch scores.  (An 8-column variant executes fewer instructions but its larger loop
+// body costs more in instruction-cache misses than it saves: measured 12 % slower end to end.)  In exact mode the running H row is updated in the same pass and the
+// row maximum (with the reference's tie order) is found with one integer key per cell and a single warp reduction.
+// Direction bytes use the sign-bit format:
 //   bits 0-3: "below the maximum" for (s,a,b,a2) [left-aligned gaps] or (b2,a,b,a2) [right-aligned]
 //   bits 4-7: "gap does not continue" for x,y,x2,y2
 // Requests that contain an ambiguous base, or whose band does not fit the window, return false and take the scalar path.
@@ -11,9 +16,10 @@
 
 namespace telr {
 
-constexpr int VSC = 1024;             // shared-memory state window (columns); covers the default alignment band (1.5 * 500 + 1) + group slack
+constexpr int VSC = 1024;             // shared-memory state window (columns), power of two
 constexpr int VCW = 1024;             // window of staged sequence codes (2 bits each), power of two
-__device__ __forceinline__ int vwr(int i) { return (VSC & (VSC - 1)) ? (int)((unsigned)(i + VSC) % (unsigned)VSC) : (i & (VSC - 1)); }   // window slot of column i (i >= -VSC)
+constexpr int VEC_MAX_NCOL = VSC - 136;   // widest live band: leaves room for one 128-code staging step + group slack (default band: 752)
+__device__ __forceinline__ int vwr(int i) { return i & (VSC - 1); }   // window slot of column i
 struct VecSmem { int8_t st[6][VSC]; int32_t H[VSC]; uint8_t tb[VCW / 4]; uint8_t qb[VCW / 4]; };
 // Score lookup: index = XOR of four packed 2-bit target codes with the four query codes they meet; value = the packed
 // match/mismatch scores of cells (0,1) and (2,3).  256 entries per CTA, filled once at kernel start.
@@ -33,11 +39,20 @@ __host__ __device__ __forceinline__ int vec_ncol(int qlen, int tlen, int w_in)
     if (ncol > w + 1) ncol = w + 1;
     return ncol;
 }
+// one row of direction bytes: the 4-column groups that overlap [st, en]
 __host__ __device__ __forceinline__ int vec_stride(int qlen, int tlen, int w_in) { return (vec_ncol(qlen, tlen, w_in) + 11) & ~3; }
 __host__ __device__ __forceinline__ int64_t vec_dir_bytes(int qlen, int tlen, int w_in)
 {
     if (qlen <= 0 || tlen <= 0) return 0;
     return (int64_t)(qlen + tlen - 1) * vec_stride(qlen, tlen, w_in);
+}
+// shape test of the vectorised path (ambiguous bases are detected while staging)
+__host__ __device__ __forceinline__ bool vec_ok(const Opt &o, int qlen, int tlen, int w_in)
+{
+    if (qlen <= 0 || tlen <= 0 || vec_ncol(qlen, tlen, w_in) > VEC_MAX_NCOL) return false;
+    // |H| must stay below 2^20 for the packed (score, rank) keys
+    const long long mab = o.a > o.b ? o.a : o.b, me = o.e > o.e2 ? o.e : o.e2;
+    return mab * (qlen < tlen ? qlen : tlen) + o.q + o.q2 + me * ((long long)qlen + tlen) < (1 << 20) - 64;
 }
 
 __device__ bool warp_extd2_vec(const Opt &o, const DpTask &T, DpRes &R, VecSmem &M, const uint2 *stab, uint8_t *p, unsigned long long *cells_acc)
@@ -50,7 +65,7 @@ __device__ bool warp_extd2_vec(const Opt &o, const DpTask &T, DpRes &R, VecSmem 
     if (q2 + e2 < q + e) { int t = q; q = q2; q2 = t; t = e; e = e2; e2 = t; }
     const int qe = q + e, qe2 = q2 + e2;
     const int w = T.w < 0 ? (tlen > qlen ? tlen : qlen) : T.w;
-    const int ncol = vec_ncol(qlen, tlen, T.w), vstride = vec_stride(qlen, tlen, T.w);
+    const int vstride = vec_stride(qlen, tlen, T.w);
     int LT = e != e2 ? (q2 - q) / (e - e2) - 1 : 0;
     if (q2 + e2 + LT * e2 > q + e + LT * e) ++LT;
     const int LD = LT * (e - e2) - (q2 - q) - e2;
@@ -59,7 +74,10 @@ __device__ bool warp_extd2_vec(const Opt &o, const DpTask &T, DpRes &R, VecSmem 
     const uint32_t QC1 = pk1(q - 1 + (RIGHT ? 1 : 0)), QC2 = pk1(q2 - 1 + (RIGHT ? 1 : 0));
     int8_t *u = M.st[0], *v = M.st[1], *x = M.st[2], *y = M.st[3], *x2 = M.st[4], *y2 = M.st[5];
     int32_t *H = M.H;
-    (void)ncol;
+    // seed roles: lanes 0..5 write one array each when a column enters the band; lanes 0..2 write the left neighbour of st
+    int8_t *const enter_arr = M.st[lane < 6 ? lane : 0];
+    const int enter_val = lane < 4 ? -qe : -qe2;
+    int8_t *const left_arr = lane == 0 ? x : lane == 1 ? x2 : v;
     int pst = -1, pen = -1, t_loaded = 0, q_loaded = 0;
     int32_t ez_max = 0, ez_max_t = -1, ez_max_q = -1, ez_mqe = KSW_NEG_INF, ez_mqe_t = -1, ez_mte = KSW_NEG_INF, ez_mte_q = -1;
     int32_t ez_score = KSW_NEG_INF, zdropped = 0, H0 = 0, last_H0_t = 0;
@@ -74,59 +92,64 @@ __device__ bool warp_extd2_vec(const Opt &o, const DpTask &T, DpRes &R, VecSmem 
         if (en > (r + w) >> 1) en = (r + w) >> 1;
         if (st > en) { zdropped = 1; break; }
         cells += (unsigned long long)(en - st + 1);
-        // ---- stage sequence codes 32 at a time (columns up to en, rows up to r - st) ----
+        // ---- stage sequence codes, 128 at a time: byte = four 2-bit codes ----
         while (t_loaded <= en) {
-            int i = t_loaded + lane, c = i < tlen ? dp_base(T.t, T.tstep, 0, i) : 0;
-            if (__any_sync(FULL, c > 3)) { bail = true; break; }
-            uint32_t pk = (uint32_t)c << (2 * (lane & 3));
-            pk |= __shfl_xor_sync(FULL, pk, 1); pk |= __shfl_xor_sync(FULL, pk, 2);
-            if (!(lane & 3)) M.tb[(i >> 2) & (VCW / 4 - 1)] = (uint8_t)pk;
-            t_loaded += 32;
+            uint32_t pk = 0; bool amb = false;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = t_loaded + 4 * lane + k, c = i < tlen ? dp_base(T.t, T.tstep, 0, i) : 0;
+                amb |= c > 3; pk |= (uint32_t)(c & 3) << (2 * k);
+            }
+            if (__any_sync(FULL, amb)) { bail = true; break; }
+            M.tb[((t_loaded >> 2) + lane) & (VCW / 4 - 1)] = (uint8_t)pk;
+            t_loaded += 128;
         }
-        while (!bail && q_loaded <= r - st) {
-            int i = q_loaded + lane, c = i < qlen ? dp_base(T.q, T.qstep, T.qcomp, i) : 0;
-            if (__any_sync(FULL, c > 3)) { bail = true; break; }
-            uint32_t pk = (uint32_t)c << (2 * (3 - (lane & 3)));      // the query runs backwards along an anti-diagonal: row i sits at stream position 3 - i
-            pk |= __shfl_xor_sync(FULL, pk, 1); pk |= __shfl_xor_sync(FULL, pk, 2);
-            if (!(lane & 3)) M.qb[(-(i >> 2)) & (VCW / 4 - 1)] = (uint8_t)pk;
-            q_loaded += 32;
+        while (!bail && q_loaded <= r - st) {      // the query runs backwards along an anti-diagonal: row i sits at stream position 3 - i
+            uint32_t pk = 0; bool amb = false;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = q_loaded + 4 * lane + k, c = i < qlen ? dp_base(T.q, T.qstep, T.qcomp, i) : 0;
+                amb |= c > 3; pk |= (uint32_t)(c & 3) << (2 * (3 - k));
+            }
+            if (__any_sync(FULL, amb)) { bail = true; break; }
+            M.qb[(-((q_loaded >> 2) + lane)) & (VCW / 4 - 1)] = (uint8_t)pk;
+            q_loaded += 128;
         }
         if (bail) break;
         // ---- seeds: entering column, top boundary, left neighbour of the first cell ----
         const int bnd = r == 0 ? -q - e : r < LT ? -e : r == LT ? LD : -e2;
-        if (lane == 0) {
-            if (en > pen) {
-                const int se = vwr(en);
-                u[se] = v[se] = x[se] = y[se] = (int8_t)(-q - e);
-                x2[se] = y2[se] = (int8_t)(-q2 - e2);
-            }
-            if (en == r) { y[vwr(r)] = (int8_t)(-q - e); y2[vwr(r)] = (int8_t)(-q2 - e2); u[vwr(r)] = (int8_t)bnd; }
-            const int sl = vwr(st - 1);
-            if (st == 0) { x[sl] = (int8_t)(-q - e); x2[sl] = (int8_t)(-q2 - e2); v[sl] = (int8_t)bnd; }
-            else if (!(st - 1 >= pst && st - 1 <= pen)) { x[sl] = (int8_t)(-q - e); x2[sl] = (int8_t)(-q2 - e2); v[sl] = (int8_t)(-q - e); }
-        }
+        if (en > pen && lane < 6) enter_arr[vwr(en)] = (int8_t)enter_val;           // u,v,x,y = -q-e; x2,y2 = -q2-e2
+        if (en == r && lane == 0) u[vwr(r)] = (int8_t)bnd;                            // (en == r implies en > pen: y, y2 are already seeded)
+        if ((st == 0 || !(st - 1 >= pst && st - 1 <= pen)) && lane < 3)
+            left_arr[vwr(st - 1)] = (int8_t)(lane == 0 ? -qe : lane == 1 ? -qe2 : st == 0 ? bnd : -qe);
+        int32_t Hp = 0;
+        if (!approx && r > 0) Hp = H[vwr(en > 0 ? en - 1 : 0)];                       // last row's H next to (or at) the entering end
         __syncwarp();
         const int gs = st >> 2, ge = en >> 2, nchunk = ((ge - gs) >> 5) + 1;
         uint8_t *pr = p + (int64_t)r * vstride - (gs << 2);
+        const int en1 = st + ((en - st) >> 2 << 2);                                    // [st, en1): the reference's 4-wide groups; [en1, en): its scalar tail
+        const unsigned n_upd = (unsigned)(en - st), n_trk = (unsigned)(en1 - st);
+        int32_t kmax = INT32_MIN;
         for (int cb = nchunk - 1; cb >= 0; --cb) {
             const int g = gs + (cb << 5) + lane;
             const bool act = g <= ge;
-            uint32_t Wu = 0, Wv = 0, Wx = 0, Wy = 0, Wx2 = 0, Wy2 = 0, Lv4 = 0, Lx4 = 0, Lx24 = 0, X4 = 0;
+            const int c0 = g << 2, gw = vwr(c0);
+            uint32_t Wu = 0, Wv = 0, Wx = 0, Wy = 0, Wx2 = 0, Wy2 = 0, Lv4 = 0, Lx4 = 0, Lx24 = 0, X = 0;
             if (act) {
-                const int gw = vwr(g << 2), gl = vwr((g << 2) - 4);
                 Wu = *reinterpret_cast<const uint32_t *>(u + gw); Wy = *reinterpret_cast<const uint32_t *>(y + gw); Wy2 = *reinterpret_cast<const uint32_t *>(y2 + gw);
                 Wv = *reinterpret_cast<const uint32_t *>(v + gw); Wx = *reinterpret_cast<const uint32_t *>(x + gw); Wx2 = *reinterpret_cast<const uint32_t *>(x2 + gw);
-                Lv4 = __byte_perm(*reinterpret_cast<const uint32_t *>(v + gl), Wv, 0x6543);
+                const int gl = vwr(c0 - 4);
+                Lv4 = __byte_perm(*reinterpret_cast<const uint32_t *>(v + gl), Wv, 0x6543);      // the same arrays, one column to the left
                 Lx4 = __byte_perm(*reinterpret_cast<const uint32_t *>(x + gl), Wx, 0x6543);
                 Lx24 = __byte_perm(*reinterpret_cast<const uint32_t *>(x2 + gl), Wx2, 0x6543);
-                const int p0 = ((g << 2) + 3 - r) & (VCW - 1);      // stream position of the query row that meets the group's first column
-                const uint32_t qh = (uint32_t)M.qb[p0 >> 2] | (uint32_t)M.qb[((p0 >> 2) + 1) & (VCW / 4 - 1)] << 8;
-                X4 = ((uint32_t)M.tb[g & (VCW / 4 - 1)] ^ (qh >> (2 * (p0 & 3)))) & 0xffu;
+                const int p0 = (c0 + 3 - r) & (VCW - 1), qi = p0 >> 2;      // stream position of the query row that meets the group's first column
+                const uint32_t qh = (uint32_t)M.qb[qi] | (uint32_t)M.qb[(qi + 1) & (VCW / 4 - 1)] << 8;
+                X = ((uint32_t)M.tb[g & (VCW / 4 - 1)] ^ (qh >> (2 * (p0 & 3)))) & 0xffu;
             }
             __syncwarp();
             if (act) {
+                const uint2 SS = stab[X];
                 uint32_t nU[2], nV[2], nX[2], nY[2], nX2[2], nY2[2], fO[2], fA[2], fB[2], fA2[2], fX[2], fY[2], fX2[2], fY2[2];
-                const uint2 SS = stab[X4];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const uint32_t sxl = h ? 0xB3A2 : 0x9180;
@@ -136,8 +159,7 @@ __device__ bool warp_extd2_vec(const Opt &o, const DpTask &T, DpRes &R, VecSmem 
                     const uint32_t A = __vadd2(Lx, Lv), A2 = __vadd2(Lx2, Lv), B = __vadd2(up_y, up_u), B2 = __vadd2(up_y2, up_u);
                     uint32_t Z = __vimax3_s16x2(S, A, B);
                     Z = __vimax3_s16x2(Z, A2, B2);
-                    const uint32_t DA = __vsub2(A, Z), DB = __vsub2(B, Z), DA2 = __vsub2(A2, Z);
-                    const uint32_t DB2 = __vsub2(B2, Z);
+                    const uint32_t DA = __vsub2(A, Z), DB = __vsub2(B, Z), DA2 = __vsub2(A2, Z), DB2 = __vsub2(B2, Z);
                     fO[h] = __vsub2(RIGHT ? B2 : S, Z);          // the one candidate the two tie-break orders do not share
                     nU[h] = __vsub2(Z, Lv); nV[h] = __vsub2(Z, up_u);
                     nX[h] = __viaddmax_s16x2(DA, NE1, NQE1); nY[h] = __viaddmax_s16x2(DB, NE1, NQE1);
@@ -156,7 +178,6 @@ __device__ bool warp_extd2_vec(const Opt &o, const DpTask &T, DpRes &R, VecSmem 
                 dw |= prmt(fY2[0], fY2[1], 0xFDB9) & 0x80808080u;
                 // Whole words are written back: cells outside [st, en] hold garbage, which is never read (a column is
                 // re-seeded when it enters the band, and the left neighbour of st is either last row's cell or a constant).
-                const int c0 = g << 2, gw = vwr(c0);
 #define PACK8(a) __byte_perm((a)[0], (a)[1], 0x6420)
                 *reinterpret_cast<uint32_t *>(u + gw) = PACK8(nU);
                 *reinterpret_cast<uint32_t *>(v + gw) = PACK8(nV);
@@ -166,38 +187,50 @@ __device__ bool warp_extd2_vec(const Opt &o, const DpTask &T, DpRes &R, VecSmem 
                 *reinterpret_cast<uint32_t *>(y2 + gw) = PACK8(nY2);
 #undef PACK8
                 *reinterpret_cast<uint32_t *>(pr + c0) = dw;
+                if (!approx && r > 0) {
+                    // H[t] += v[t] for t in [st, en); one integer key per cell orders (H, then the reference's scan order):
+                    // (t - st) = 4 * idx + cls, and among equal maxima the reference keeps the smallest (cls, idx)
+                    const int4 h4 = *reinterpret_cast<const int4 *>(H + gw);
+                    int32_t hv[4] = {h4.x, h4.y, h4.z, h4.w};
+                    const int d = c0 - st;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int32_t vk = (k & 1) ? (int32_t)nV[k >> 1] >> 16 : (int32_t)(int16_t)(nV[k >> 1] & 0xffffu);
+                        const int rel = d + k;
+                        if ((unsigned)rel < n_upd) hv[k] += vk;
+                        const int32_t key = hv[k] * 2048 + (2046 - (rel & 3) * 256 - (rel >> 2));
+                        if ((unsigned)rel < n_trk && key > kmax) kmax = key;
+                    }
+                    *reinterpret_cast<int4 *>(H + gw) = make_int4(hv[0], hv[1], hv[2], hv[3]);
+                }
             }
             __syncwarp();
         }
         if (!approx) {
             int32_t max_H, max_t, Hen, Hst;
             if (r > 0) {
-                Hen = en > 0 ? H[vwr(en - 1)] + u[vwr(en)] : H[vwr(en)] + v[vwr(en)];
-                __syncwarp();
-                const int en1 = st + (en - st) / 4 * 4;
-                int32_t bh = KSW_NEG_INF * 2; int brank = 0x7fffffff, bt = -1, hst = 0;
-                for (int t = st + lane; t < en; t += 32) {
-                    int32_t h = H[vwr(t)] + v[vwr(t)];
-                    H[vwr(t)] = h;
-                    if (t == st) hst = h;
-                    int rank = t < en1 ? 1 + (((t - st) & 3) << 20) + ((t - st) >> 2) : 1 + (4 << 20) + (t - en1);
-                    if (h > bh || (h == bh && rank < brank)) bh = h, brank = rank, bt = t;
+                Hen = Hp + (en > 0 ? (int32_t)u[vwr(en)] : (int32_t)v[vwr(0)]);
+                if (lane < 3 && en1 + lane < en) {                    // the scalar tail of the reference's row scan
+                    const int32_t key = H[vwr(en1 + lane)] * 2048 + (2046 - 1024 - lane);
+                    if (key > kmax) kmax = key;
                 }
-                if (lane == 0) { H[vwr(en)] = Hen; if (Hen >= bh) bh = Hen, brank = 0, bt = en; }
-#pragma unroll
-                for (int d = 16; d; d >>= 1) {
-                    int32_t oh = __shfl_xor_sync(FULL, bh, d); int orank = __shfl_xor_sync(FULL, brank, d), ot = __shfl_xor_sync(FULL, bt, d);
-                    if (oh > bh || (oh == bh && orank < brank)) bh = oh, brank = orank, bt = ot;
+                {   // the entering end is compared last with >=: it wins every tie
+                    const int32_t key = Hen * 2048 + 2047;
+                    if (key > kmax) kmax = key;
                 }
-                max_H = bh, max_t = bt;
-                Hst = st == en ? Hen : __shfl_sync(FULL, hst, 0);
-                __syncwarp();
+                const int32_t kall = __reduce_max_sync(FULL, kmax);
+                max_H = kall >> 11;
+                const int rk = 2047 - (kall & 2047);
+                if (rk == 0) max_t = en;
+                else { const int cls = (rk - 1) >> 8, idx = (rk - 1) & 255; max_t = cls < 4 ? st + 4 * idx + cls : en1 + idx; }
+                Hst = st == en ? Hen : H[vwr(st)];
+                if (lane == 0) H[vwr(en)] = Hen;
             } else {
                 Hen = Hst = (int32_t)v[0] - qe;
                 if (lane == 0) H[0] = Hen;
                 max_H = Hen, max_t = 0;
-                __syncwarp();
             }
+            __syncwarp();           // H[en] is read by every lane at the top of the next row
             if (en == tlen - 1 && Hen > ez_mte) ez_mte = Hen, ez_mte_q = r - en;
             if (r - st == qlen - 1 && Hst > ez_mqe) ez_mqe = Hst, ez_mqe_t = st;
             bool stop = false;
