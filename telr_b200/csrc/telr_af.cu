@@ -782,12 +782,15 @@ extern "C" int telr_af_dp(telr_af_ctx *ctx, int32_t preset, int32_t n_tasks, con
     A.warp_scratch = ctx->b_alws.as<uint8_t>(); A.work_counter = (int32_t *)(ctr + C_WORK_ALIGN); A.err = (int32_t *)(ctr + C_ERR);
     A.cells = (unsigned long long *)(ctr + C_CELLS);
     CK(cudaFuncSetAttribute(k_dp_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(AL_WARPS * sizeof(VecSmem))));
+    CK(cudaEventRecord(ctx->ev[0], st));
     k_dp_stage<<<grid, AL_THREADS, AL_WARPS * sizeof(VecSmem), st>>>(A);
+    CK(cudaEventRecord(ctx->ev[1], st));
     int64_t hc[C_SLOTS];
     CK(cudaMemcpyAsync(hc, ctr, sizeof(hc), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(out, ctx->b_in[3].p, (size_t)n_tasks * sizeof(telr_dp_out), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
+    if (ctx->census) { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); fprintf(stderr, "[census] k_dp_stage %.3f ms, %lld cells\n", ms, (long long)hc[C_CELLS]); }
     if (hc[C_ERR] & 0xffffffff) return TELR_ECAP;
     if (hc[C_NCIG]) CK(cudaMemcpy(cigar, ctx->b_cigout.p, (size_t)hc[C_NCIG] * 4, cudaMemcpyDeviceToHost));
     return TELR_OK;

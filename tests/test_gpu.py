@@ -141,6 +141,35 @@ def test_dp_stage_matches_oracle(ctx, preset):
         assert len(gc) == len(ref["cigar"]) and (gc == ref["cigar"]).all(), i
 
 
+@pytest.mark.parametrize("flag", [0x40, 0xC2, 0x00, 0x42, 0x08])
+def test_dp_small_shapes_match_oracle(ctx, flag):
+    """Every lane-group / window edge of the DP kernels: 1x1 up to band-limited shapes, both gap alignments,
+    extension / global / approximate-max flags (ksw_extd2 flag bits, minimap2 ksw2.h)."""
+    rng = np.random.default_rng(5 + flag)
+    o = orc.opt(0)
+    shapes = [(1, 1, 751), (1, 7, 751), (3, 5, 751), (4, 4, 751), (5, 9, 751), (8, 8, 751), (9, 9, 751), (9, 12, 751), (12, 9, 751),
+              (13, 13, 751), (16, 16, 751), (9, 17, 751), (33, 40, 751), (64, 64, 751), (100, 130, 751), (129, 200, 751),
+              (255, 256, 751), (256, 257, 751), (300, 350, 751), (700, 900, 751), (300, 300, 20), (900, 1000, 100), (40, 2000, 751), (2000, 40, 751)]
+    tasks, qs, ts_ = [], [], []
+    qo = to = 0
+    for (ql, tl, w) in shapes:
+        for rep in range(2):
+            t = rng.integers(0, 4, tl).astype(np.uint8)
+            q = _mut(rng, np.resize(t, max(ql * 2, 4)), .12)[:ql]
+            if len(q) == 0:
+                q = np.zeros(1, np.uint8)
+            ww = -1 if flag == 0x08 else w
+            tasks.append((qo, to, len(q), len(t), ww, 400, -1, flag)); qs.append(q); ts_.append(t); qo += len(q); to += len(t)
+    out, cig = ctx.dp(0, np.array(tasks, lib.DPTASK_DTYPE), np.concatenate(qs), np.concatenate(ts_))
+    for i, (q, t) in enumerate(zip(qs, ts_)):
+        w, zd, eb, fl = tasks[i][4:]
+        ref = orc.ksw_extd2(q, t, o, w, zd, eb, fl); g = out[i]
+        names = ["zdropped", "cells"] + ([] if fl & 0x08 else ["max", "max_q", "max_t"])
+        assert all(int(ref[n]) == int(g[n]) for n in names), (i, len(q), len(t), {n: (int(ref[n]), int(g[n])) for n in names})
+        gc = cig[g["cigar_off"]: g["cigar_off"] + g["n_cigar"]]
+        assert len(gc) == len(ref["cigar"]) and (gc == ref["cigar"]).all(), (i, len(q), len(t))
+
+
 @pytest.mark.parametrize("cfg,n,kw", [("ont_3k_50x", 10, {}), ("clr_3k_40x", 6, {}), ("hifi_3k_40x", 6, {}),
                                       ("poly_10k_200x", 2, dict(depth=60)), ("ont_3k_50x", 4, dict(p_n=0.002))])
 def test_full_pipeline_matches_oracle(ctx, cfg, n, kw):
