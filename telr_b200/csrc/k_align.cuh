@@ -541,8 +541,8 @@ __global__ void __launch_bounds__(AL_THREADS, AL_BLOCKS_PER_SM) k_al_fused(const
 // deferred statistics + final region pass + outputs, one thread per problem
 __global__ void __launch_bounds__(128) k_al_finish(const __grid_constant__ AlignArgs A)
 {
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= A.n_work) return;
+    const int w = tp_problem<TP_FINISH>(A.n_work);
+    if (w < 0) return;
     AlnCtx &c = A.actx[w];
     const int pidx = A.work[w].pidx;
     const int read = A.prob_read[pidx], strand = A.prob_ls[pidx] & 1;

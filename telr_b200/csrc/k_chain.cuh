@@ -14,7 +14,10 @@
 
 namespace telr {
 
-constexpr int CH_THREADS = 256;
+#ifndef TELR_CH_THREADS
+#define TELR_CH_THREADS 1024
+#endif
+constexpr int CH_THREADS = TELR_CH_THREADS;
 constexpr int CH_WARPS = CH_THREADS / 32;
 constexpr int IDX_SLOTS = 8192;          // power of two
 constexpr int IDX_MAXMZ = 4096;          // contig minimizers that fit the shared-memory index
@@ -96,7 +99,7 @@ __device__ void idx_build(IdxSmem &I, const Opt &o, int n_c, const uint64_t *cx,
     {   // exclusive scan of cnt over slots -> start; 32 slots per thread
         int sum = 0;
         for (int c = 0; c < IDX_SLOTS / CH_THREADS; ++c) sum += (int)I.cnt[tid * (IDX_SLOTS / CH_THREADS) + c];
-        int tot, pre = block_excl_scan(sum, &tot, I.ws);
+        int tot, pre = block_excl_scan_t<CH_THREADS>(sum, &tot, I.ws);
         for (int c = 0; c < IDX_SLOTS / CH_THREADS; ++c) {
             int s = tid * (IDX_SLOTS / CH_THREADS) + c;
             I.start[s] = (uint16_t)pre;
@@ -484,10 +487,24 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const __grid_constant__ Ch
 }
 
 // ---- sequential steps, one THREAD per problem (latency hidden by thread-level parallelism) ----
+// Sequential per-problem kernels: only every TP_STRIDE-th lane owns a problem.  A warp of 32 unrelated sequential
+// jobs executes the union of their control paths (6 of 32 threads active on average, ncu); spreading the jobs over
+// 32 / TP_STRIDE times more warps trades idle lanes, which these latency-bound kernels do not miss, for divergence.
+constexpr int TP_CHAIN = 32;      // k_chain_sort / k_chain_bt / k_chain_regs: one problem per warp (seed+chain stage 48.0 -> 33.0 ms at 296 loci)
+constexpr int TP_FINISH = 8;      // k_al_finish: four problems per warp (11.4 -> 7.5 ms)
+template <int STRIDE> __host__ __device__ __forceinline__ int tp_blocks(int n_prob, int threads) { return (int)(((long long)n_prob * STRIDE + threads - 1) / threads); }
+template <int STRIDE> __device__ __forceinline__ int tp_problem(int n_prob)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t % STRIDE) return -1;
+    const int p = t / STRIDE;
+    return p < n_prob ? p : -1;
+}
+
 __global__ void __launch_bounds__(128) k_chain_sort(const __grid_constant__ ChainArgs A)
 {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= A.n_prob) return;
+    const int p = tp_problem<TP_CHAIN>(A.n_prob);
+    if (p < 0) return;
     const int n_a = (int)(A.prob_aoff[p + 1] - A.prob_aoff[p]);
     A.prob_nu[p] = 0; A.prob_m[p] = 0; A.prob_nregs[p] = 0; A.prob_nca[p] = 0;
     if (n_a == 0) return;
@@ -513,8 +530,8 @@ __global__ void __launch_bounds__(256) k_chain_dp(const __grid_constant__ ChainA
 
 __global__ void __launch_bounds__(128) k_chain_bt(const __grid_constant__ ChainArgs A)
 {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= A.n_prob) return;
+    const int p = tp_problem<TP_CHAIN>(A.n_prob);
+    if (p < 0) return;
     const int n_a = (int)(A.prob_aoff[p + 1] - A.prob_aoff[p]);
     if (n_a == 0) return;
     const Opt &o = A.o;
@@ -553,8 +570,8 @@ __global__ void __launch_bounds__(256) k_chain_rmq(const __grid_constant__ Chain
 
 __global__ void __launch_bounds__(128) k_chain_regs(const __grid_constant__ ChainArgs A)
 {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= A.n_prob) return;
+    const int p = tp_problem<TP_CHAIN>(A.n_prob);
+    if (p < 0) return;
     const int n_a = (int)(A.prob_aoff[p + 1] - A.prob_aoff[p]);
     if (n_a == 0) return;
     const Opt &o = A.o;

@@ -38,7 +38,8 @@ struct SketchArgs {
     uint64_t *mz_x; uint32_t *mz_y;
 };
 
-__device__ __forceinline__ int block_excl_scan(int v, int *total, int *smem_ws /* >= 9 ints */)
+// exclusive scan over the NT threads of a CTA (NT a multiple of 32, <= 1024); smem_ws >= 33 ints
+template <int NT> __device__ __forceinline__ int block_excl_scan_t(int v, int *total, int *smem_ws)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int x = v;
@@ -50,20 +51,21 @@ __device__ __forceinline__ int block_excl_scan(int v, int *total, int *smem_ws /
     if (lane == 31) smem_ws[wid] = x;
     __syncthreads();
     if (wid == 0) {
-        int s = lane < (SK_THREADS / 32) ? smem_ws[lane] : 0;
+        int s = lane < (NT / 32) ? smem_ws[lane] : 0;
 #pragma unroll
-        for (int d = 1; d < 8; d <<= 1) {
+        for (int d = 1; d < 32; d <<= 1) {
             int y = __shfl_up_sync(0xffffffffu, s, d);
             if (lane >= d) s += y;
         }
-        if (lane < SK_THREADS / 32) smem_ws[lane] = s;
+        if (lane < NT / 32) smem_ws[lane] = s;
     }
     __syncthreads();
     int base = wid ? smem_ws[wid - 1] : 0;
-    *total = smem_ws[SK_THREADS / 32 - 1];
+    *total = smem_ws[NT / 32 - 1];
     __syncthreads();
     return base + x - v;
 }
+__device__ __forceinline__ int block_excl_scan(int v, int *total, int *smem_ws) { return block_excl_scan_t<SK_THREADS>(v, total, smem_ws); }
 
 struct SkSmem {
     uint64_t X[SK_XH + SK_TILE];
@@ -72,7 +74,7 @@ struct SkSmem {
     uint8_t code[SK_CH + SK_TILE + 8];
     uint8_t z[SK_XH + SK_TILE];
     uint8_t lcap[SK_TILE];
-    int ws[16];
+    int ws[40];
 };
 
 // pushes of the sequential algorithm at local step j (0-based in tile); X index = SK_XH + j

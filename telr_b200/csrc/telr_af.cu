@@ -248,12 +248,12 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
     ca.prob_nu = ctx->b_pnu.as<int32_t>(); ca.prob_m = ctx->b_pm.as<int32_t>(); ca.n_prob = n_prob;
     k_chain<<<ch_grid, CH_THREADS, ch_smem, st>>>(ca);
     {
-        const int tb = (n_prob + 127) / 128, wg = std::max(1, std::min((n_prob + 7) / 8, sm * 8));
-        k_chain_sort<<<tb, 128, 0, st>>>(ca);
+        const int tpb = tp_blocks<TP_CHAIN>(n_prob, 128), wg = std::max(1, std::min((n_prob + 7) / 8, sm * 8));
+        k_chain_sort<<<tpb, 128, 0, st>>>(ca);
         k_chain_dp<<<wg, 256, 0, st>>>(ca);
-        k_chain_bt<<<tb, 128, 0, st>>>(ca);
+        k_chain_bt<<<tpb, 128, 0, st>>>(ca);
         k_chain_rmq<<<wg, 256, 0, st>>>(ca);
-        k_chain_regs<<<tb, 128, 0, st>>>(ca);
+        k_chain_regs<<<tpb, 128, 0, st>>>(ca);
     }
     CK(cudaEventRecord(ctx->ev[2], st));
     // ---- (d) alignment ----
@@ -343,7 +343,7 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
         k_al_init<<<tb, 128, 0, st>>>(aa);
         CK(cudaFuncSetAttribute(k_al_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(AL_WARPS * sizeof(VecSmem))));
         k_al_fused<<<al_grid, AL_THREADS, AL_WARPS * sizeof(VecSmem), st>>>(aa);
-        k_al_finish<<<tb, 128, 0, st>>>(aa);
+        k_al_finish<<<tp_blocks<TP_FINISH>(n_work, 128), 128, 0, st>>>(aa);
     }
     CK(cudaEventRecord(ctx->ev[4], st));
     // ---- (e)+(f) depth, medians, AF ----
