@@ -839,6 +839,7 @@ static void append_cigar(actx_t *c, reg_t *r, uint32_t n_cigar, const uint32_t *
 int64_t orc_cell_stats[8];   /* debugging: cells by task class */
 int64_t orc_size_hist[4][16];
 int64_t orc_tlen_hist[64], orc_qlen_hist[64];
+int64_t orc_fill_model[4];   /* debugging: fill cells; cell slots of the 8-column systolic mapping; of a flexible-width mapping */
 static void align_pair(actx_t *c, int qlen, const uint8_t *qseq, int tlen, const uint8_t *tseq, int w, int end_bonus,
                        int zdrop, int flag)
 {
@@ -870,6 +871,22 @@ static void align_pair(actx_t *c, int qlen, const uint8_t *qseq, int tlen, const
             orc_tlen_hist[tb] += ez->cells;
 #pragma omp atomic
             orc_qlen_hist[qb] += ez->cells;
+            {
+                int64_t npairs = (qlen + 1) / 2, stepsA = 0, slotsB;
+                for (int t0 = 0; t0 < tlen; t0 += 256) {
+                    int rem = tlen - t0, nlive = rem >= 256 ? 32 : (rem + 7) / 8;
+                    stepsA += npairs + nlive - 1;
+                }
+                int fc = (tlen + 31) / 32; fc += fc & 1; if (fc < 2) fc = 2;
+                if (fc <= 16) { int nlive = (tlen + fc - 1) / fc; slotsB = (npairs + nlive - 1) * 32 * (fc + 1) * 2; }
+                else { int np = (tlen + 511) / 512; slotsB = (int64_t)np * (npairs + 31) * 32 * 17 * 2; }
+#pragma omp atomic
+                orc_fill_model[0] += ez->cells;
+#pragma omp atomic
+                orc_fill_model[1] += stepsA * 32 * 18;
+#pragma omp atomic
+                orc_fill_model[2] += slotsB;
+            }
         }
     }
 }

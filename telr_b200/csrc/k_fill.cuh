@@ -226,8 +226,12 @@ __device__ bool warp_fill_fast(const Opt &o, const DpTask &T, DpRes &R, uint8_t 
         if (__any_sync(0xffffffffu, n)) return false;
     }
     if (o.a > 127 || o.b > 127) return false;            // score tables are int8
+#if defined(TELR_FILL_FC12) && TELR_FILL_FC12
+    if (fill_width(T.tlen) == 12) warp_fill_fwd<12>(o, T, R, dir, bnd, cells_acc);
+    else
+#endif
     warp_fill_fwd<8>(o, T, R, dir, bnd, cells_acc);     // a second instantiation (12 columns per lane) halves the passes of 257..384-column fills but
-                                                         // doubles the hot code: measured 35 % slower end to end (instruction-cache misses), so it stays off
+                                                         // doubles the hot code: measured slower end to end (instruction-cache misses), so it stays off
     return true;
 }
 

@@ -77,28 +77,47 @@ struct SkSmem {
     int ws[40];
 };
 
-// pushes of the sequential algorithm at local step j (0-based in tile); X index = SK_XH + j
+// pushes of the sequential algorithm at local step j (0-based in tile); X index = SK_XH + j.
+// One scan over steps -(w-1)..-1 yields the window minimum m1 (rightmost on ties), its distance d1 and how many
+// entries equal it; the minimum over -w..-1 (mp), the one over -(w-1)..0 (mn) and the number of identical-hash
+// duplicates each case would flush follow from m1, X[-w] and X[0] without further loops.  The duplicate-flush loops
+// themselves only run when such duplicates exist (tandem repeats).
 template <class Emit> __device__ __forceinline__ void sk_step(const SkSmem &S, int j, int w, int k, Emit &emit)
 {
     const uint64_t MAXV = ~0ULL;
     const uint64_t *X = S.X + SK_XH + j;        // X[0] = this step, X[-d] = d steps back
-    const uint64_t info = X[0];
+    const uint64_t info = X[0], xw = X[-w];
     const int l = S.lcap[j];
-    uint64_t mp = MAXV; int mpd = w;            // previous minimum over steps -w..-1 (rightmost on ties)
-    for (int d = w; d >= 1; --d) { uint64_t v = X[-d]; if (v <= mp) mp = v, mpd = d; }
+    uint64_t m1 = MAXV; int d1 = w - 1, c1 = 0;
+    for (int d = w - 1; d >= 1; --d) {
+        const uint64_t v = X[-d];
+        if (v < m1) m1 = v, d1 = d, c1 = 1;
+        else if (v == m1) d1 = d, ++c1;
+    }
+    if (w < 2) c1 = 0;
+    // previous minimum over steps -w..-1 (rightmost on ties)
+    const bool from_w = xw < m1;
+    const uint64_t mp = from_w ? xw : m1;
+    const int mpd = (from_w || w < 2) ? w : d1;
     if (l == w + k - 1 && mp != MAXV) {
-        for (int d = w - 1; d >= 1; --d)
-            if (X[-d] == mp && d != mpd) emit(j - d);
+        const int dup = from_w ? 0 : c1 - 1;      // other entries of -(w-1)..-1 equal to mp
+        if (dup > 0)
+            for (int d = w - 1; d >= 1; --d)
+                if (X[-d] == mp && d != mpd) emit(j - d);
     }
     if (info <= mp) {
         if (l >= w + k && mp != MAXV) emit(j - mpd);
     } else if (mpd == w) {
         if (l >= w + k - 1 && mp != MAXV) emit(j - mpd);
-        uint64_t mn = MAXV; int mnd = w - 1;
-        for (int d = w - 1; d >= 0; --d) { uint64_t v = X[-d]; if (v <= mn) mn = v, mnd = d; }
+        // new minimum over steps -(w-1)..0 (rightmost on ties)
+        const bool from_0 = info <= m1;
+        const uint64_t mn = from_0 ? info : m1;
+        const int mnd = from_0 ? 0 : d1;
         if (l >= w + k - 1 && mn != MAXV) {
-            for (int d = w - 1; d >= 0; --d)
-                if (X[-d] == mn && d != mnd) emit(j - d);
+            const int dup = info == m1 ? c1 : from_0 ? 0 : c1 - 1;
+            if (dup > 0)
+                for (int d = w - 1; d >= 0; --d)
+                    if (X[-d] == mn && d != mnd) emit(j - d);
         }
     }
 }
