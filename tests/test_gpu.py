@@ -210,6 +210,52 @@ def test_edge_cases_empty_and_ragged(ctx):
     assert r0.cov2x.shape == (0, 8)
 
 
+def test_degenerate_reads_and_contigs(ctx):
+    """Inputs the reference would still hand to minimap2/samtools: reads shorter than a k-mer, all-N reads, N every few
+    bases, a read identical to the contig, N runs inside the contig, a TE annotation touching both contig ends."""
+    from telr_b200.batch import Batch, pack_sequences, name_hash
+    rng = np.random.default_rng(99)
+    base = synth.generate("ont_3k_50x", 0, 3, depth=6)
+    ACGT = np.frombuffer(b"ACGTN", np.uint8)
+    seqs, read_len, lrb = [], [], [0]
+    contigs = []
+    for l in range(3):
+        c = base.unpack(int(base.contig_off[l]), int(base.contig_len[l])).copy()
+        if l == 1:
+            c[500:520] = 4; c[1200] = 4                       # N run + single N in the contig
+        contigs.append(c)
+        reads = [base.unpack(int(base.read_off[r]), int(base.read_len[r])) for r in range(base.locus_read_begin[l], base.locus_read_begin[l + 1])]
+        reads += [np.array([0], np.uint8), rng.integers(0, 4, 14).astype(np.uint8), rng.integers(0, 4, 15).astype(np.uint8),
+                  np.full(300, 4, np.uint8), c.copy(), c[::-1].copy() ^ 3 if l != 1 else c[:40].copy()]
+        nr = reads[0].copy(); nr[::7] = 4; reads.append(nr)          # an ambiguous base every 7: no k-mer survives
+        nr = reads[1].copy(); nr[100:103] = 4; nr[900] = 4; reads.append(nr)
+        seqs += [bytes(ACGT[r]) for r in reads]
+        lrb.append(len(seqs))
+    n_reads = len(seqs)
+    seqs += [bytes(ACGT[c]) for c in contigs]
+    seq2, nmask, offs, lens = pack_sequences(seqs)
+    te_s = base.te_start.copy(); te_e = base.te_end.copy()
+    te_s[2] = 0; te_e[2] = int(base.contig_len[2])               # TE covers the whole contig: every flank window is clamped
+    b = Batch(base.preset, seq2, nmask, offs[:n_reads].copy(), lens[:n_reads].copy(),
+              np.array([name_hash("r%d" % i) for i in range(n_reads)], np.uint32), np.array(lrb, np.int32),
+              offs[n_reads:].copy(), lens[n_reads:].copy(), te_s, te_e)
+    for k in ("flank_len", "flank_off", "te_len", "te_off"):
+        if hasattr(base, k):
+            setattr(b, k, getattr(base, k))
+    r = ctx.run(b, want_depth=True, want_aln=True)
+    ro = orc.af_run(b, threads=0)
+    util.assert_same_results(r, ro)
+    assert r.c.dp_cells == ro.c.dp_cells
+
+
+def test_long_read_config_matches_oracle(ctx):
+    b = synth.generate("ont_30k_30x", 0, 2, depth=5)
+    r = ctx.run(b, want_depth=True, want_aln=True)
+    ro = orc.af_run(b, threads=0)
+    util.assert_same_results(r, ro)
+    assert r.c.dp_cells == ro.c.dp_cells
+
+
 def test_chunking_and_rerun_are_identical(built, monkeypatch):
     b = synth.generate("ont_3k_50x", 0, 12, depth=12)
     c1 = lib.Context(0)
