@@ -130,6 +130,9 @@ __device__ bool warp_extd2_vec(const Opt &o, const DpTask &T, DpRes &R, VecSmem 
         const int en1 = st + ((en - st) >> 2 << 2);                                    // [st, en1): the reference's 4-wide groups; [en1, en): its scalar tail
         const unsigned n_upd = (unsigned)(en - st), n_trk = (unsigned)(en1 - st);
         int32_t kmax = INT32_MIN;
+        int kc[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) kc[k] = 2046 - ((k - st) & 3) * 256 - ((k - st) >> 2);
         for (int cb = nchunk - 1; cb >= 0; --cb) {
             const int g = gs + (cb << 5) + lane;
             const bool act = g <= ge;
@@ -198,7 +201,8 @@ __device__ bool warp_extd2_vec(const Opt &o, const DpTask &T, DpRes &R, VecSmem 
                         const int32_t vk = (k & 1) ? (int32_t)nV[k >> 1] >> 16 : (int32_t)(int16_t)(nV[k >> 1] & 0xffffu);
                         const int rel = d + k;
                         if ((unsigned)rel < n_upd) hv[k] += vk;
-                        const int32_t key = hv[k] * 2048 + (2046 - (rel & 3) * 256 - (rel >> 2));
+                        // rank code 2046 - cls * 256 - idx with cls = (k - st) & 3 and idx = g + ((k - st) >> 2): kc[k] is uniform over the row
+                        const int32_t key = hv[k] * 2048 + (kc[k] - g);
                         if ((unsigned)rel < n_trk && key > kmax) kmax = key;
                     }
                     *reinterpret_cast<int4 *>(H + gw) = make_int4(hv[0], hv[1], hv[2], hv[3]);

@@ -102,7 +102,7 @@ __device__ void warp_fill_fwd(const Opt &o, const DpTask &T, DpRes &R, uint8_t *
             const int r = t0 + k;
             Uu[k] = pk2(0, BNDF(r)); Uy[k] = pk2(0, -qe); Uy2[k] = pk2(0, -qe2);
         }
-        uint32_t inV = 0, inX = 0, inX2 = 0, inQ = 0, Ufirst = 0;
+        uint32_t inV = 0, inX = 0, inX2 = 0, Ufirst = 0;
         const bool last_pass = pass == npass - 1;
         const int nlive = tlen - pass * FW >= FW ? 32 : (tlen - pass * FW + FC - 1) / FC;      // lanes that own columns in this pass
         for (int s = 0; s < npairs + nlive - 1; ++s) {
@@ -110,10 +110,6 @@ __device__ void warp_fill_fwd(const Opt &o, const DpTask &T, DpRes &R, uint8_t *
             const bool active = live && m >= 0 && m < npairs;
             if (lane == 0 && s < npairs) {
                 const int j = 2 * s;
-                // the two query bases of this row pair travel as the PRMT selector that looks them up in the score tables:
-                // lo half <- sign-extended byte q[j] of the first table, hi half <- byte q[j+1] of the second
-                const uint32_t q0 = Q[j], q1 = j + 1 < qlen ? Q[j + 1] : 0;
-                inQ = q0 | (q0 | 8u) << 4 | (q1 + 4u) << 8 | (q1 + 12u) << 12;
                 if (pass == 0) {
                     inV = pk2(BNDF(j), BNDF(j + 1)); inX = NQE1; inX2 = NQE2;
                 } else { inV = bnd[3 * s]; inX = bnd[3 * s + 1]; inX2 = bnd[3 * s + 2]; }
@@ -121,6 +117,10 @@ __device__ void warp_fill_fwd(const Opt &o, const DpTask &T, DpRes &R, uint8_t *
             uint32_t outV = 0, outX = 0, outX2 = 0;
             if (active) {
                 const int j = 2 * m;
+                // the two query bases of this row pair become the PRMT selector that looks them up in the score tables:
+                // lo half <- sign-extended byte q[j] of the first table, hi half <- byte q[j+1] of the second
+                const uint32_t q0 = Q[j], q1 = j + 1 < qlen ? Q[j + 1] : 0;
+                const uint32_t inQ = q0 | (q0 | 8u) << 4 | (q1 + 4u) << 8 | (q1 + 12u) << 12;
                 uint32_t Lv = inV, Lx = inX, Lx2 = inX2, pu = 0, py = 0, py2 = 0, kV = 0, kX = 0, kX2 = 0;
                 uint32_t W[FC / 2 + 1];             // W[p]: flag bytes of cells (2p, j), (2p-1, j+1), (2p+1, j), (2p, j+1)
                 uint32_t eDS = 0, eDA = 0, eDB = 0, eDA2 = 0, eCX = 0, eCY = 0, eCX2 = 0, eCY2 = 0;   // even iteration, waiting for its partner
@@ -191,8 +191,7 @@ __device__ void warp_fill_fwd(const Opt &o, const DpTask &T, DpRes &R, uint8_t *
             }
             // systolic hand-over to the next lane (used by it in the next step)
             const uint32_t sV = __shfl_up_sync(FULL, outV, 1), sX = __shfl_up_sync(FULL, outX, 1), sX2 = __shfl_up_sync(FULL, outX2, 1);
-            const uint32_t sQ = __shfl_up_sync(FULL, inQ, 1);
-            if (lane > 0) { inV = sV; inX = sX; inX2 = sX2; inQ = sQ; }
+            if (lane > 0) { inV = sV; inX = sX; inX2 = sX2; }
         }
         // u of the last query row for this lane's columns (score = boundary + sum of u along the last row)
         if (live) {
