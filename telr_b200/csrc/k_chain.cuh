@@ -19,17 +19,25 @@ namespace telr {
 #endif
 constexpr int CH_THREADS = TELR_CH_THREADS;
 constexpr int CH_WARPS = CH_THREADS / 32;
-constexpr int IDX_SLOTS = 8192;          // power of two
-constexpr int IDX_MAXMZ = 4096;          // contig minimizers that fit the shared-memory index
-
+// Contig minimizer index: open-addressing table (hash -> occurrence list).  Contigs with up to IDX_MAXMZ minimizers
+// (~22 kb) use the shared-memory instance; longer ones (up to IDX_BIG_MAXMZ, ~360 kb) a per-CTA slice of global
+// memory (L2-resident) with the same code.
+template <int SLOTS, int MAXMZ, class U> struct IdxT {
+    static constexpr int kSlots = SLOTS, kMax = MAXMZ;
+    using slot_t = U;
+    uint64_t keys[SLOTS];
+    uint32_t cnt[SLOTS];
+    uint32_t fill[SLOTS];
+    U start[SLOTS];
+    uint32_t occ_y[MAXMZ];
+    U slot_of[MAXMZ];
+    uint8_t occ_span[MAXMZ];
+};
+constexpr int IDX_MAXMZ = 4096, IDX_BIG_MAXMZ = 65536;
+using IdxSmall = IdxT<8192, IDX_MAXMZ, uint16_t>;
+using IdxBig = IdxT<131072, IDX_BIG_MAXMZ, uint32_t>;
 struct IdxSmem {
-    uint64_t keys[IDX_SLOTS];
-    uint32_t cnt[IDX_SLOTS];
-    uint32_t fill[IDX_SLOTS];
-    uint16_t start[IDX_SLOTS];
-    uint32_t occ_y[IDX_MAXMZ];
-    uint16_t slot_of[IDX_MAXMZ];
-    uint8_t occ_span[IDX_MAXMZ];
+    IdxSmall t;
     int hist[260];
     int ws[40];
     int mid_occ, n_keys, item;
@@ -54,6 +62,7 @@ struct ChainArgs {
     uint8_t *prob_scratch; const int64_t *prob_soff;
     int32_t *prob_nu, *prob_m;      // chains found; anchors to re-chain (0 = no re-chaining)
     int32_t n_prob;
+    IdxBig *idx_big;                // [gridDim.x] global-memory index slices for long contigs
 };
 
 __device__ __forceinline__ void prob_carve(const ChainArgs &A, int p, int n_a, ChainScratch &cs, HitScratch &hs, int *cap_regs)
@@ -67,59 +76,60 @@ __device__ __forceinline__ void prob_carve(const ChainArgs &A, int p, int n_a, C
 __device__ __forceinline__ uint32_t idx_hash(uint64_t key) { return (uint32_t)(mix64(key) >> 24); }
 
 // occurrences of a minimizer hash in the contig index
-__device__ __forceinline__ int idx_lookup(const IdxSmem &I, uint64_t key, int *start)
+template <class IDX> __device__ __forceinline__ int idx_lookup(const IDX &I, uint64_t key, int *start)
 {
-    uint32_t s = idx_hash(key) & (IDX_SLOTS - 1);
+    uint32_t s = idx_hash(key) & (IDX::kSlots - 1);
     for (;;) {
         uint64_t kk = I.keys[s];
-        if (kk == key) { *start = I.start[s]; return (int)I.cnt[s]; }
+        if (kk == key) { *start = (int)I.start[s]; return (int)I.cnt[s]; }
         if (kk == ~0ULL) return 0;
-        s = (s + 1) & (IDX_SLOTS - 1);
+        s = (s + 1) & (IDX::kSlots - 1);
     }
 }
 
-__device__ void idx_build(IdxSmem &I, const Opt &o, int n_c, const uint64_t *cx, const uint32_t *cy)
+template <class IDX> __device__ void idx_build(IDX &I, IdxSmem &C, const Opt &o, int n_c, const uint64_t *cx, const uint32_t *cy)
 {
     const int tid = threadIdx.x;
-    for (int i = tid; i < IDX_SLOTS; i += CH_THREADS) I.keys[i] = ~0ULL, I.cnt[i] = 0, I.fill[i] = 0;
-    for (int i = tid; i < 260; i += CH_THREADS) I.hist[i] = 0;
+    constexpr int SLOTS = IDX::kSlots;
+    for (int i = tid; i < SLOTS; i += CH_THREADS) I.keys[i] = ~0ULL, I.cnt[i] = 0, I.fill[i] = 0;
+    for (int i = tid; i < 260; i += CH_THREADS) C.hist[i] = 0;
     __syncthreads();
     for (int i = tid; i < n_c; i += CH_THREADS) {
         const uint64_t key = cx[i] >> 8;
-        uint32_t s = idx_hash(key) & (IDX_SLOTS - 1);
+        uint32_t s = idx_hash(key) & (SLOTS - 1);
         for (;;) {
             unsigned long long old = atomicCAS((unsigned long long *)&I.keys[s], ~0ULL, (unsigned long long)key);
             if (old == ~0ULL || old == key) break;
-            s = (s + 1) & (IDX_SLOTS - 1);
+            s = (s + 1) & (SLOTS - 1);
         }
         atomicAdd(&I.cnt[s], 1u);
-        I.slot_of[i] = (uint16_t)s;
+        I.slot_of[i] = (typename IDX::slot_t)s;
     }
     __syncthreads();
-    {   // exclusive scan of cnt over slots -> start; 32 slots per thread
+    {   // exclusive scan of cnt over slots -> start
         int sum = 0;
-        for (int c = 0; c < IDX_SLOTS / CH_THREADS; ++c) sum += (int)I.cnt[tid * (IDX_SLOTS / CH_THREADS) + c];
-        int tot, pre = block_excl_scan_t<CH_THREADS>(sum, &tot, I.ws);
-        for (int c = 0; c < IDX_SLOTS / CH_THREADS; ++c) {
-            int s = tid * (IDX_SLOTS / CH_THREADS) + c;
-            I.start[s] = (uint16_t)pre;
+        for (int c = 0; c < SLOTS / CH_THREADS; ++c) sum += (int)I.cnt[tid * (SLOTS / CH_THREADS) + c];
+        int tot, pre = block_excl_scan_t<CH_THREADS>(sum, &tot, C.ws);
+        for (int c = 0; c < SLOTS / CH_THREADS; ++c) {
+            int s = tid * (SLOTS / CH_THREADS) + c;
+            I.start[s] = (typename IDX::slot_t)pre;
             pre += (int)I.cnt[s];
         }
     }
     __syncthreads();
     for (int i = tid; i < n_c; i += CH_THREADS) {
-        int s = I.slot_of[i];
-        int at = I.start[s] + (int)atomicAdd(&I.fill[s], 1u);
+        int s = (int)I.slot_of[i];
+        int at = (int)I.start[s] + (int)atomicAdd(&I.fill[s], 1u);
         I.occ_y[at] = cy[i];
         I.occ_span[at] = (uint8_t)(cx[i] & 0xff);
     }
     __syncthreads();
     // lists in (span, position) order == the order minimap2's per-bucket sort leaves (buckets <= 64 entries)
-    for (int s = tid; s < IDX_SLOTS; s += CH_THREADS) {
+    for (int s = tid; s < SLOTS; s += CH_THREADS) {
         int c = (int)I.cnt[s];
-        if (c > 0) atomicAdd(&I.hist[c < 255 ? c : 255], 1);
+        if (c > 0) atomicAdd(&C.hist[c < 255 ? c : 255], 1);
         if (c > 1) {
-            int b = I.start[s];
+            int b = (int)I.start[s];
             for (int i = 1; i < c; ++i) {
                 uint32_t y = I.occ_y[b + i]; uint8_t sp = I.occ_span[b + i];
                 uint64_t kk = (uint64_t)sp << 32 | y;
@@ -135,17 +145,17 @@ __device__ void idx_build(IdxSmem &I, const Opt &o, int n_c, const uint64_t *cx,
     __syncthreads();
     if (tid == 0) {     // mm_idx_cal_max_occ + mm_mapopt_update
         int nk = 0;
-        for (int c = 1; c <= 255; ++c) nk += I.hist[c];
+        for (int c = 1; c <= 255; ++c) nk += C.hist[c];
         int mid = 0x7fffffff;
         if (nk > 0 && o.mid_occ_frac > 0.f) {
             uint32_t kk = (uint32_t)((1. - (double)o.mid_occ_frac) * nk);
             int acc = 0, c;
-            for (c = 1; c <= 255; ++c) { acc += I.hist[c]; if ((uint32_t)acc > kk) break; }
+            for (c = 1; c <= 255; ++c) { acc += C.hist[c]; if ((uint32_t)acc > kk) break; }
             mid = c + 1;
         }
         if (mid < o.min_mid_occ) mid = o.min_mid_occ;
         if (o.max_mid_occ > o.min_mid_occ && mid > o.max_mid_occ) mid = o.max_mid_occ;
-        I.mid_occ = mid; I.n_keys = nk;
+        C.mid_occ = mid; C.n_keys = nk;
     }
     __syncthreads();
 }
@@ -376,18 +386,106 @@ __device__ void chain_rmq_warp(const Opt &o, int n, const Anchor *a, ChainScratc
     }
 }
 
+// one (locus, strand) item: build the index, then stream the locus's reads against it (warp per read)
+template <class IDX>
+__device__ void chain_item(const ChainArgs &A, IDX &I, IdxSmem &C, int item, int rb, int nr, int strand, int64_t cb, int n_c)
+{
+    const Opt &o = A.o;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned FULL = 0xffffffffu;
+    (void)tid;
+    idx_build(I, C, o, n_c, A.mz_x + cb, A.mz_y + cb);
+    const int mid_occ = C.mid_occ;
+    for (int r = wid; r < nr; r += CH_WARPS) {
+        const int read = rb + r, pidx = 2 * rb + strand * nr + r;
+        const int64_t qb = A.mz_off[read];
+        const int n = (int)(A.mz_off[read + 1] - qb);
+        const uint64_t *qx = A.mz_x + qb; const uint32_t *qy = A.mz_y + qb; const uint16_t *qc = A.selfcnt + qb;
+        const int qlen = A.read_len[read];
+        const bool do_flt = o.q_occ_frac > 0.0f && mid_occ > 0 && n > mid_occ;
+        const float thr = (float)n * o.q_occ_frac;
+        if (A.mode == 0) {
+            int na = 0;
+            for (int i = lane; i < n; i += 32) {
+                int c = qc[i];
+                if (do_flt && c > mid_occ && (float)c > thr) continue;
+                int st, t = idx_lookup(I, qx[i] >> 8, &st);
+                if (t <= mid_occ) na += t;
+            }
+#pragma unroll
+            for (int d = 16; d; d >>= 1) na += __shfl_xor_sync(FULL, na, d);
+            if (lane == 0) { A.prob_na[pidx] = na; A.prob_read[pidx] = read; A.prob_ls[pidx] = item; }
+            continue;
+        }
+        // ---------------- fill mode ----------------
+        const int64_t ao = A.prob_aoff[pidx];
+        const int n_a = (int)(A.prob_aoff[pidx + 1] - ao);
+        Anchor *a = A.anchors + ao;
+        if (n_a == 0) continue;
+        uint8_t *wsb = A.warp_scratch + (size_t)(blockIdx.x * CH_WARPS + wid) * A.warp_scratch_stride;
+        int32_t *kept = (int32_t *)wsb;    // indices of minimizers that survive the query-occurrence filter
+        int nk = 0;
+        for (int ib = 0; ib < n; ib += 32) {
+            int i = ib + lane;
+            bool keep = false;
+            if (i < n) { int c = qc[i]; keep = !(do_flt && c > mid_occ && (float)c > thr); }
+            unsigned m = __ballot_sync(FULL, keep);
+            if (keep) kept[nk + __popc(m & ((1u << lane) - 1))] = i;
+            nk += __popc(m);
+        }
+        __syncwarp();
+        int run = 0;
+        for (int jb = 0; jb < nk; jb += 32) {
+            int j = jb + lane, t = 0, st = 0; uint64_t x = 0; uint32_t y = 0; bool tandem = false;
+            if (j < nk) {
+                int i = kept[j];
+                x = qx[i]; y = qy[i];
+                t = idx_lookup(I, x >> 8, &st);
+                if (t > mid_occ) t = 0;
+                if (t) {
+                    if (j > 0 && (qx[kept[j - 1]] >> 8) == (x >> 8)) tandem = true;
+                    if (j < nk - 1 && (qx[kept[j + 1]] >> 8) == (x >> 8)) tandem = true;
+                }
+            }
+            int pre = t;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { int yv = __shfl_up_sync(FULL, pre, d); if (lane >= d) pre += yv; }
+            int tot = __shfl_sync(FULL, pre, 31);
+            pre -= t;
+            const uint32_t q_span = (uint32_t)(x & 0xff), q_pos = y;
+            for (int k = 0; k < t; ++k) {
+                uint32_t ry = I.occ_y[st + k];
+                int32_t rpos = (int32_t)(ry >> 1);
+                Anchor an;
+                if ((ry & 1) == (q_pos & 1)) {
+                    an.x = (uint64_t)(uint32_t)rpos;
+                    an.y = (uint64_t)q_span << 32 | (q_pos >> 1);
+                } else {
+                    an.x = 1ULL << 63 | (uint64_t)(uint32_t)rpos;
+                    an.y = (uint64_t)q_span << 32 | (uint32_t)(qlen - ((int32_t)(q_pos >> 1) + 1 - (int32_t)q_span) - 1);
+                }
+                if (tandem) an.y |= SEED_TANDEM;
+                a[run + pre + k] = an;
+            }
+            run += tot;
+        }
+        if (lane == 0) atomicAdd(A.stat_anchors, (unsigned long long)n_a);
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(CH_THREADS) k_chain(const __grid_constant__ ChainArgs A)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    IdxSmem &I = *reinterpret_cast<IdxSmem *>(smem_raw);
+    IdxSmem &C = *reinterpret_cast<IdxSmem *>(smem_raw);
     const Opt &o = A.o;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const unsigned FULL = 0xffffffffu;
     const int n_items = 2 * A.n_loci;
     for (;;) {
-        if (tid == 0) I.item = atomicAdd(A.work_counter, 1);
+        if (tid == 0) C.item = atomicAdd(A.work_counter, 1);
         __syncthreads();
-        const int item = I.item;
+        const int item = C.item;
         __syncthreads();
         if (item >= n_items) break;
         const int l = item >> 1, strand = item & 1;
@@ -395,7 +493,7 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const __grid_constant__ Ch
         const int cseq = A.n_reads + strand * A.n_loci + l;
         const int64_t cb = A.mz_off[cseq];
         const int n_c = (int)(A.mz_off[cseq + 1] - cb);
-        if (n_c > IDX_MAXMZ) {
+        if (n_c > IDX_BIG_MAXMZ || (n_c > IDX_MAXMZ && !A.idx_big)) {
             if (tid == 0) atomicOr(A.err, 16);
             for (int r = tid; r < nr; r += CH_THREADS) {
                 int pidx = 2 * rb + strand * nr + r;
@@ -404,84 +502,8 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const __grid_constant__ Ch
             }
             continue;
         }
-        idx_build(I, o, n_c, A.mz_x + cb, A.mz_y + cb);
-        const int mid_occ = I.mid_occ;
-        for (int r = wid; r < nr; r += CH_WARPS) {
-            const int read = rb + r, pidx = 2 * rb + strand * nr + r;
-            const int64_t qb = A.mz_off[read];
-            const int n = (int)(A.mz_off[read + 1] - qb);
-            const uint64_t *qx = A.mz_x + qb; const uint32_t *qy = A.mz_y + qb; const uint16_t *qc = A.selfcnt + qb;
-            const int qlen = A.read_len[read];
-            const bool do_flt = o.q_occ_frac > 0.0f && mid_occ > 0 && n > mid_occ;
-            const float thr = (float)n * o.q_occ_frac;
-            if (A.mode == 0) {
-                int na = 0;
-                for (int i = lane; i < n; i += 32) {
-                    int c = qc[i];
-                    if (do_flt && c > mid_occ && (float)c > thr) continue;
-                    int st, t = idx_lookup(I, qx[i] >> 8, &st);
-                    if (t <= mid_occ) na += t;
-                }
-#pragma unroll
-                for (int d = 16; d; d >>= 1) na += __shfl_xor_sync(FULL, na, d);
-                if (lane == 0) { A.prob_na[pidx] = na; A.prob_read[pidx] = read; A.prob_ls[pidx] = item; }
-                continue;
-            }
-            // ---------------- fill mode ----------------
-            const int64_t ao = A.prob_aoff[pidx];
-            const int n_a = (int)(A.prob_aoff[pidx + 1] - ao);
-            Anchor *a = A.anchors + ao;
-            if (n_a == 0) continue;
-            uint8_t *wsb = A.warp_scratch + (size_t)(blockIdx.x * CH_WARPS + wid) * A.warp_scratch_stride;
-            int32_t *kept = (int32_t *)wsb;    // indices of minimizers that survive the query-occurrence filter
-            int nk = 0;
-            for (int ib = 0; ib < n; ib += 32) {
-                int i = ib + lane;
-                bool keep = false;
-                if (i < n) { int c = qc[i]; keep = !(do_flt && c > mid_occ && (float)c > thr); }
-                unsigned m = __ballot_sync(FULL, keep);
-                if (keep) kept[nk + __popc(m & ((1u << lane) - 1))] = i;
-                nk += __popc(m);
-            }
-            __syncwarp();
-            int run = 0;
-            for (int jb = 0; jb < nk; jb += 32) {
-                int j = jb + lane, t = 0, st = 0; uint64_t x = 0; uint32_t y = 0; bool tandem = false;
-                if (j < nk) {
-                    int i = kept[j];
-                    x = qx[i]; y = qy[i];
-                    t = idx_lookup(I, x >> 8, &st);
-                    if (t > mid_occ) t = 0;
-                    if (t) {
-                        if (j > 0 && (qx[kept[j - 1]] >> 8) == (x >> 8)) tandem = true;
-                        if (j < nk - 1 && (qx[kept[j + 1]] >> 8) == (x >> 8)) tandem = true;
-                    }
-                }
-                int pre = t;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { int yv = __shfl_up_sync(FULL, pre, d); if (lane >= d) pre += yv; }
-                int tot = __shfl_sync(FULL, pre, 31);
-                pre -= t;
-                const uint32_t q_span = (uint32_t)(x & 0xff), q_pos = y;
-                for (int k = 0; k < t; ++k) {
-                    uint32_t ry = I.occ_y[st + k];
-                    int32_t rpos = (int32_t)(ry >> 1);
-                    Anchor an;
-                    if ((ry & 1) == (q_pos & 1)) {
-                        an.x = (uint64_t)(uint32_t)rpos;
-                        an.y = (uint64_t)q_span << 32 | (q_pos >> 1);
-                    } else {
-                        an.x = 1ULL << 63 | (uint64_t)(uint32_t)rpos;
-                        an.y = (uint64_t)q_span << 32 | (uint32_t)(qlen - ((int32_t)(q_pos >> 1) + 1 - (int32_t)q_span) - 1);
-                    }
-                    if (tandem) an.y |= SEED_TANDEM;
-                    a[run + pre + k] = an;
-                }
-                run += tot;
-            }
-            if (lane == 0) atomicAdd(A.stat_anchors, (unsigned long long)n_a);
-            __syncwarp();
-        }
+        if (n_c <= IDX_MAXMZ) chain_item(A, C.t, C, item, rb, nr, strand, cb, n_c);
+        else chain_item(A, A.idx_big[blockIdx.x], C, item, rb, nr, strand, cb, n_c);
         __syncthreads();
     }
 }

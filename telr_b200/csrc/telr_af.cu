@@ -59,7 +59,7 @@ struct telr_af_ctx {
     DevBuf b_lrb, b_cboff, b_ctg, b_descs, b_counts, b_mzoff, b_mzx, b_mzy, b_self, b_tabk, b_tabc, b_hpc, b_hpp, b_hpr;
     DevBuf b_pna, b_pread, b_pls, b_paoff, b_prcap, b_proff, b_pnregs, b_pnca, b_anch, b_regs, b_chws, b_alws, b_work;
     DevBuf b_psb, b_psoff, b_pscr, b_pnu, b_pm;
-    DevBuf b_rbytes, b_rboff, b_alwork, b_alctx, b_altask, b_alres, b_alsz, b_aloff, b_cigs, b_pool, b_tlist, b_rc, b_opt;
+    DevBuf b_rbytes, b_rboff, b_alwork, b_alctx, b_altask, b_alres, b_alsz, b_aloff, b_cigs, b_pool, b_tlist, b_rc, b_opt, b_idxbig;
     int64_t pool_cap = (int64_t)6144 << 20;
     DevBuf b_blk, b_pblkoff, b_pblkcnt, b_ctr, b_alnout, b_cigout, b_doff, b_big, b_biglock;
     int n_big = 8; int64_t big_cap = (int64_t)208 << 20;
@@ -223,6 +223,8 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
     ca.prob_nregs = ctx->b_pnregs.as<int32_t>(); ca.prob_nca = ctx->b_pnca.as<int32_t>();
     ca.work_counter = (int32_t *)(ctr + C_WORK_CHAIN); ca.err = (int32_t *)(ctr + C_ERR); ca.stat_anchors = (unsigned long long *)(ctr + C_ANCH);
     const int ch_grid = std::min(2 * n_loci, sm);
+    ENS(ctx->b_idxbig, sizeof(IdxBig) * (size_t)ch_grid);
+    ca.idx_big = ctx->b_idxbig.as<IdxBig>();
     const size_t ch_smem = sizeof(IdxSmem);
     CK(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch_smem));
     k_chain<<<ch_grid, CH_THREADS, ch_smem, st>>>(ca);
@@ -494,7 +496,7 @@ int telr_af_destroy(telr_af_ctx *ctx)
                      &ctx->b_pls, &ctx->b_paoff, &ctx->b_prcap, &ctx->b_proff, &ctx->b_pnregs, &ctx->b_pnca, &ctx->b_anch, &ctx->b_regs, &ctx->b_chws,
                      &ctx->b_alws, &ctx->b_work, &ctx->b_blk, &ctx->b_pblkoff, &ctx->b_pblkcnt, &ctx->b_ctr, &ctx->b_alnout, &ctx->b_cigout, &ctx->b_doff,
                      &ctx->b_big, &ctx->b_biglock, &ctx->b_rbytes, &ctx->b_rboff, &ctx->b_alwork, &ctx->b_alctx, &ctx->b_altask, &ctx->b_alres, &ctx->b_alsz, &ctx->b_aloff,
-                     &ctx->b_cigs, &ctx->b_pool, &ctx->b_tlist, &ctx->b_rc, &ctx->b_opt, &ctx->b_psb, &ctx->b_psoff, &ctx->b_pscr, &ctx->b_pnu, &ctx->b_pm};
+                     &ctx->b_cigs, &ctx->b_pool, &ctx->b_tlist, &ctx->b_rc, &ctx->b_opt, &ctx->b_idxbig, &ctx->b_psb, &ctx->b_psoff, &ctx->b_pscr, &ctx->b_pnu, &ctx->b_pm};
     for (auto *b : all) b->release();
     for (auto &b : ctx->b_in) b.release();
     for (auto &e : ctx->ev) cudaEventDestroy(e);

@@ -256,6 +256,16 @@ def test_long_read_config_matches_oracle(ctx):
     assert r.c.dp_cells == ro.c.dp_cells
 
 
+def test_long_contig_uses_the_global_index(ctx):
+    """A 36 kb contig has more minimizers than the shared-memory index holds (4096): the global-memory instance takes over."""
+    b = synth.generate("ont_3k_50x", 0, 2, depth=6, te_min=30000, te_max=31000, te_median=30500)
+    assert int(b.contig_len.max()) > 30000
+    r = ctx.run(b, want_depth=True, want_aln=True)
+    ro = orc.af_run(b, threads=0)
+    util.assert_same_results(r, ro)
+    assert r.c.dp_cells == ro.c.dp_cells and r.c.n_anchors == ro.c.n_anchors
+
+
 def test_chunking_and_rerun_are_identical(built, monkeypatch):
     b = synth.generate("ont_3k_50x", 0, 12, depth=12)
     c1 = lib.Context(0)
