@@ -538,6 +538,107 @@ __global__ void __launch_bounds__(AL_THREADS, AL_BLOCKS_PER_SM) k_al_fused(const
     }
 }
 
+// Deferred mm_update_extra statistics (matches, block length, ambiguous bases, best local score dp_max), one warp per
+// problem.  Lane 0 runs the sequential CIGAR clean-up (fix_cigar); the per-base pass is then spread over the lanes one
+// CIGAR op each.  The score recurrence s <- max(0, s + x) with its running maximum is a monoid over ops:
+//   f(s) = max(s + A, B),   best prefix value given s = max(s + MA, MB)
+// combined left-to-right by an ordered warp reduction, so the result equals the sequential scan exactly.
+struct RfMono { int32_t A, B, MA, MB; };
+__device__ __forceinline__ RfMono rf_combine(const RfMono &l, const RfMono &r)
+{
+    RfMono o;
+    o.A = l.A + r.A;
+    o.B = max(l.B + r.A, r.B);
+    o.MA = max(l.MA, l.A + r.MA);
+    o.MB = max(max(l.MB, l.B + r.MA), r.MB);
+    return o;
+}
+
+__global__ void __launch_bounds__(256) k_al_regfin(const __grid_constant__ AlignArgs A)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    const int NEG = -(1 << 28);
+    const int nw = gridDim.x * (blockDim.x >> 5);
+    for (int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < A.n_work; w += nw) {
+        AlnCtx &c = A.actx[w];
+        if (c.phase != PH_FINISH) continue;
+        const Opt &o = *c.o;
+        for (int i = 0; i < c.n_regs; ++i) {
+            Reg &r = c.regs[i];
+            if (!r.need_fin) continue;
+            if (!r.has_p) { if (lane == 0) r.need_fin = 0; __syncwarp(); continue; }
+            const uint8_t *qseq = &c.qseq[r.rev][r.fin_q], *tseq = &c.tseq[r.fin_t];
+            int qshift = 0, tshift = 0;
+            if (lane == 0) fix_cigar(c, r, qseq, tseq, &qshift, &tshift);
+            __syncwarp();
+            qshift = __shfl_sync(FULL, qshift, 0); tshift = __shfl_sync(FULL, tshift, 0);
+            qseq += qshift; tseq += tshift;
+            const uint32_t *cg = c.cig + r.cig;
+            const int n_cigar = r.n_cigar;
+            int qoff = 0, toff = 0, s = 0, mx = 0, blen = 0, mlen = 0, n_ambi = 0;
+            for (int kb = 0; kb < n_cigar; kb += 32) {
+                const int k = kb + lane;
+                int op = 3, len = 0;
+                if (k < n_cigar) { op = (int)(cg[k] & 0xf); len = (int)(cg[k] >> 4); }
+                // query / target offsets of this lane's op: exclusive prefix sums of the lengths it consumes
+                int ql = (op == 0 || op == 1) ? len : 0, tl = (op == 0 || op == 2) ? len : 0;
+                int qp = ql, tp = tl;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    int a = __shfl_up_sync(FULL, qp, d), b = __shfl_up_sync(FULL, tp, d);
+                    if (lane >= d) qp += a, tp += b;
+                }
+                const int qtot = __shfl_sync(FULL, qp, 31), ttot = __shfl_sync(FULL, tp, 31);
+                const int q0 = qoff + qp - ql, t0 = toff + tp - tl;
+                RfMono m; m.A = 0; m.B = NEG; m.MA = NEG; m.MB = NEG;      // identity
+                int amb = 0, diff = 0;
+                if (op == 0) {
+                    int ss = 0, bb = NEG, ma = NEG;
+                    for (int l = 0; l < len; ++l) {
+                        const int cq = qseq[q0 + l], ct = tseq[t0 + l];
+                        if (ct > 3 || cq > 3) ++amb; else if (ct != cq) ++diff;
+                        const int x = sc_pair(o, ct, cq);
+                        // append the single-base element (A = x, B = 0, MA = x, MB = 0)
+                        ma = max(ma, ss + x);
+                        bb = max(bb + x, 0);
+                        ss += x;
+                        m.MB = max(m.MB, bb);
+                    }
+                    if (len > 0) { m.A = ss; m.B = bb; m.MA = ma; }
+                } else if (op == 1 || op == 2) {
+                    const uint8_t *sq = op == 1 ? qseq + q0 : tseq + t0;
+                    for (int l = 0; l < len; ++l) amb += sq[l] > 3;
+                    m.A = -(o.q + o.e * len); m.B = 0;                      // s <- max(0, s - cost); the maximum is not updated
+                }
+                // ordered reduction: lane 0 ends with op kb .. kb+31 combined left to right
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    RfMono rr;
+                    rr.A = __shfl_down_sync(FULL, m.A, d); rr.B = __shfl_down_sync(FULL, m.B, d);
+                    rr.MA = __shfl_down_sync(FULL, m.MA, d); rr.MB = __shfl_down_sync(FULL, m.MB, d);
+                    if ((lane & (2 * d - 1)) == 0) m = rf_combine(m, rr);
+                }
+                const int tA = __shfl_sync(FULL, m.A, 0), tB = __shfl_sync(FULL, m.B, 0), tMA = __shfl_sync(FULL, m.MA, 0), tMB = __shfl_sync(FULL, m.MB, 0);
+                mx = max(mx, max(s + tMA, tMB));
+                s = max(s + tA, tB);
+                // counts
+                int cb = op == 3 ? 0 : len - amb, cm = op == 0 ? len - (amb + diff) : 0, ca = amb;
+#pragma unroll
+                for (int d = 16; d; d >>= 1) { cb += __shfl_xor_sync(FULL, cb, d); cm += __shfl_xor_sync(FULL, cm, d); ca += __shfl_xor_sync(FULL, ca, d); }
+                blen += cb; mlen += cm; n_ambi += ca;
+                qoff += qtot; toff += ttot;
+            }
+            if (lane == 0) {
+                r.blen = blen; r.mlen = mlen; r.n_ambi += n_ambi;
+                r.dp_max = mx;          // (int32_t)(mx + .499) of an integer-valued maximum
+                r.need_fin = 0;
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // deferred statistics + final region pass + outputs, one thread per problem
 __global__ void __launch_bounds__(128) k_al_finish(const __grid_constant__ AlignArgs A)
 {

@@ -345,6 +345,7 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
         k_al_init<<<tb, 128, 0, st>>>(aa);
         CK(cudaFuncSetAttribute(k_al_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(AL_WARPS * sizeof(VecSmem))));
         k_al_fused<<<al_grid, AL_THREADS, AL_WARPS * sizeof(VecSmem), st>>>(aa);
+        k_al_regfin<<<std::max(1, std::min((n_work + 7) / 8, sm * 8)), 256, 0, st>>>(aa);
         k_al_finish<<<tp_blocks<TP_FINISH>(n_work, 128), 128, 0, st>>>(aa);
     }
     CK(cudaEventRecord(ctx->ev[4], st));
@@ -386,7 +387,7 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
     }
     stats->dp_cells += hc[C_CELLS]; stats->n_dp_tasks += hc[C_TASKS]; stats->n_anchors += hc[C_ANCH]; stats->n_minimizers += n_mz;
     stats->n_aln_blocks += hc[C_NBLK];
-    ctx->launches += 22 + (n_work > 0 ? 6 : 0);   // unpack, descs, sketch x2, scan x4, self_count, chain x2 + sort/dp/bt/rmq/regs, reg_caps, worklist, align, depth_af
+    ctx->launches += 22 + (n_work > 0 ? 7 : 0);   // unpack, descs, sketch x2, scan x4, self_count, chain x2 + sort/dp/bt/rmq/regs, reg_caps, worklist, align, depth_af
     if (d_aln_out) { stats->n_aln = hc[C_NALN]; stats->n_cigar = hc[C_NCIG]; }
     float ms;
     static const int pairs[5][3] = {{0, 1, 0}, {1, 2, 1}, {2, 3, 2}, {3, 4, 3}, {4, 5, 6}};
