@@ -170,6 +170,45 @@ def test_dp_small_shapes_match_oracle(ctx, flag):
         assert len(gc) == len(ref["cigar"]) and (gc == ref["cigar"]).all(), (i, len(q), len(t))
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_dp_fuzz_matches_oracle(ctx, seed):
+    """Random shapes, bands, z-drop thresholds, end bonuses and flag combinations through all three DP kernels
+    (systolic fill, vectorised general DP, scalar fallback for ambiguous bases)."""
+    rng = np.random.default_rng(1000 + seed)
+    preset = [0, 1, 2][seed % 3]
+    o = orc.opt(preset)
+    tasks, qs, ts_ = [], [], []
+    qo = to = 0
+    for _ in range(160):
+        tl = int(rng.choice([rng.integers(1, 40), rng.integers(40, 300), rng.integers(300, 900)]))
+        rate = float(rng.choice([0.0, 0.05, 0.15, 0.4]))
+        t = rng.integers(0, 4, tl).astype(np.uint8)
+        q = _mut(rng, np.resize(t, max(4, int(tl * rng.uniform(.5, 1.6)))), rate)
+        q = q[: max(1, int(len(q) * rng.uniform(.6, 1.0)))]
+        if rng.random() < .15 and len(q) > 8:
+            q[rng.integers(0, len(q))] = 4
+        if rng.random() < .1 and len(t) > 8:
+            t[rng.integers(0, len(t))] = 4
+        flag = int(rng.choice([0x08, 0x08, 0x00, 0x40, 0x42, 0xC2, 0x80, 0x48]))
+        w = int(rng.choice([-1, 3, 17, 100, 751])) if flag != 0x08 else int(rng.choice([-1, 30001]))
+        zd = int(rng.choice([-1, 40, 400])); eb = int(rng.choice([-1, 0, 10]))
+        tasks.append((qo, to, len(q), len(t), w, zd, eb, flag)); qs.append(q); ts_.append(t); qo += len(q); to += len(t)
+    out, cig = ctx.dp(preset, np.array(tasks, lib.DPTASK_DTYPE), np.concatenate(qs), np.concatenate(ts_))
+    for i, (q, t) in enumerate(zip(qs, ts_)):
+        w, zd, eb, flag = tasks[i][4:]
+        ref = orc.ksw_extd2(q, t, o, w, zd, eb, flag); g = out[i]
+        names = ["zdropped", "reach_end", "cells"]
+        if not flag & 0x08:
+            names += ["max", "max_q", "max_t"]
+        if not (flag & 0x40) and not ref["zdropped"]:
+            names += ["score"]
+        if flag & 0x40 and not (flag & 0x08) and not ref["zdropped"]:
+            names += ["mqe", "mqe_t"]
+        assert all(int(ref[n]) == int(g[n]) for n in names), (i, tasks[i], {n: (int(ref[n]), int(g[n])) for n in names})
+        gc = cig[g["cigar_off"]: g["cigar_off"] + g["n_cigar"]]
+        assert len(gc) == len(ref["cigar"]) and (gc == ref["cigar"]).all(), (i, tasks[i])
+
+
 @pytest.mark.parametrize("cfg,n,kw", [("ont_3k_50x", 10, {}), ("clr_3k_40x", 6, {}), ("hifi_3k_40x", 6, {}),
                                       ("poly_10k_200x", 2, dict(depth=60)), ("ont_3k_50x", 4, dict(p_n=0.002))])
 def test_full_pipeline_matches_oracle(ctx, cfg, n, kw):
