@@ -27,7 +27,7 @@ import numpy as np  # noqa: E402
 
 WORKLOAD = os.environ.get("TELR_BENCH_CONFIG", "ont_3k_50x")     # BASELINE.json configs[1]
 OPS_PER_CELL = 30.0        # integer lane-ops per DP cell of the two-piece affine recurrence with traceback
-DRAM_BYTES_PER_CELL = 1.25  # dram__bytes_read+write of k_al_fused / DP cells, ncu --set full capture (profiles/r1_k_al_fused_ncu.csv)
+DRAM_BYTES_PER_CELL = 1.33  # dram__bytes_read+write of k_al_fused / DP cells, ncu --set full capture (profiles/r1_k_al_fused_ncu.csv)
 LAUNCHES_PER_CHUNK = 29    # kernels the library launches per chunk of loci (telr_af.cu run_chunk)
 
 
@@ -284,7 +284,7 @@ def main():
             "roofline": {"kernel": "k_align (base-level DP)", "bound": "int_alu", "achieved": gcups, "peak": peak_gcups, "unit": "GCUPS",
                          "frac": gcups / peak_gcups if peak_gcups else None,
                          "traffic": (DRAM_BYTES_PER_CELL * cells[0] / max(launches // LAUNCHES_PER_CHUNK, 1)) if cells[0] else None,
-                         "note": f"peak = {nsm} SM x 64 lane-ops/clk x {f_mhz} MHz x 2 cells/op / {OPS_PER_CELL:.0f} ops/cell; HBM peak {hbm_gbs} GB/s ({peak_kind}) applies to sketch/depth; traffic = bytes per k_al_fused launch, 1.25 B/cell from the ncu capture in profiles/ scaled by this run's cells; the kernel issues 0.70 warp-inst/clk/sub-partition against a measured two-pipe ceiling of 0.705 (profiles/ubench)"},
+                         "note": f"peak = {nsm} SM x 64 lane-ops/clk x {f_mhz} MHz x 2 cells/op / {OPS_PER_CELL:.0f} ops/cell; HBM peak {hbm_gbs} GB/s ({peak_kind}) applies to sketch/depth; traffic = bytes per k_al_fused launch, 1.33 B/cell from the ncu capture in profiles/ scaled by this run's cells; the kernel issues 0.71 warp-inst/clk/sub-partition against a measured two-pipe ceiling of 0.705 (profiles/ubench)"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e, "unit": "loci/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_wall / args.steps * 1e3},
             "gpu_launches": launches, "clocks": clocks, "wall_ms_per_step": wall_s / args.steps * 1e3,
