@@ -77,20 +77,19 @@ struct SkSmem {
     int ws[40];
 };
 
-// pushes of the sequential algorithm at local step j (0-based in tile); X index = SK_XH + j.
+// pushes of the sequential algorithm at one step.  Xd(d) = hash of the step d steps back (d = 0: this step), l = the
+// capped count of unambiguous bases ending here; emit(j - d) names the step whose minimizer is pushed.
 // One scan over steps -(w-1)..-1 yields the window minimum m1 (rightmost on ties), its distance d1 and how many
 // entries equal it; the minimum over -w..-1 (mp), the one over -(w-1)..0 (mn) and the number of identical-hash
 // duplicates each case would flush follow from m1, X[-w] and X[0] without further loops.  The duplicate-flush loops
 // themselves only run when such duplicates exist (tandem repeats).
-template <class Emit> __device__ __forceinline__ void sk_step(const SkSmem &S, int j, int w, int k, Emit &emit)
+template <class XF, class Emit> __device__ __forceinline__ void sk_step_g(XF Xd, int j, int l, int w, int k, Emit &emit)
 {
     const uint64_t MAXV = ~0ULL;
-    const uint64_t *X = S.X + SK_XH + j;        // X[0] = this step, X[-d] = d steps back
-    const uint64_t info = X[0], xw = X[-w];
-    const int l = S.lcap[j];
+    const uint64_t info = Xd(0), xw = Xd(w);
     uint64_t m1 = MAXV; int d1 = w - 1, c1 = 0;
     for (int d = w - 1; d >= 1; --d) {
-        const uint64_t v = X[-d];
+        const uint64_t v = Xd(d);
         if (v < m1) m1 = v, d1 = d, c1 = 1;
         else if (v == m1) d1 = d, ++c1;
     }
@@ -103,7 +102,7 @@ template <class Emit> __device__ __forceinline__ void sk_step(const SkSmem &S, i
         const int dup = from_w ? 0 : c1 - 1;      // other entries of -(w-1)..-1 equal to mp
         if (dup > 0)
             for (int d = w - 1; d >= 1; --d)
-                if (X[-d] == mp && d != mpd) emit(j - d);
+                if (Xd(d) == mp && d != mpd) emit(j - d);
     }
     if (info <= mp) {
         if (l >= w + k && mp != MAXV) emit(j - mpd);
@@ -117,9 +116,14 @@ template <class Emit> __device__ __forceinline__ void sk_step(const SkSmem &S, i
             const int dup = info == m1 ? c1 : from_0 ? 0 : c1 - 1;
             if (dup > 0)
                 for (int d = w - 1; d >= 0; --d)
-                    if (X[-d] == mn && d != mnd) emit(j - d);
+                    if (Xd(d) == mn && d != mnd) emit(j - d);
         }
     }
+}
+template <class Emit> __device__ __forceinline__ void sk_step(const SkSmem &S, int j, int w, int k, Emit &emit)
+{
+    const uint64_t *X = S.X + SK_XH + j;        // X[0] = this step, X[-d] = d steps back
+    sk_step_g([X](int d) { return X[-d]; }, j, (int)S.lcap[j], w, k, emit);
 }
 
 struct SkCount { int n; __device__ __forceinline__ void operator()(int) { ++n; } };
@@ -328,6 +332,202 @@ template <bool WRITE> __global__ void __launch_bounds__(SK_THREADS) k_sketch(Ske
             if (!WRITE) A.counts[seq] = (int32_t)out_run;
         }
         __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Tile form of kernel (a) for the uncompressed presets (map-ont, map-hifi): one WARP per tile of 2048 steps, no CTA
+// barrier, no recomputation.
+//   * The warp stages the tile's 2-bit codes and N bits (plus 128 bases of lead-in) as packed words in shared
+//     memory: 17 coalesced 128-byte rows for a read tile, or a byte->2-bit pack for a contig strand.
+//   * Every iteration handles 32 consecutive steps, one per lane.  The k-mer of a step is cut out of the packed
+//     stream with two funnel shifts (no rolling state): the forward k-mer is its 2-bit-group reversal (BREV), the
+//     reverse-complement k-mer its complement.  The count of unambiguous bases behind the step is a CLZ of the
+//     64 N bits that end at it.
+//   * Hashes live in a 64-entry ring; sk_step_g reads its w+1 neighbours from the ring (conflict-free: consecutive
+//     lanes, consecutive words) and records at most two pushes per step in registers; one ballot orders them.
+//   * Minimizers go to a per-tile slot of a temporary array; k_sketch_compact packs the tiles into the CSR layout
+//     after an exclusive scan of the tile counts.  Every base is read once and hashed once.
+constexpr int SKT_TILE = 2048, SKT_LEAD = 128, SKT_WARPS = 8, SKT_CAP = SKT_TILE + 32;
+constexpr int SKT_CW = (SKT_TILE + SKT_LEAD) / 16 + 2, SKT_NW = (SKT_TILE + SKT_LEAD) / 32 + 2;
+
+struct SketchTileArgs {
+    const uint32_t *seq2, *nmask;
+    const uint8_t *bytes;
+    const SeqDesc *seqs;
+    int32_t n_seq, w, k, n_tiles;
+    const int32_t *tile_first;        // [n_seq + 1] first tile of every sequence
+    uint64_t *tmp_x; uint32_t *tmp_y; // [n_tiles * SKT_CAP]
+    int32_t *tile_cnt;                // [n_tiles]
+    const int64_t *tile_off;          // [n_tiles + 1] (compact pass)
+    int64_t *mz_off;                  // [n_seq + 1]   (compact pass)
+    uint64_t *mz_x; uint32_t *mz_y;
+};
+
+struct SktWarp { uint64_t X[64]; uint32_t cw[SKT_CW]; uint32_t nw[SKT_NW]; };
+
+struct SkRec {
+    int n, t0, t1;
+    __device__ __forceinline__ void operator()(int jj) { if (n == 0) t0 = jj; else if (n == 1) t1 = jj; ++n; }
+};
+struct SkTileWrite {
+    const SktWarp *W; uint64_t *ox; uint32_t *oy; int at, cap, c, T0; uint32_t zcur, zprev;
+    __device__ __forceinline__ void operator()(int jj)
+    {
+        if (at < cap) {
+            ox[at] = W->X[jj & 63];
+            oy[at] = (uint32_t)(T0 + jj) << 1 | ((((jj >> 5) == c ? zcur : zprev) >> (jj & 31)) & 1u);
+        }
+        ++at;
+    }
+};
+
+__global__ void __launch_bounds__(SKT_WARPS * 32) k_sketch_tiles(const __grid_constant__ SketchTileArgs A)
+{
+    __shared__ SktWarp SW[SKT_WARPS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned FULL = 0xffffffffu;
+    SktWarp &W = SW[wid];
+    const int w = A.w, k = A.k, cap = w + k;
+    const uint64_t MAXV = ~0ULL, mask = (1ULL << 2 * k) - 1;
+    const bool h32 = 2 * k <= 32;
+    for (int tile = blockIdx.x * SKT_WARPS + wid; tile < A.n_tiles; tile += gridDim.x * SKT_WARPS) {
+        // sequence of this tile: the last one whose first tile is <= tile
+        int lo = 0, hi = A.n_seq;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (A.tile_first[mid] <= tile) lo = mid; else hi = mid; }
+        const int seq = lo;
+        const SeqDesc sd = A.seqs[seq];
+        const int T0 = (tile - A.tile_first[seq]) * SKT_TILE;
+        const int tn = min(SKT_TILE, sd.len - T0);
+        // ---- stage packed codes: stream index q <-> sequence position T0 - SKT_LEAD + q ----
+        if (sd.kind == 0) {
+            for (int m = lane; m < SKT_CW; m += 32) {
+                const int i0 = T0 - SKT_LEAD + 16 * m;
+                W.cw[m] = (m < SKT_CW - 2 && i0 >= 0 && i0 < sd.len) ? A.seq2[(sd.off + i0) >> 4] : 0u;
+            }
+            for (int m = lane; m < SKT_NW; m += 32) {
+                const int i0 = T0 - SKT_LEAD + 32 * m;
+                uint32_t v = 0xffffffffu;
+                if (m < SKT_NW - 2 && i0 >= 0 && i0 < sd.len) {
+                    v = A.nmask[(sd.off + i0) >> 5];
+                    if (i0 + 32 > sd.len) v |= 0xffffffffu << (sd.len - i0);
+                }
+                W.nw[m] = v;
+            }
+        } else {
+            for (int m0 = 0; m0 < SKT_CW + 31; m0 += 32) {        // every lane of the warp takes part in the shuffle
+                const int m = m0 + lane, i0 = T0 - SKT_LEAD + 16 * m;
+                uint32_t pk = 0, nb = 0;
+                if (m < SKT_CW - 2) {
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) {
+                        const int i = i0 + t;
+                        const uint32_t c = (i >= 0 && i < sd.len) ? A.bytes[sd.off + i] : 4u;
+                        pk |= (c & 3u) << (2 * t);
+                        nb |= (c > 3u ? 1u : 0u) << t;
+                    }
+                } else nb = 0xffffu;
+                const uint32_t nb_hi = __shfl_xor_sync(FULL, nb, 1);
+                if (m < SKT_CW) W.cw[m] = pk;
+                if (!(lane & 1) && (m >> 1) < SKT_NW) W.nw[m >> 1] = nb | nb_hi << 16;
+            }
+        }
+        __syncwarp();
+        uint32_t zprev = 0, zcur = 0;
+        int out_run = 0;
+        const int nblk = (tn + 31) >> 5;
+        uint64_t *ox = A.tmp_x + (int64_t)tile * SKT_CAP; uint32_t *oy = A.tmp_y + (int64_t)tile * SKT_CAP;
+        for (int c = -1; c < nblk; ++c) {
+            const int j = c * 32 + lane, s = j + SKT_LEAD;
+            // unambiguous bases ending at s: CLZ of the 64 N bits [s-63, s]
+            int l;
+            {
+                const int e = s - 63, wi = e >> 5, sh = e & 31;
+                const uint32_t n0 = W.nw[wi], n1 = W.nw[wi + 1], n2 = W.nw[wi + 2];
+                const uint32_t wl = __funnelshift_r(n0, n1, sh), wh = __funnelshift_r(n1, n2, sh);
+                const int run = wh ? __clz((int)wh) : 32 + __clz((int)wl);
+                l = run < cap ? run : cap;
+            }
+            uint64_t X = MAXV; int z = 0;
+            if (l >= k) {
+                const int sb = s - k + 1, wi = sb >> 4, sh = 2 * (sb & 15);
+                const uint32_t a = W.cw[wi], b = W.cw[wi + 1], cc = W.cw[wi + 2];
+                const uint64_t val = ((uint64_t)__funnelshift_r(b, cc, sh) << 32 | __funnelshift_r(a, b, sh)) & mask;
+                uint64_t r = __brevll(val);
+                r = ((r >> 1) & 0x5555555555555555ULL) | ((r & 0x5555555555555555ULL) << 1);
+                const uint64_t k0 = r >> (64 - 2 * k), k1 = ~val & mask;
+                z = k0 < k1 ? 0 : 1;
+                const uint64_t km = z ? k1 : k0;
+                uint64_t h;
+                if (h32) {
+                    const uint32_t m32 = (uint32_t)mask;
+                    uint32_t key = (uint32_t)km;
+                    key = (~key + (key << 21)) & m32;
+                    key = key ^ key >> 24;
+                    key = (key * 265u) & m32;
+                    key = key ^ key >> 14;
+                    key = (key * 21u) & m32;
+                    key = key ^ key >> 28;
+                    key = (key + (key << 31)) & m32;
+                    h = key;
+                } else h = mix64_masked(km, mask);
+                X = h << 8 | (uint64_t)k;
+            }
+            zprev = zcur; zcur = __ballot_sync(FULL, z);
+            W.X[j & 63] = X;
+            __syncwarp();
+            if (c >= 0) {
+                SkRec rec; rec.n = 0; rec.t0 = 0; rec.t1 = 0;
+                const SktWarp *Wp = &W;
+                if (j < tn) sk_step_g([Wp, j](int d) { return Wp->X[(j - d) & 63]; }, j, l, w, k, rec);
+                const unsigned m1 = __ballot_sync(FULL, rec.n > 0);
+                int pre, tot;
+                if (!__any_sync(FULL, rec.n > 1)) { pre = __popc(m1 & ((1u << lane) - 1)); tot = __popc(m1); }
+                else {
+                    int x = rec.n;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(FULL, x, d); if (lane >= d) x += y; }
+                    tot = __shfl_sync(FULL, x, 31); pre = x - rec.n;
+                }
+                if (rec.n) {
+                    SkTileWrite wr; wr.W = &W; wr.ox = ox; wr.oy = oy; wr.at = out_run + pre; wr.cap = SKT_CAP; wr.c = c; wr.T0 = T0; wr.zcur = zcur; wr.zprev = zprev;
+                    if (rec.n <= 2) { wr(rec.t0); if (rec.n == 2) wr(rec.t1); }
+                    else sk_step_g([Wp, j](int d) { return Wp->X[(j - d) & 63]; }, j, l, w, k, wr);
+                }
+                out_run += tot;
+            }
+            __syncwarp();
+        }
+        // ---- the pending minimum of the sequence's last window ----
+        if (lane == 0) {
+            if (tn > 0 && T0 + tn == sd.len) {
+                const int last = tn - 1;
+                uint64_t mn = MAXV; int mnd = 0;
+                for (int d = w - 1; d >= 0; --d) { const uint64_t v = W.X[(last - d) & 63]; if (v <= mn) mn = v, mnd = d; }
+                if (mn != MAXV) {
+                    SkTileWrite wr; wr.W = &W; wr.ox = ox; wr.oy = oy; wr.at = out_run; wr.cap = SKT_CAP; wr.c = nblk - 1; wr.T0 = T0; wr.zcur = zcur; wr.zprev = zprev;
+                    wr(last - mnd);
+                    ++out_run;
+                }
+            }
+            A.tile_cnt[tile] = out_run < SKT_CAP ? out_run : SKT_CAP;
+        }
+        __syncwarp();
+    }
+}
+
+// pack the per-tile slots into the CSR minimizer arrays; one warp per tile.  Also publishes the per-sequence offsets.
+__global__ void __launch_bounds__(256) k_sketch_compact(const __grid_constant__ SketchTileArgs A)
+{
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x >> 5);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= A.n_seq; i += gridDim.x * blockDim.x)
+        A.mz_off[i] = A.tile_off[A.tile_first[i]];
+    for (int tile = gw; tile < A.n_tiles; tile += nw) {
+        const int64_t base = A.tile_off[tile];
+        const int cnt = (int)(A.tile_off[tile + 1] - base);
+        const uint64_t *sx = A.tmp_x + (int64_t)tile * SKT_CAP; const uint32_t *sy = A.tmp_y + (int64_t)tile * SKT_CAP;
+        for (int i = lane; i < cnt; i += 32) { A.mz_x[base + i] = sx[i]; A.mz_y[base + i] = sy[i]; }
     }
 }
 

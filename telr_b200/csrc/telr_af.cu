@@ -59,6 +59,8 @@ struct telr_af_ctx {
     DevBuf b_lrb, b_cboff, b_ctg, b_descs, b_counts, b_mzoff, b_mzx, b_mzy, b_self, b_tabk, b_tabc, b_hpc, b_hpp, b_hpr;
     DevBuf b_pna, b_pread, b_pls, b_paoff, b_prcap, b_proff, b_pnregs, b_pnca, b_anch, b_regs, b_chws, b_alws, b_work;
     DevBuf b_psb, b_psoff, b_pscr, b_pnu, b_pm;
+    DevBuf b_tfirst, b_tcnt, b_toff, b_tmpx, b_tmpy;     // tile sketch: first tile per sequence, per-tile counts/offsets, per-tile slots
+    int sketch_tiles = 1;
     DevBuf b_rbytes, b_rboff, b_alwork, b_alctx, b_altask, b_alres, b_alsz, b_aloff, b_cigs, b_pool, b_tlist, b_rc, b_opt, b_idxbig;
     int64_t pool_cap = (int64_t)6144 << 20;
     DevBuf b_blk, b_pblkoff, b_pblkcnt, b_ctr, b_alnout, b_cigout, b_doff, b_big, b_biglock;
@@ -137,6 +139,38 @@ __global__ void k_al_offsets(AlignArgs A, const int64_t *off)
     A.work[w].ez_off = off[w] + A.work[w].cig_cap; A.work[w].ez_cap = qlen + L + 16;
 }
 
+// Kernel (a), uncompressed presets: k_sketch_tiles -> scan of the tile counts -> k_sketch_compact.
+// `lens` are the sequence lengths in descriptor order; on return b_mzoff / b_mzx / b_mzy hold the CSR minimizer lists.
+static int sketch_tiled(telr_af_ctx *ctx, const SketchArgs &sa, const int32_t *lens, int64_t *n_mz_out)
+{
+    cudaStream_t st = ctx->stream;
+    const int n_seq = sa.n_seq;
+    std::vector<int32_t> tf((size_t)n_seq + 1);
+    int64_t nt = 0;
+    for (int i = 0; i < n_seq; ++i) { tf[i] = (int32_t)nt; nt += ((int64_t)lens[i] + SKT_TILE - 1) / SKT_TILE; }
+    tf[n_seq] = (int32_t)nt;
+    if (nt > INT32_MAX / 2) return TELR_ECAP;
+    const int n_tiles = (int)nt;
+    ENS(ctx->b_tfirst, (size_t)(n_seq + 1) * 4); ENS(ctx->b_tcnt, (size_t)(n_tiles + 1) * 4); ENS(ctx->b_toff, (size_t)(n_tiles + 2) * 8);
+    ENS(ctx->b_tmpx, ((size_t)n_tiles * SKT_CAP + 1) * 8); ENS(ctx->b_tmpy, ((size_t)n_tiles * SKT_CAP + 1) * 4);
+    CK(cudaMemcpyAsync(ctx->b_tfirst.p, tf.data(), (size_t)(n_seq + 1) * 4, cudaMemcpyHostToDevice, st));
+    SketchTileArgs ta; memset(&ta, 0, sizeof(ta));
+    ta.seq2 = sa.seq2; ta.nmask = sa.nmask; ta.bytes = sa.bytes; ta.seqs = sa.seqs; ta.n_seq = n_seq; ta.w = sa.w; ta.k = sa.k; ta.n_tiles = n_tiles;
+    ta.tile_first = ctx->b_tfirst.as<int32_t>(); ta.tmp_x = ctx->b_tmpx.as<uint64_t>(); ta.tmp_y = ctx->b_tmpy.as<uint32_t>();
+    ta.tile_cnt = ctx->b_tcnt.as<int32_t>(); ta.tile_off = ctx->b_toff.as<int64_t>(); ta.mz_off = ctx->b_mzoff.as<int64_t>();
+    const int grid = std::max(1, std::min((n_tiles + SKT_WARPS - 1) / SKT_WARPS, ctx->sm_count * 8));
+    if (n_tiles > 0) k_sketch_tiles<<<grid, SKT_WARPS * 32, 0, st>>>(ta);
+    k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_tcnt.as<int32_t>(), ctx->b_toff.as<int64_t>(), n_tiles, nullptr);
+    int64_t n_mz = 0;
+    CK(cudaMemcpyAsync(&n_mz, ctx->b_toff.as<int64_t>() + n_tiles, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));     // tf[] must outlive its upload; n_mz sizes the CSR arrays
+    ENS(ctx->b_mzx, (n_mz + 1) * 8); ENS(ctx->b_mzy, (n_mz + 1) * 4);
+    ta.mz_x = ctx->b_mzx.as<uint64_t>(); ta.mz_y = ctx->b_mzy.as<uint32_t>();
+    k_sketch_compact<<<std::max(1, std::min((n_tiles + 7) / 8, ctx->sm_count * 8)), 256, 0, st>>>(ta);
+    *n_mz_out = n_mz;
+    return TELR_OK;
+}
+
 struct HostMeta {       // host copies of the small per-read / per-locus arrays
     std::vector<int32_t> read_len, lrb, contig_len;
 };
@@ -192,14 +226,23 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
         sa.hp_code = ctx->b_hpc.as<uint8_t>(); sa.hp_pos = ctx->b_hpp.as<int32_t>(); sa.hp_rl = ctx->b_hpr.as<uint16_t>(); sa.hp_stride = stride;
     }
     sa.counts = ctx->b_counts.as<int32_t>();
-    k_sketch<false><<<sk_grid, SK_THREADS, 0, st>>>(sa);
-    k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_counts.as<int32_t>(), ctx->b_mzoff.as<int64_t>(), n_seq, nullptr);
     int64_t n_mz = 0;
-    CK(cudaMemcpyAsync(&n_mz, ctx->b_mzoff.as<int64_t>() + n_seq, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    ENS(ctx->b_mzx, (n_mz + 1) * 8); ENS(ctx->b_mzy, (n_mz + 1) * 4); ENS(ctx->b_self, (n_mz + 1) * 2);
-    sa.offs = ctx->b_mzoff.as<int64_t>(); sa.mz_x = ctx->b_mzx.as<uint64_t>(); sa.mz_y = ctx->b_mzy.as<uint32_t>();
-    k_sketch<true><<<sk_grid, SK_THREADS, 0, st>>>(sa);
+    if (!o.hpc && ctx->sketch_tiles) {
+        std::vector<int32_t> lens((size_t)n_seq);
+        for (int r = 0; r < n_reads; ++r) lens[r] = hm.read_len[r0 + r];
+        for (int l = 0; l < n_loci; ++l) lens[n_reads + l] = lens[n_reads + n_loci + l] = hm.contig_len[l0 + l];
+        int rc = sketch_tiled(ctx, sa, lens.data(), &n_mz);
+        if (rc != TELR_OK) return rc;
+        ENS(ctx->b_self, (n_mz + 1) * 2);
+    } else {
+        k_sketch<false><<<sk_grid, SK_THREADS, 0, st>>>(sa);
+        k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_counts.as<int32_t>(), ctx->b_mzoff.as<int64_t>(), n_seq, nullptr);
+        CK(cudaMemcpyAsync(&n_mz, ctx->b_mzoff.as<int64_t>() + n_seq, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        ENS(ctx->b_mzx, (n_mz + 1) * 8); ENS(ctx->b_mzy, (n_mz + 1) * 4); ENS(ctx->b_self, (n_mz + 1) * 2);
+        sa.offs = ctx->b_mzoff.as<int64_t>(); sa.mz_x = ctx->b_mzx.as<uint64_t>(); sa.mz_y = ctx->b_mzy.as<uint32_t>();
+        k_sketch<true><<<sk_grid, SK_THREADS, 0, st>>>(sa);
+    }
     CK(cudaEventRecord(ctx->ev[1], st));
     {
         int64_t max_nmz = (int64_t)max_qlen + 16, tab = 64;
@@ -477,6 +520,8 @@ int telr_af_create(telr_af_ctx **out, int device, size_t workspace_bytes)
     if (uf) ctx->use_fast = atoi(uf) ? 1 : 0;
     const char *uv = getenv("TELR_VEC_EXT");
     if (uv) ctx->use_vec = atoi(uv) ? 1 : 0;
+    const char *skt = getenv("TELR_SKETCH_TILES");
+    if (skt) ctx->sketch_tiles = atoi(skt) != 0;
     const char *cs = getenv("TELR_CENSUS");
     if (cs) ctx->census = atoi(cs) ? 1 : 0;
     const char *pm = getenv("TELR_POOL_MB");
@@ -497,7 +542,8 @@ int telr_af_destroy(telr_af_ctx *ctx)
                      &ctx->b_pls, &ctx->b_paoff, &ctx->b_prcap, &ctx->b_proff, &ctx->b_pnregs, &ctx->b_pnca, &ctx->b_anch, &ctx->b_regs, &ctx->b_chws,
                      &ctx->b_alws, &ctx->b_work, &ctx->b_blk, &ctx->b_pblkoff, &ctx->b_pblkcnt, &ctx->b_ctr, &ctx->b_alnout, &ctx->b_cigout, &ctx->b_doff,
                      &ctx->b_big, &ctx->b_biglock, &ctx->b_rbytes, &ctx->b_rboff, &ctx->b_alwork, &ctx->b_alctx, &ctx->b_altask, &ctx->b_alres, &ctx->b_alsz, &ctx->b_aloff,
-                     &ctx->b_cigs, &ctx->b_pool, &ctx->b_tlist, &ctx->b_rc, &ctx->b_opt, &ctx->b_idxbig, &ctx->b_psb, &ctx->b_psoff, &ctx->b_pscr, &ctx->b_pnu, &ctx->b_pm};
+                     &ctx->b_cigs, &ctx->b_pool, &ctx->b_tlist, &ctx->b_rc, &ctx->b_opt, &ctx->b_idxbig, &ctx->b_psb, &ctx->b_psoff, &ctx->b_pscr, &ctx->b_pnu, &ctx->b_pm,
+                     &ctx->b_tfirst, &ctx->b_tcnt, &ctx->b_toff, &ctx->b_tmpx, &ctx->b_tmpy};
     for (auto *b : all) b->release();
     for (auto &b : ctx->b_in) b.release();
     for (auto &e : ctx->ev) cudaEventDestroy(e);
@@ -620,15 +666,24 @@ int telr_af_sketch(telr_af_ctx *ctx, const uint32_t *seq2, const uint32_t *nmask
         sa.hp_code = ctx->b_hpc.as<uint8_t>(); sa.hp_pos = ctx->b_hpp.as<int32_t>(); sa.hp_rl = ctx->b_hpr.as<uint16_t>(); sa.hp_stride = stride;
     }
     sa.counts = ctx->b_counts.as<int32_t>();
-    k_sketch<false><<<grid, SK_THREADS, 0, st>>>(sa);
-    k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_counts.as<int32_t>(), ctx->b_mzoff.as<int64_t>(), n_seq, nullptr);
-    CK(cudaMemcpyAsync(mz_off, ctx->b_mzoff.p, (size_t)(n_seq + 1) * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    int64_t n_mz = mz_off[n_seq];
-    if (n_mz > mz_cap) return TELR_ECAP;
-    ENS(ctx->b_mzx, (n_mz + 1) * 8); ENS(ctx->b_mzy, (n_mz + 1) * 4);
-    sa.offs = ctx->b_mzoff.as<int64_t>(); sa.mz_x = ctx->b_mzx.as<uint64_t>(); sa.mz_y = ctx->b_mzy.as<uint32_t>();
-    k_sketch<true><<<grid, SK_THREADS, 0, st>>>(sa);
+    int64_t n_mz = 0;
+    if (!hpc && ctx->sketch_tiles) {
+        int rc = sketch_tiled(ctx, sa, seq_len, &n_mz);
+        if (rc != TELR_OK) return rc;
+        CK(cudaMemcpyAsync(mz_off, ctx->b_mzoff.p, (size_t)(n_seq + 1) * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (n_mz > mz_cap) return TELR_ECAP;
+    } else {
+        k_sketch<false><<<grid, SK_THREADS, 0, st>>>(sa);
+        k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_counts.as<int32_t>(), ctx->b_mzoff.as<int64_t>(), n_seq, nullptr);
+        CK(cudaMemcpyAsync(mz_off, ctx->b_mzoff.p, (size_t)(n_seq + 1) * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        n_mz = mz_off[n_seq];
+        if (n_mz > mz_cap) return TELR_ECAP;
+        ENS(ctx->b_mzx, (n_mz + 1) * 8); ENS(ctx->b_mzy, (n_mz + 1) * 4);
+        sa.offs = ctx->b_mzoff.as<int64_t>(); sa.mz_x = ctx->b_mzx.as<uint64_t>(); sa.mz_y = ctx->b_mzy.as<uint32_t>();
+        k_sketch<true><<<grid, SK_THREADS, 0, st>>>(sa);
+    }
     std::vector<uint32_t> y32(n_mz + 1);
     CK(cudaMemcpyAsync(mz_x, ctx->b_mzx.p, (size_t)n_mz * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(y32.data(), ctx->b_mzy.p, (size_t)n_mz * 4, cudaMemcpyDeviceToHost, st));
