@@ -515,6 +515,15 @@ __global__ void __launch_bounds__(AL_THREADS, AL_BLOCKS_PER_SM) k_al_fused(const
                     atomicAdd(&A.rc[5 + path], (unsigned long long)(t1 - t0));
                     atomicAdd(&A.rc[12 + path], 1ULL);
                     atomicAdd(&A.rc[16 + path], (unsigned long long)W.task.qlen * (unsigned long long)W.task.tlen);
+                    if (path == 1) {        // shape census of the general DP: buckets of min(qlen, tlen)
+                        const int mn = W.task.qlen < W.task.tlen ? W.task.qlen : W.task.tlen;
+                        const int b = mn < 64 ? 0 : mn < 128 ? 1 : mn < 256 ? 2 : mn < 512 ? 3 : mn < 1024 ? 4 : 5;
+                        atomicAdd(&A.rc[32 + b], (unsigned long long)(t1 - t0));
+                        atomicAdd(&A.rc[38 + b], 1ULL);
+                        if (W.res.zdropped) atomicAdd(&A.rc[44 + b], 1ULL);
+                        atomicAdd(&A.rc[50 + b], (unsigned long long)(W.res.max_t + W.res.max_q + 2));
+                        atomicAdd(&A.rc[56 + b], (unsigned long long)(W.task.qlen + W.task.tlen));
+                    }
                     t0 = t1;
                 }
                 if (done_fast) fill_traceback(W.task, W.res, S.dir, S.ezcig, S.ezcap, A.err, *reinterpret_cast<TbSmem *>(DS[wid].H));     // the DP state window is idle during traceback

@@ -1,8 +1,8 @@
 // telr_af.cu — C ABI (include/telr_af.h) and host orchestration of the stage-4 device pipeline.
 //
 // Stage order per chunk of loci (all on the ctx's stream):
-//   k_unpack_contigs -> k_sketch<COUNT> -> scan -> k_sketch<WRITE> -> k_self_count
-//   -> k_chain<count> -> scans -> k_chain<fill> -> k_worklist -> k_align -> k_depth_af
+//   k_unpack_contigs -> k_sketch_tiles -> scan -> k_sketch_compact (map-pb: k_sketch<COUNT> -> scan -> k_sketch<WRITE>) -> k_self_count
+//   -> k_chain<count> -> scans -> k_chain<fill> -> k_work_flags -> scan -> k_work_scatter -> k_align -> k_depth_af
 // There is no CPU execution path: every entry point fails with TELR_ENODEV when no sm_100 device is present.
 #include <cuda_runtime.h>
 #include <math.h>
@@ -59,8 +59,10 @@ struct telr_af_ctx {
     DevBuf b_lrb, b_cboff, b_ctg, b_descs, b_counts, b_mzoff, b_mzx, b_mzy, b_self, b_tabk, b_tabc, b_hpc, b_hpp, b_hpr;
     DevBuf b_pna, b_pread, b_pls, b_paoff, b_prcap, b_proff, b_pnregs, b_pnca, b_anch, b_regs, b_chws, b_alws, b_work;
     DevBuf b_psb, b_psoff, b_pscr, b_pnu, b_pm;
+    DevBuf b_order, b_wflag, b_woff;      // LPT order of the chunk's problems, work-list filter
     DevBuf b_tfirst, b_tcnt, b_toff, b_tmpx, b_tmpy;     // tile sketch: first tile per sequence, per-tile counts/offsets, per-tile slots
     int sketch_tiles = 1;
+    int al_blocks = AL_BLOCKS_PER_SM;    // resident k_al_fused CTAs per SM this context asks for (fewer leaves room for a second context's kernels)
     DevBuf b_rbytes, b_rboff, b_alwork, b_alctx, b_altask, b_alres, b_alsz, b_aloff, b_cigs, b_pool, b_tlist, b_rc, b_opt, b_idxbig;
     int64_t pool_cap = (int64_t)6144 << 20;
     DevBuf b_blk, b_pblkoff, b_pblkcnt, b_ctr, b_alnout, b_cigout, b_doff, b_big, b_biglock;
@@ -115,10 +117,19 @@ __global__ void k_reg_caps(int n, const int32_t *na, int32_t *cap, int32_t *sbyt
     }
 }
 
-__global__ void k_worklist(int n, const int32_t *nregs, int32_t *list, int32_t *count)
+// Work list of the alignment kernel = the problems that kept a region, longest read first (LPT order for the persistent
+// warps).  The order of ALL problems is known before anything runs (read lengths), so the host sorts it once per chunk
+// while the sketch kernels execute; the device only filters it: flags -> exclusive scan -> stable scatter.
+__global__ void k_work_flags(int n, const int32_t *order, const int32_t *nregs, int32_t *flags)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && nregs[i] > 0) list[atomicAdd(count, 1)] = i;
+    if (i < n) flags[i] = nregs[order[i]] > 0;
+}
+__global__ void k_work_scatter(int n, const int32_t *order, const int32_t *flags, const int64_t *offs, int32_t *list, int64_t *count)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flags[i]) list[offs[i]] = order[i];
+    if (i == 0) *count = offs[n];
 }
 
 __global__ void k_al_sizes(AlignArgs A, int32_t *sizes)
@@ -141,7 +152,9 @@ __global__ void k_al_offsets(AlignArgs A, const int64_t *off)
 
 // Kernel (a), uncompressed presets: k_sketch_tiles -> scan of the tile counts -> k_sketch_compact.
 // `lens` are the sequence lengths in descriptor order; on return b_mzoff / b_mzx / b_mzy hold the CSR minimizer lists.
-static int sketch_tiled(telr_af_ctx *ctx, const SketchArgs &sa, const int32_t *lens, int64_t *n_mz_out)
+// host_overlap() runs on the host while the tile kernel executes (before the one synchronisation of this stage).
+template <class F>
+static int sketch_tiled(telr_af_ctx *ctx, const SketchArgs &sa, const int32_t *lens, int64_t *n_mz_out, F host_overlap)
 {
     cudaStream_t st = ctx->stream;
     const int n_seq = sa.n_seq;
@@ -163,6 +176,7 @@ static int sketch_tiled(telr_af_ctx *ctx, const SketchArgs &sa, const int32_t *l
     k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_tcnt.as<int32_t>(), ctx->b_toff.as<int64_t>(), n_tiles, nullptr);
     int64_t n_mz = 0;
     CK(cudaMemcpyAsync(&n_mz, ctx->b_toff.as<int64_t>() + n_tiles, 8, cudaMemcpyDeviceToHost, st));
+    host_overlap();
     CK(cudaStreamSynchronize(st));     // tf[] must outlive its upload; n_mz sizes the CSR arrays
     ENS(ctx->b_mzx, (n_mz + 1) * 8); ENS(ctx->b_mzy, (n_mz + 1) * 4);
     ta.mz_x = ctx->b_mzx.as<uint64_t>(); ta.mz_y = ctx->b_mzy.as<uint32_t>();
@@ -225,25 +239,41 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
         ENS(ctx->b_hpc, stride * sk_grid); ENS(ctx->b_hpp, stride * sk_grid * 4); ENS(ctx->b_hpr, stride * sk_grid * 2);
         sa.hp_code = ctx->b_hpc.as<uint8_t>(); sa.hp_pos = ctx->b_hpp.as<int32_t>(); sa.hp_rl = ctx->b_hpr.as<uint16_t>(); sa.hp_stride = stride;
     }
+    // LPT order of the chunk's problems (problem index 2*rb + strand*nr + r of k_chain -> read rb + r; longest read first,
+    // ties by problem index): sorted on the host while the sketch kernels run
+    std::vector<int32_t> order((size_t)std::max(n_prob, 1));
+    auto make_order = [&]() {
+        std::vector<int32_t> plen((size_t)std::max(n_prob, 1));
+        for (int l = 0; l < n_loci; ++l) {
+            const int rb = lrb[l], nr = lrb[l + 1] - rb;
+            for (int sr = 0; sr < 2; ++sr)
+                for (int r = 0; r < nr; ++r) plen[2 * rb + sr * nr + r] = hm.read_len[r0 + rb + r];
+        }
+        for (int i = 0; i < n_prob; ++i) order[i] = i;
+        std::sort(order.begin(), order.begin() + n_prob, [&](int32_t a, int32_t b) { return plen[a] != plen[b] ? plen[a] > plen[b] : a < b; });
+    };
     sa.counts = ctx->b_counts.as<int32_t>();
     int64_t n_mz = 0;
     if (!o.hpc && ctx->sketch_tiles) {
         std::vector<int32_t> lens((size_t)n_seq);
         for (int r = 0; r < n_reads; ++r) lens[r] = hm.read_len[r0 + r];
         for (int l = 0; l < n_loci; ++l) lens[n_reads + l] = lens[n_reads + n_loci + l] = hm.contig_len[l0 + l];
-        int rc = sketch_tiled(ctx, sa, lens.data(), &n_mz);
+        int rc = sketch_tiled(ctx, sa, lens.data(), &n_mz, make_order);
         if (rc != TELR_OK) return rc;
         ENS(ctx->b_self, (n_mz + 1) * 2);
     } else {
         k_sketch<false><<<sk_grid, SK_THREADS, 0, st>>>(sa);
         k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_counts.as<int32_t>(), ctx->b_mzoff.as<int64_t>(), n_seq, nullptr);
         CK(cudaMemcpyAsync(&n_mz, ctx->b_mzoff.as<int64_t>() + n_seq, 8, cudaMemcpyDeviceToHost, st));
+        make_order();
         CK(cudaStreamSynchronize(st));
         ENS(ctx->b_mzx, (n_mz + 1) * 8); ENS(ctx->b_mzy, (n_mz + 1) * 4); ENS(ctx->b_self, (n_mz + 1) * 2);
         sa.offs = ctx->b_mzoff.as<int64_t>(); sa.mz_x = ctx->b_mzx.as<uint64_t>(); sa.mz_y = ctx->b_mzy.as<uint32_t>();
         k_sketch<true><<<sk_grid, SK_THREADS, 0, st>>>(sa);
     }
     CK(cudaEventRecord(ctx->ev[1], st));
+    ENS(ctx->b_order, (size_t)(n_prob + 1) * 4);
+    CK(cudaMemcpyAsync(ctx->b_order.p, order.data(), (size_t)n_prob * 4, cudaMemcpyHostToDevice, st));
     {
         int64_t max_nmz = (int64_t)max_qlen + 16, tab = 64;
         while (tab < 2 * max_nmz) tab <<= 1;
@@ -282,6 +312,14 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
     CK(cudaMemcpyAsync(&tot_scr, ctx->b_psoff.as<int64_t>() + n_prob, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&max_na, ctr + C_MAXNA, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (ctx->census) {
+        std::vector<int32_t> na((size_t)n_prob);
+        CK(cudaMemcpy(na.data(), ctx->b_pna.p, (size_t)n_prob * 4, cudaMemcpyDeviceToHost));
+        std::sort(na.begin(), na.end());
+        long long s2 = 0; for (int v : na) s2 += (long long)v * v;
+        fprintf(stderr, "[census] anchors per problem: n %d total %lld max %lld p50 %d p90 %d p99 %d p99.9 %d sum-of-squares %.3g\n", n_prob, (long long)tot_na, (long long)max_na,
+                na[n_prob / 2], na[(size_t)n_prob * 9 / 10], na[(size_t)n_prob * 99 / 100], na[(size_t)n_prob * 999 / 1000], (double)s2);
+    }
     ENS(ctx->b_anch, (tot_na + 1) * sizeof(Anchor)); ENS(ctx->b_regs, (tot_rcap + 1) * sizeof(Reg)); ENS(ctx->b_pscr, tot_scr + 256);
     const size_t ch_stride = (((size_t)max_qlen + 64) * 4 + 255) & ~(size_t)255;
     ENS(ctx->b_chws, ch_stride * (size_t)ch_grid * CH_WARPS);
@@ -303,23 +341,15 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
     CK(cudaEventRecord(ctx->ev[2], st));
     // ---- (d) alignment ----
     ENS(ctx->b_work, (size_t)(n_prob + 1) * 4);
-    k_worklist<<<(n_prob + 255) / 256, 256, 0, st>>>(n_prob, ctx->b_pnregs.as<int32_t>(), ctx->b_work.as<int32_t>(), (int32_t *)(ctr + C_NWORK));
+    ENS(ctx->b_wflag, (size_t)(n_prob + 1) * 4); ENS(ctx->b_woff, (size_t)(n_prob + 2) * 8);
+    k_work_flags<<<(n_prob + 255) / 256, 256, 0, st>>>(n_prob, ctx->b_order.as<int32_t>(), ctx->b_pnregs.as<int32_t>(), ctx->b_wflag.as<int32_t>());
+    k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_wflag.as<int32_t>(), ctx->b_woff.as<int64_t>(), n_prob, nullptr);
+    k_work_scatter<<<(n_prob + 255) / 256, 256, 0, st>>>(n_prob, ctx->b_order.as<int32_t>(), ctx->b_wflag.as<int32_t>(), ctx->b_woff.as<int64_t>(),
+                                                         ctx->b_work.as<int32_t>(), ctr + C_NWORK);
     int64_t n_work64 = 0;
     CK(cudaMemcpyAsync(&n_work64, ctr + C_NWORK, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const int n_work = (int)(n_work64 & 0xffffffff);
-    if (n_work > 1) {   // longest problems first (LPT): the persistent warps drain the queue in this order
-        std::vector<int32_t> wl(n_work), pr(n_prob);
-        CK(cudaMemcpyAsync(wl.data(), ctx->b_work.p, (size_t)n_work * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(pr.data(), ctx->b_pread.p, (size_t)n_prob * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        std::sort(wl.begin(), wl.end(), [&](int32_t a, int32_t b) {
-            int la = hm.read_len[r0 + pr[a]], lb = hm.read_len[r0 + pr[b]];
-            return la != lb ? la > lb : a < b;
-        });
-        CK(cudaMemcpyAsync(ctx->b_work.p, wl.data(), (size_t)n_work * 4, cudaMemcpyHostToDevice, st));
-        CK(cudaStreamSynchronize(st));
-    }
     int64_t chunk_bases = 0;
     for (int r = r0; r < r1; ++r) chunk_bases += hm.read_len[r];
     int64_t blocks_cap = chunk_bases / 2 + (int64_t)n_prob * 8 + 1024;
@@ -336,22 +366,21 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
     aa.anchors = ctx->b_anch.as<Anchor>(); aa.regs = ctx->b_regs.as<Reg>();
     aa.prob_scratch = ctx->b_pscr.as<uint8_t>(); aa.prob_soff = ctx->b_psoff.as<int64_t>();
     aa.work_list = ctx->b_work.as<int32_t>();
+    std::vector<int64_t> rbo(n_reads + 1);     // outlives its upload: the function synchronises again before it returns
     {   // nt4 bytes of every read of the chunk (forward + reverse complement)
-        std::vector<int64_t> rbo(n_reads + 1);
         int64_t acc = 0;
         for (int r = 0; r < n_reads; ++r) { rbo[r] = acc; acc += 2 * (((int64_t)hm.read_len[r0 + r] + 15) & ~15LL); }
         rbo[n_reads] = acc;
         ENS(ctx->b_rboff, (size_t)(n_reads + 1) * 8); ENS(ctx->b_rbytes, acc + 64);
         CK(cudaMemcpyAsync(ctx->b_rboff.p, rbo.data(), (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
-        CK(cudaStreamSynchronize(st));
         k_unpack_reads<<<std::max(1, std::min(n_reads, sm * 16)), 128, 0, st>>>(n_reads, db->seq2, db->nmask, read_off, read_len, ctx->b_rboff.as<int64_t>(), ctx->b_rbytes.as<uint8_t>());
         aa.read_bytes = ctx->b_rbytes.as<uint8_t>(); aa.rbyte_off = ctx->b_rboff.as<int64_t>();
     }
     const int nwk = std::max(n_work, 1);
     ENS(ctx->b_alwork, (size_t)nwk * sizeof(AlWork)); ENS(ctx->b_alctx, (size_t)nwk * sizeof(AlnCtx)); ENS(ctx->b_altask, (size_t)nwk * sizeof(DpTask));
     ENS(ctx->b_alres, (size_t)nwk * sizeof(DpRes)); ENS(ctx->b_alsz, (size_t)(nwk + 1) * 4); ENS(ctx->b_aloff, (size_t)(nwk + 2) * 8);
-    ENS(ctx->b_rc, 256);
-    const int al_grid = std::max(1, std::min((n_work + AL_WARPS - 1) / AL_WARPS, sm * AL_BLOCKS_PER_SM));
+    ENS(ctx->b_rc, 512);
+    const int al_grid = std::max(1, std::min((n_work + AL_WARPS - 1) / AL_WARPS, sm * ctx->al_blocks));
     {
         size_t maxT = ((size_t)max_tlen + 64) & ~(size_t)15;
         aa.max_tlen = max_tlen; aa.max_qlen = max_qlen; aa.dir_cap = ctx->dir_cap; aa.use_fast = ctx->use_fast; aa.use_vec = ctx->use_vec; aa.census = ctx->census;
@@ -383,7 +412,7 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
         CK(cudaStreamSynchronize(st));
         ENS(ctx->b_cigs, (size_t)(cig_total + 16) * 4);
         aa.cigs = ctx->b_cigs.as<uint32_t>();
-        CK(cudaMemsetAsync(ctx->b_rc.p, 0, 256, st));
+        CK(cudaMemsetAsync(ctx->b_rc.p, 0, 512, st));
         k_al_offsets<<<tb, 128, 0, st>>>(aa, ctx->b_aloff.as<int64_t>());
         k_al_init<<<tb, 128, 0, st>>>(aa);
         CK(cudaFuncSetAttribute(k_al_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(AL_WARPS * sizeof(VecSmem))));
@@ -421,12 +450,15 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
         return (err & 16) ? TELR_EUNSUPPORTED : TELR_ECAP;
     }
     if (ctx->census && n_work > 0) {     // where the alignment kernel's warp cycles go (diagnostic, TELR_CENSUS=1)
-        unsigned long long rc[32];
+        unsigned long long rc[64];
         CK(cudaMemcpy(rc, ctx->b_rc.p, sizeof(rc), cudaMemcpyDeviceToHost));
         fprintf(stderr, "[census] cycles(M): coroutine %.1f | fill dp %.1f tb %.1f | vec dp %.1f tb %.1f | scalar dp %.1f tb %.1f | ll %.1f\n",
                 rc[4] / 1e6, rc[5] / 1e6, rc[8] / 1e6, rc[6] / 1e6, rc[9] / 1e6, rc[7] / 1e6, rc[10] / 1e6, rc[11] / 1e6);
         fprintf(stderr, "[census] tasks: fill %llu vec %llu scalar %llu ll %llu | q*t (M): fill %.1f vec %.1f scalar %.1f\n",
                 rc[12], rc[13], rc[14], rc[15], rc[16] / 1e6, rc[17] / 1e6, rc[18] / 1e6);
+        for (int b = 0; b < 6; ++b)
+            fprintf(stderr, "[census] vec min(q,t) bucket %d: tasks %llu zdropped %llu cycles(M) %.1f mean max-diag %.0f mean q+t %.0f\n", b, rc[38 + b], rc[44 + b],
+                    rc[32 + b] / 1e6, rc[38 + b] ? (double)rc[50 + b] / rc[38 + b] : 0.0, rc[38 + b] ? (double)rc[56 + b] / rc[38 + b] : 0.0);
     }
     stats->dp_cells += hc[C_CELLS]; stats->n_dp_tasks += hc[C_TASKS]; stats->n_anchors += hc[C_ANCH]; stats->n_minimizers += n_mz;
     stats->n_aln_blocks += hc[C_NBLK];
@@ -520,6 +552,8 @@ int telr_af_create(telr_af_ctx **out, int device, size_t workspace_bytes)
     if (uf) ctx->use_fast = atoi(uf) ? 1 : 0;
     const char *uv = getenv("TELR_VEC_EXT");
     if (uv) ctx->use_vec = atoi(uv) ? 1 : 0;
+    const char *alb = getenv("TELR_AL_CTAS");
+    if (alb && atoi(alb) >= 1 && atoi(alb) <= AL_BLOCKS_PER_SM) ctx->al_blocks = atoi(alb);
     const char *skt = getenv("TELR_SKETCH_TILES");
     if (skt) ctx->sketch_tiles = atoi(skt) != 0;
     const char *cs = getenv("TELR_CENSUS");
@@ -543,7 +577,7 @@ int telr_af_destroy(telr_af_ctx *ctx)
                      &ctx->b_alws, &ctx->b_work, &ctx->b_blk, &ctx->b_pblkoff, &ctx->b_pblkcnt, &ctx->b_ctr, &ctx->b_alnout, &ctx->b_cigout, &ctx->b_doff,
                      &ctx->b_big, &ctx->b_biglock, &ctx->b_rbytes, &ctx->b_rboff, &ctx->b_alwork, &ctx->b_alctx, &ctx->b_altask, &ctx->b_alres, &ctx->b_alsz, &ctx->b_aloff,
                      &ctx->b_cigs, &ctx->b_pool, &ctx->b_tlist, &ctx->b_rc, &ctx->b_opt, &ctx->b_idxbig, &ctx->b_psb, &ctx->b_psoff, &ctx->b_pscr, &ctx->b_pnu, &ctx->b_pm,
-                     &ctx->b_tfirst, &ctx->b_tcnt, &ctx->b_toff, &ctx->b_tmpx, &ctx->b_tmpy};
+                     &ctx->b_tfirst, &ctx->b_tcnt, &ctx->b_toff, &ctx->b_tmpx, &ctx->b_tmpy, &ctx->b_order, &ctx->b_wflag, &ctx->b_woff};
     for (auto *b : all) b->release();
     for (auto &b : ctx->b_in) b.release();
     for (auto &e : ctx->ev) cudaEventDestroy(e);
@@ -668,7 +702,7 @@ int telr_af_sketch(telr_af_ctx *ctx, const uint32_t *seq2, const uint32_t *nmask
     sa.counts = ctx->b_counts.as<int32_t>();
     int64_t n_mz = 0;
     if (!hpc && ctx->sketch_tiles) {
-        int rc = sketch_tiled(ctx, sa, seq_len, &n_mz);
+        int rc = sketch_tiled(ctx, sa, seq_len, &n_mz, []() {});
         if (rc != TELR_OK) return rc;
         CK(cudaMemcpyAsync(mz_off, ctx->b_mzoff.p, (size_t)(n_seq + 1) * 8, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
