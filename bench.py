@@ -207,6 +207,7 @@ def main():
 
     stage_ms = {}
     cells = [0]
+    counts = {"mz": 0, "blk": 0}
 
     def fan_out(fn):
         if K == 1:
@@ -233,6 +234,7 @@ def main():
             for i in range(8):
                 stage_ms[i] = stage_ms.get(i, 0.0) + float(sl.cres.ms_stage[i])
             cells[0] += int(sl.cres.dp_cells)
+            counts["mz"] += int(sl.cres.n_minimizers); counts["blk"] += int(sl.cres.n_aln_blocks)
 
     def one_host(sl):
         rc = lib.lib().telr_af_run(sl.ctx._h, C.byref(sl.hb), C.byref(sl.hres))
@@ -244,7 +246,7 @@ def main():
 
     for _ in range(max(args.warmup, 3)):
         step_dev()
-    stage_ms.clear(); cells[0] = 0
+    stage_ms.clear(); cells[0] = 0; counts["mz"] = counts["blk"] = 0
     sampler = ClockSampler(local)
     sampler.start()
     l0 = sum(sl.ctx.launches for sl in slices)
@@ -264,6 +266,13 @@ def main():
     f_mhz = clocks["sm_mhz"] or sm_max_mhz
     nsm = torch.cuda.get_device_properties(local).multi_processor_count
     peak_gcups = nsm * 64 * f_mhz * 1e6 * 2 / OPS_PER_CELL / 1e9      # alu pipe, 16x2 packed ops: 2 cells per lane-op
+    # HBM-bound stages (SURVEY 8d work units): sketch reads ceil(len/4) + ceil(len/8) bytes per sequence (reads and both
+    # contig strands) and writes 12 B per minimizer; depth+AF reads 8 B per alignment block (per-base depth is not
+    # requested in the bench, so nothing is written).  Stage times are CUDA events around the stage's kernels.
+    seq_lens = np.concatenate([batch.read_len.astype(np.int64), batch.contig_len.astype(np.int64), batch.contig_len.astype(np.int64)])
+    sk_bytes = float(((seq_lens + 3) // 4 + (seq_lens + 7) // 8).sum()) * args.steps + 12.0 * counts["mz"]
+    dp_bytes = 8.0 * counts["blk"]
+    sk_s, de_s = stage_ms.get(0, 0.0) / 1e3 / K, stage_ms.get(6, 0.0) / 1e3 / K
     h2d = batch.h2d_bytes()
     d2h = int(batch.n_loci * 40)
     line = None
@@ -285,6 +294,10 @@ def main():
                          "frac": gcups / peak_gcups if peak_gcups else None,
                          "traffic": (DRAM_BYTES_PER_CELL * cells[0] / max(launches // LAUNCHES_PER_CHUNK, 1)) if cells[0] else None,
                          "note": f"peak = {nsm} SM x 64 lane-ops/clk x {f_mhz} MHz x 2 cells/op / {OPS_PER_CELL:.0f} ops/cell; HBM peak {hbm_gbs} GB/s ({peak_kind}) applies to sketch/depth; traffic = bytes per k_al_fused launch, 1.33 B/cell from the ncu capture in profiles/ scaled by this run's cells; the kernel issues 0.71 warp-inst/clk/sub-partition against a measured two-pipe ceiling of 0.705 (profiles/ubench)"},
+            "hbm_stages": {"sketch": {"bound": "hbm", "achieved": sk_bytes / sk_s / 1e9 if sk_s > 0 else None, "peak": hbm_gbs, "unit": "GB/s",
+                                      "frac": sk_bytes / sk_s / 1e9 / hbm_gbs if sk_s > 0 else None, "minimizers_per_step": counts["mz"] // max(args.steps, 1)},
+                           "depth_af": {"bound": "hbm", "achieved": dp_bytes / de_s / 1e9 if de_s > 0 else None, "peak": hbm_gbs, "unit": "GB/s",
+                                        "frac": dp_bytes / de_s / 1e9 / hbm_gbs if de_s > 0 else None, "blocks_per_step": counts["blk"] // max(args.steps, 1)}},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e, "unit": "loci/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_wall / args.steps * 1e3},
             "gpu_launches": launches, "clocks": clocks, "wall_ms_per_step": wall_s / args.steps * 1e3,

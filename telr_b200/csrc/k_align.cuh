@@ -16,6 +16,12 @@
 
 namespace telr {
 
+// The cycle census (TELR_CENSUS=1) costs 1.5 KB of code inside the hottest loop of an instruction-cache-bound kernel, so it is
+// compiled in only with -DTELR_CENSUS_BUILD=1 (profiles/census.sh builds that variant).
+#ifndef TELR_CENSUS_BUILD
+#define TELR_CENSUS_BUILD 0
+#endif
+#define AL_CENSUS(A) (TELR_CENSUS_BUILD && (A).census)
 constexpr int AL_THREADS = 128;
 constexpr int AL_WARPS = AL_THREADS / 32;
 #ifndef TELR_AL_BLOCKS
@@ -479,13 +485,13 @@ __global__ void __launch_bounds__(AL_THREADS, AL_BLOCKS_PER_SM) k_al_fused(const
         for (;;) {
             long long t0 = 0;
             if (lane == 0) {
-                if (A.census) t0 = clock64();
+                if (AL_CENSUS(A)) t0 = clock64();
                 W.more = aln_next(W.c, W.res, W.task) ? 1 : 0;
-                if (A.census) atomicAdd(&A.rc[4], (unsigned long long)(clock64() - t0));
+                if (AL_CENSUS(A)) atomicAdd(&A.rc[4], (unsigned long long)(clock64() - t0));
             }
             __syncwarp();
             if (!W.more) break;
-            if (A.census) t0 = clock64();
+            if (AL_CENSUS(A)) t0 = clock64();
             if (W.task.kind == 0) {
                 const bool fast = A.use_fast && fill_fast_ok(W.task);
                 const int64_t need = fast ? (int64_t)W.task.qlen * fill_stride(W.task.tlen) : vec_dir_bytes(W.task.qlen, W.task.tlen, W.task.w);
@@ -510,11 +516,18 @@ __global__ void __launch_bounds__(AL_THREADS, AL_BLOCKS_PER_SM) k_al_fused(const
                 if (!done_fast) vec = warp_extd2(o, W.task, W.res, S, A.stat_cells, A.err);
                 __syncwarp();
                 const int path = done_fast ? 0 : vec ? 1 : 2;
-                if (A.census && lane == 0) {
+                if (AL_CENSUS(A) && lane == 0) {
                     long long t1 = clock64();
                     atomicAdd(&A.rc[5 + path], (unsigned long long)(t1 - t0));
                     atomicAdd(&A.rc[12 + path], 1ULL);
                     atomicAdd(&A.rc[16 + path], (unsigned long long)W.task.qlen * (unsigned long long)W.task.tlen);
+                    if (path == 0) {        // gap fills by target length: one 256-column pass, or two
+                        const int tl = W.task.tlen;
+                        const int b = tl <= 256 ? 0 : tl <= 288 ? 1 : tl <= 320 ? 2 : tl <= 384 ? 3 : tl <= 512 ? 4 : 5;
+                        atomicAdd(&A.rc[64 + b], 1ULL);
+                        atomicAdd(&A.rc[70 + b], (unsigned long long)(t1 - t0));
+                        atomicAdd(&A.rc[76 + b], (unsigned long long)W.task.qlen * (unsigned long long)W.task.tlen);
+                    }
                     if (path == 1) {        // shape census of the general DP: buckets of min(qlen, tlen)
                         const int mn = W.task.qlen < W.task.tlen ? W.task.qlen : W.task.tlen;
                         const int b = mn < 64 ? 0 : mn < 128 ? 1 : mn < 256 ? 2 : mn < 512 ? 3 : mn < 1024 ? 4 : 5;
@@ -530,11 +543,11 @@ __global__ void __launch_bounds__(AL_THREADS, AL_BLOCKS_PER_SM) k_al_fused(const
                 if (lane == 0) {
                     if (!done_fast) { if (vec) extd2_traceback_vec(W.task, W.res, S.dir, S.ezcig, S.ezcap, A.err); else extd2_traceback(W.task, W.res, S.dir, S.ezcig, S.ezcap, A.err); }
                     if (big_slot >= 0) { __threadfence(); atomicExch(&A.big_lock[big_slot], 0); }
-                    if (A.census) atomicAdd(&A.rc[8 + path], (unsigned long long)(clock64() - t0));
+                    if (AL_CENSUS(A)) atomicAdd(&A.rc[8 + path], (unsigned long long)(clock64() - t0));
                 }
             } else {
                 warp_ll(o, W.task, W.res, S, A.stat_cells);
-                if (A.census && lane == 0) { atomicAdd(&A.rc[11], (unsigned long long)(clock64() - t0)); atomicAdd(&A.rc[15], 1ULL); }
+                if (AL_CENSUS(A) && lane == 0) { atomicAdd(&A.rc[11], (unsigned long long)(clock64() - t0)); atomicAdd(&A.rc[15], 1ULL); }
             }
             __syncwarp();
         }

@@ -57,6 +57,7 @@ struct ChainArgs {
     int32_t *prob_nregs, *prob_nca;
     uint8_t *warp_scratch; size_t warp_scratch_stride; int32_t max_na;   // per-warp: kept-minimizer list of the fill pass
     int32_t *work_counter; int32_t *err;
+    int32_t *dp_counter, *rmq_counter;      // dynamic problem queues of k_chain_dp / k_chain_rmq (problem sizes vary 7x)
     unsigned long long *stat_anchors;
     // per-problem scratch for the chaining kernels (ChainScratch + HitScratch carved at prob_soff[p])
     uint8_t *prob_scratch; const int64_t *prob_soff;
@@ -539,14 +540,16 @@ __global__ void __launch_bounds__(128) k_chain_sort(const __grid_constant__ Chai
 __global__ void __launch_bounds__(256) k_chain_dp(const __grid_constant__ ChainArgs A)
 {
     const int lane = threadIdx.x & 31;
-    const int nw = gridDim.x * (blockDim.x >> 5);
-    for (int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < A.n_prob; p += nw) {
+    for (;;) {
+        int p = 0;
+        if (lane == 0) p = atomicAdd(A.dp_counter, 1);
+        p = __shfl_sync(0xffffffffu, p, 0);
+        if (p >= A.n_prob) break;
         const int n_a = (int)(A.prob_aoff[p + 1] - A.prob_aoff[p]);
         if (n_a == 0) continue;
         ChainScratch cs; HitScratch hs; int cap;
         prob_carve(A, p, n_a, cs, hs, &cap);
         chain_dp_warp(A.o, n_a, A.anchors + A.prob_aoff[p], cs);
-        (void)lane;
     }
 }
 
@@ -579,8 +582,12 @@ __global__ void __launch_bounds__(128) k_chain_bt(const __grid_constant__ ChainA
 // re-chaining DP, one WARP per flagged problem
 __global__ void __launch_bounds__(256) k_chain_rmq(const __grid_constant__ ChainArgs A)
 {
-    const int nw = gridDim.x * (blockDim.x >> 5);
-    for (int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < A.n_prob; p += nw) {
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        int p = 0;
+        if (lane == 0) p = atomicAdd(A.rmq_counter, 1);
+        p = __shfl_sync(0xffffffffu, p, 0);
+        if (p >= A.n_prob) break;
         const int m = A.prob_m[p];
         if (m == 0) continue;
         const int n_a = (int)(A.prob_aoff[p + 1] - A.prob_aoff[p]);

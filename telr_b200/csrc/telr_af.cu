@@ -190,7 +190,7 @@ struct HostMeta {       // host copies of the small per-read / per-locus arrays
 };
 
 // counters layout in b_ctr (int64 slots)
-enum { C_WORK_CHAIN = 0, C_WORK_ALIGN = 1, C_ERR = 2, C_NWORK = 3, C_ANCH = 4, C_CELLS = 5, C_TASKS = 6, C_NBLK = 7, C_NALN = 8, C_NCIG = 9, C_MAXNA = 10, C_SLOTS = 16 };
+enum { C_WORK_CHAIN = 0, C_WORK_ALIGN = 1, C_ERR = 2, C_NWORK = 3, C_ANCH = 4, C_CELLS = 5, C_TASKS = 6, C_NBLK = 7, C_NALN = 8, C_NCIG = 9, C_MAXNA = 10, C_WORK_DP = 11, C_WORK_RMQ = 12, C_SLOTS = 16 };
 
 static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* device pointers */, const HostMeta &hm,
                      int l0, int l1, telr_af_result *dres /* device pointers for cov2x/af/depth */, const int64_t *h_depth_off,
@@ -249,8 +249,10 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
             for (int sr = 0; sr < 2; ++sr)
                 for (int r = 0; r < nr; ++r) plen[2 * rb + sr * nr + r] = hm.read_len[r0 + rb + r];
         }
-        for (int i = 0; i < n_prob; ++i) order[i] = i;
-        std::sort(order.begin(), order.begin() + n_prob, [&](int32_t a, int32_t b) { return plen[a] != plen[b] ? plen[a] > plen[b] : a < b; });
+        std::vector<int32_t> start((size_t)max_qlen + 2, 0);      // counting sort: descending length, ascending problem index
+        for (int i = 0; i < n_prob; ++i) ++start[max_qlen - plen[i] + 1];
+        for (int v = 0; v <= max_qlen; ++v) start[v + 1] += start[v];
+        for (int i = 0; i < n_prob; ++i) order[start[max_qlen - plen[i]]++] = i;
     };
     sa.counts = ctx->b_counts.as<int32_t>();
     int64_t n_mz = 0;
@@ -294,7 +296,8 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
     ca.read_len = read_len; ca.read_hash = read_hash;
     ca.prob_na = ctx->b_pna.as<int32_t>(); ca.prob_read = ctx->b_pread.as<int32_t>(); ca.prob_ls = ctx->b_pls.as<int32_t>();
     ca.prob_nregs = ctx->b_pnregs.as<int32_t>(); ca.prob_nca = ctx->b_pnca.as<int32_t>();
-    ca.work_counter = (int32_t *)(ctr + C_WORK_CHAIN); ca.err = (int32_t *)(ctr + C_ERR); ca.stat_anchors = (unsigned long long *)(ctr + C_ANCH);
+    ca.work_counter = (int32_t *)(ctr + C_WORK_CHAIN); ca.err = (int32_t *)(ctr + C_ERR);
+    ca.dp_counter = (int32_t *)(ctr + C_WORK_DP); ca.rmq_counter = (int32_t *)(ctr + C_WORK_RMQ); ca.stat_anchors = (unsigned long long *)(ctr + C_ANCH);
     const int ch_grid = std::min(2 * n_loci, sm);
     ENS(ctx->b_idxbig, sizeof(IdxBig) * (size_t)ch_grid);
     ca.idx_big = ctx->b_idxbig.as<IdxBig>();
@@ -379,7 +382,7 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
     const int nwk = std::max(n_work, 1);
     ENS(ctx->b_alwork, (size_t)nwk * sizeof(AlWork)); ENS(ctx->b_alctx, (size_t)nwk * sizeof(AlnCtx)); ENS(ctx->b_altask, (size_t)nwk * sizeof(DpTask));
     ENS(ctx->b_alres, (size_t)nwk * sizeof(DpRes)); ENS(ctx->b_alsz, (size_t)(nwk + 1) * 4); ENS(ctx->b_aloff, (size_t)(nwk + 2) * 8);
-    ENS(ctx->b_rc, 512);
+    ENS(ctx->b_rc, 1024);
     const int al_grid = std::max(1, std::min((n_work + AL_WARPS - 1) / AL_WARPS, sm * ctx->al_blocks));
     {
         size_t maxT = ((size_t)max_tlen + 64) & ~(size_t)15;
@@ -412,7 +415,7 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
         CK(cudaStreamSynchronize(st));
         ENS(ctx->b_cigs, (size_t)(cig_total + 16) * 4);
         aa.cigs = ctx->b_cigs.as<uint32_t>();
-        CK(cudaMemsetAsync(ctx->b_rc.p, 0, 512, st));
+        CK(cudaMemsetAsync(ctx->b_rc.p, 0, 1024, st));
         k_al_offsets<<<tb, 128, 0, st>>>(aa, ctx->b_aloff.as<int64_t>());
         k_al_init<<<tb, 128, 0, st>>>(aa);
         CK(cudaFuncSetAttribute(k_al_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(AL_WARPS * sizeof(VecSmem))));
@@ -450,12 +453,15 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
         return (err & 16) ? TELR_EUNSUPPORTED : TELR_ECAP;
     }
     if (ctx->census && n_work > 0) {     // where the alignment kernel's warp cycles go (diagnostic, TELR_CENSUS=1)
-        unsigned long long rc[64];
+        unsigned long long rc[128];
         CK(cudaMemcpy(rc, ctx->b_rc.p, sizeof(rc), cudaMemcpyDeviceToHost));
         fprintf(stderr, "[census] cycles(M): coroutine %.1f | fill dp %.1f tb %.1f | vec dp %.1f tb %.1f | scalar dp %.1f tb %.1f | ll %.1f\n",
                 rc[4] / 1e6, rc[5] / 1e6, rc[8] / 1e6, rc[6] / 1e6, rc[9] / 1e6, rc[7] / 1e6, rc[10] / 1e6, rc[11] / 1e6);
         fprintf(stderr, "[census] tasks: fill %llu vec %llu scalar %llu ll %llu | q*t (M): fill %.1f vec %.1f scalar %.1f\n",
                 rc[12], rc[13], rc[14], rc[15], rc[16] / 1e6, rc[17] / 1e6, rc[18] / 1e6);
+        static const char *fb[6] = {"<=256", "<=288", "<=320", "<=384", "<=512", ">512"};
+        for (int b = 0; b < 6; ++b)
+            fprintf(stderr, "[census] fill tlen %s: tasks %llu cycles(M) %.1f q*t(M) %.1f\n", fb[b], rc[64 + b], rc[70 + b] / 1e6, rc[76 + b] / 1e6);
         for (int b = 0; b < 6; ++b)
             fprintf(stderr, "[census] vec min(q,t) bucket %d: tasks %llu zdropped %llu cycles(M) %.1f mean max-diag %.0f mean q+t %.0f\n", b, rc[38 + b], rc[44 + b],
                     rc[32 + b] / 1e6, rc[38 + b] ? (double)rc[50 + b] / rc[38 + b] : 0.0, rc[38 + b] ? (double)rc[56 + b] / rc[38 + b] : 0.0);
