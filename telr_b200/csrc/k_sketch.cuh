@@ -10,6 +10,7 @@
 // map-pb's homopolymer compression runs as a per-sequence pre-pass (run ends -> steps).
 #pragma once
 #include <cuda_runtime.h>
+#include <type_traits>
 #include "mm_types.cuh"
 
 namespace telr {
@@ -83,26 +84,34 @@ struct SkSmem {
 // entries equal it; the minimum over -w..-1 (mp), the one over -(w-1)..0 (mn) and the number of identical-hash
 // duplicates each case would flush follow from m1, X[-w] and X[0] without further loops.  The duplicate-flush loops
 // themselves only run when such duplicates exist (tandem repeats).
-template <class XF, class Emit> __device__ __forceinline__ void sk_step_g(XF Xd, int j, int l, int w, int k, Emit &emit)
+// T = key type (uint64_t: hash<<8|span; uint32_t: the bare hash when 2k <= 30 and the span is the constant k — same order),
+// WT = compile-time window length (0: use the run-time w).  The scan is branch-free.
+template <class T, int WT, class XF, class Emit> __device__ __forceinline__ void sk_step_g(XF Xd, int j, int l, int w_rt, int k, Emit &emit)
 {
-    const uint64_t MAXV = ~0ULL;
-    const uint64_t info = Xd(0), xw = Xd(w);
-    uint64_t m1 = MAXV; int d1 = w - 1, c1 = 0;
+    const int w = WT ? WT : w_rt;
+    const T MAXV = ~(T)0;
+    const T info = Xd(0), xw = Xd(w);
+    T m1 = MAXV; int d1 = w - 1, c1 = 0;
+#pragma unroll
     for (int d = w - 1; d >= 1; --d) {
-        const uint64_t v = Xd(d);
-        if (v < m1) m1 = v, d1 = d, c1 = 1;
-        else if (v == m1) d1 = d, ++c1;
+        const T v = Xd(d);
+        const bool lt = v < m1, eq = v == m1;
+        m1 = lt ? v : m1;
+        d1 = (lt || eq) ? d : d1;
+        c1 = lt ? 1 : c1 + (eq ? 1 : 0);
     }
     if (w < 2) c1 = 0;
     // previous minimum over steps -w..-1 (rightmost on ties)
     const bool from_w = xw < m1;
-    const uint64_t mp = from_w ? xw : m1;
+    const T mp = from_w ? xw : m1;
     const int mpd = (from_w || w < 2) ? w : d1;
     if (l == w + k - 1 && mp != MAXV) {
         const int dup = from_w ? 0 : c1 - 1;      // other entries of -(w-1)..-1 equal to mp
-        if (dup > 0)
+        if (dup > 0) {
+#pragma unroll 1
             for (int d = w - 1; d >= 1; --d)
                 if (Xd(d) == mp && d != mpd) emit(j - d);
+        }
     }
     if (info <= mp) {
         if (l >= w + k && mp != MAXV) emit(j - mpd);
@@ -110,20 +119,22 @@ template <class XF, class Emit> __device__ __forceinline__ void sk_step_g(XF Xd,
         if (l >= w + k - 1 && mp != MAXV) emit(j - mpd);
         // new minimum over steps -(w-1)..0 (rightmost on ties)
         const bool from_0 = info <= m1;
-        const uint64_t mn = from_0 ? info : m1;
+        const T mn = from_0 ? info : m1;
         const int mnd = from_0 ? 0 : d1;
         if (l >= w + k - 1 && mn != MAXV) {
             const int dup = info == m1 ? c1 : from_0 ? 0 : c1 - 1;
-            if (dup > 0)
+            if (dup > 0) {
+#pragma unroll 1
                 for (int d = w - 1; d >= 0; --d)
                     if (Xd(d) == mn && d != mnd) emit(j - d);
+            }
         }
     }
 }
 template <class Emit> __device__ __forceinline__ void sk_step(const SkSmem &S, int j, int w, int k, Emit &emit)
 {
     const uint64_t *X = S.X + SK_XH + j;        // X[0] = this step, X[-d] = d steps back
-    sk_step_g([X](int d) { return X[-d]; }, j, (int)S.lcap[j], w, k, emit);
+    sk_step_g<uint64_t, 0>([X](int d) { return X[-d]; }, j, (int)S.lcap[j], w, k, emit);
 }
 
 struct SkCount { int n; __device__ __forceinline__ void operator()(int) { ++n; } };
@@ -344,8 +355,10 @@ template <bool WRITE> __global__ void __launch_bounds__(SK_THREADS) k_sketch(Ske
 //     stream with two funnel shifts (no rolling state): the forward k-mer is its 2-bit-group reversal (BREV), the
 //     reverse-complement k-mer its complement.  The count of unambiguous bases behind the step is a CLZ of the
 //     64 N bits that end at it.
-//   * Hashes live in a 64-entry ring; sk_step_g reads its w+1 neighbours from the ring (conflict-free: consecutive
-//     lanes, consecutive words) and records at most two pushes per step in registers; one ballot orders them.
+//   * Hashes live in a two-block (previous 32 steps, current 32 steps) shared array; sk_step_g reads its w+1 neighbours from
+//     it at fixed offsets (conflict-free: consecutive lanes, consecutive words) and records at most two pushes per step in
+//     registers; one ballot orders them.  With 2k <= 30 (map-ont) the array holds the bare 32-bit hash and the k-mer is one
+//     funnel shift; the window length is a template parameter for the two presets, so the scan is straight-line code.
 //   * Minimizers go to a per-tile slot of a temporary array; k_sketch_compact packs the tiles into the CSR layout
 //     after an exclusive scan of the tile counts.  Every base is read once and hashed once.
 constexpr int SKT_TILE = 2048, SKT_LEAD = 128, SKT_WARPS = 8, SKT_CAP = SKT_TILE + 32;
@@ -364,33 +377,39 @@ struct SketchTileArgs {
     uint64_t *mz_x; uint32_t *mz_y;
 };
 
-struct SktWarp { uint64_t X[64]; uint32_t cw[SKT_CW]; uint32_t nw[SKT_NW]; };
+template <class T> struct SktWarp { T X[64]; uint32_t cw[SKT_CW]; uint32_t nw[SKT_NW]; };   // X[0..31]: previous 32 steps, X[32..63]: current
 
 struct SkRec {
     int n, t0, t1;
     __device__ __forceinline__ void operator()(int jj) { if (n == 0) t0 = jj; else if (n == 1) t1 = jj; ++n; }
 };
-struct SkTileWrite {
-    const SktWarp *W; uint64_t *ox; uint32_t *oy; int at, cap, c, T0; uint32_t zcur, zprev;
+// writes the minimizer of local step jj (jj in [c*32 - w, c*32 + 31]) into the tile's slot
+template <class T> struct SkTileWrite {
+    const T *X; uint64_t *ox; uint32_t *oy; int at, cap, c, T0, k; uint32_t zcur, zprev;
     __device__ __forceinline__ void operator()(int jj)
     {
         if (at < cap) {
-            ox[at] = W->X[jj & 63];
+            const T x = X[32 + jj - c * 32];
+            ox[at] = sizeof(T) == 4 ? ((uint64_t)x << 8 | (uint64_t)k) : (uint64_t)x;
             oy[at] = (uint32_t)(T0 + jj) << 1 | ((((jj >> 5) == c ? zcur : zprev) >> (jj & 31)) & 1u);
         }
         ++at;
     }
 };
 
+// K32: 2k <= 30, the ring holds the bare 30-bit hash (the span is the constant k, so the order is the same).
+// WT: compile-time window length of the instance (0 = run-time w).
+template <bool K32, int WT>
 __global__ void __launch_bounds__(SKT_WARPS * 32) k_sketch_tiles(const __grid_constant__ SketchTileArgs A)
 {
-    __shared__ SktWarp SW[SKT_WARPS];
+    typedef typename std::conditional<K32, uint32_t, uint64_t>::type T;
+    __shared__ SktWarp<T> SW[SKT_WARPS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned FULL = 0xffffffffu;
-    SktWarp &W = SW[wid];
-    const int w = A.w, k = A.k, cap = w + k;
-    const uint64_t MAXV = ~0ULL, mask = (1ULL << 2 * k) - 1;
-    const bool h32 = 2 * k <= 32;
+    SktWarp<T> &W = SW[wid];
+    const int w = WT ? WT : A.w, k = A.k, cap = w + k;
+    const T MAXV = ~(T)0;
+    const uint64_t mask = (1ULL << 2 * k) - 1;
     for (int tile = blockIdx.x * SKT_WARPS + wid; tile < A.n_tiles; tile += gridDim.x * SKT_WARPS) {
         // sequence of this tile: the last one whose first tile is <= tile
         int lo = 0, hi = A.n_seq;
@@ -437,6 +456,8 @@ __global__ void __launch_bounds__(SKT_WARPS * 32) k_sketch_tiles(const __grid_co
         int out_run = 0;
         const int nblk = (tn + 31) >> 5;
         uint64_t *ox = A.tmp_x + (int64_t)tile * SKT_CAP; uint32_t *oy = A.tmp_y + (int64_t)tile * SKT_CAP;
+        const T *Xme = W.X + 32 + lane;            // X of this lane's step; Xme[-d] = d steps back
+        T Xprev = MAXV;
         for (int c = -1; c < nblk; ++c) {
             const int j = c * 32 + lane, s = j + SKT_LEAD;
             // unambiguous bases ending at s: CLZ of the 64 N bits [s-63, s]
@@ -448,20 +469,18 @@ __global__ void __launch_bounds__(SKT_WARPS * 32) k_sketch_tiles(const __grid_co
                 const int run = wh ? __clz((int)wh) : 32 + __clz((int)wl);
                 l = run < cap ? run : cap;
             }
-            uint64_t X = MAXV; int z = 0;
+            T X = MAXV; int z = 0;
             if (l >= k) {
                 const int sb = s - k + 1, wi = sb >> 4, sh = 2 * (sb & 15);
                 const uint32_t a = W.cw[wi], b = W.cw[wi + 1], cc = W.cw[wi + 2];
-                const uint64_t val = ((uint64_t)__funnelshift_r(b, cc, sh) << 32 | __funnelshift_r(a, b, sh)) & mask;
-                uint64_t r = __brevll(val);
-                r = ((r >> 1) & 0x5555555555555555ULL) | ((r & 0x5555555555555555ULL) << 1);
-                const uint64_t k0 = r >> (64 - 2 * k), k1 = ~val & mask;
-                z = k0 < k1 ? 0 : 1;
-                const uint64_t km = z ? k1 : k0;
-                uint64_t h;
-                if (h32) {
+                if (K32) {
                     const uint32_t m32 = (uint32_t)mask;
-                    uint32_t key = (uint32_t)km;
+                    const uint32_t val = __funnelshift_r(a, b, sh) & m32;                 // 2k <= 30 bits: one funnel shift
+                    uint32_t r = __brev(val);
+                    r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+                    const uint32_t k0 = r >> (32 - 2 * k), k1 = ~val & m32;
+                    z = k0 < k1 ? 0 : 1;
+                    uint32_t key = z ? k1 : k0;
                     key = (~key + (key << 21)) & m32;
                     key = key ^ key >> 24;
                     key = (key * 265u) & m32;
@@ -469,17 +488,22 @@ __global__ void __launch_bounds__(SKT_WARPS * 32) k_sketch_tiles(const __grid_co
                     key = (key * 21u) & m32;
                     key = key ^ key >> 28;
                     key = (key + (key << 31)) & m32;
-                    h = key;
-                } else h = mix64_masked(km, mask);
-                X = h << 8 | (uint64_t)k;
+                    X = (T)key;
+                } else {
+                    const uint64_t val = ((uint64_t)__funnelshift_r(b, cc, sh) << 32 | __funnelshift_r(a, b, sh)) & mask;
+                    uint64_t r = __brevll(val);
+                    r = ((r >> 1) & 0x5555555555555555ULL) | ((r & 0x5555555555555555ULL) << 1);
+                    const uint64_t k0 = r >> (64 - 2 * k), k1 = ~val & mask;
+                    z = k0 < k1 ? 0 : 1;
+                    X = (T)(mix64_masked(z ? k1 : k0, mask) << 8 | (uint64_t)k);
+                }
             }
             zprev = zcur; zcur = __ballot_sync(FULL, z);
-            W.X[j & 63] = X;
+            W.X[lane] = Xprev; W.X[32 + lane] = X; Xprev = X;
             __syncwarp();
             if (c >= 0) {
                 SkRec rec; rec.n = 0; rec.t0 = 0; rec.t1 = 0;
-                const SktWarp *Wp = &W;
-                if (j < tn) sk_step_g([Wp, j](int d) { return Wp->X[(j - d) & 63]; }, j, l, w, k, rec);
+                if (j < tn) sk_step_g<T, WT>([Xme](int d) { return Xme[-d]; }, j, l, w, k, rec);
                 const unsigned m1 = __ballot_sync(FULL, rec.n > 0);
                 int pre, tot;
                 if (!__any_sync(FULL, rec.n > 1)) { pre = __popc(m1 & ((1u << lane) - 1)); tot = __popc(m1); }
@@ -490,9 +514,9 @@ __global__ void __launch_bounds__(SKT_WARPS * 32) k_sketch_tiles(const __grid_co
                     tot = __shfl_sync(FULL, x, 31); pre = x - rec.n;
                 }
                 if (rec.n) {
-                    SkTileWrite wr; wr.W = &W; wr.ox = ox; wr.oy = oy; wr.at = out_run + pre; wr.cap = SKT_CAP; wr.c = c; wr.T0 = T0; wr.zcur = zcur; wr.zprev = zprev;
+                    SkTileWrite<T> wr; wr.X = W.X; wr.ox = ox; wr.oy = oy; wr.at = out_run + pre; wr.cap = SKT_CAP; wr.c = c; wr.T0 = T0; wr.k = k; wr.zcur = zcur; wr.zprev = zprev;
                     if (rec.n <= 2) { wr(rec.t0); if (rec.n == 2) wr(rec.t1); }
-                    else sk_step_g([Wp, j](int d) { return Wp->X[(j - d) & 63]; }, j, l, w, k, wr);
+                    else sk_step_g<T, WT>([Xme](int d) { return Xme[-d]; }, j, l, w, k, wr);
                 }
                 out_run += tot;
             }
@@ -501,11 +525,12 @@ __global__ void __launch_bounds__(SKT_WARPS * 32) k_sketch_tiles(const __grid_co
         // ---- the pending minimum of the sequence's last window ----
         if (lane == 0) {
             if (tn > 0 && T0 + tn == sd.len) {
-                const int last = tn - 1;
-                uint64_t mn = MAXV; int mnd = 0;
-                for (int d = w - 1; d >= 0; --d) { const uint64_t v = W.X[(last - d) & 63]; if (v <= mn) mn = v, mnd = d; }
+                const int last = tn - 1, c = nblk - 1;
+                const T *Xl = W.X + 32 + (last - c * 32);
+                T mn = MAXV; int mnd = 0;
+                for (int d = w - 1; d >= 0; --d) { const T v = Xl[-d]; if (v <= mn) mn = v, mnd = d; }
                 if (mn != MAXV) {
-                    SkTileWrite wr; wr.W = &W; wr.ox = ox; wr.oy = oy; wr.at = out_run; wr.cap = SKT_CAP; wr.c = nblk - 1; wr.T0 = T0; wr.zcur = zcur; wr.zprev = zprev;
+                    SkTileWrite<T> wr; wr.X = W.X; wr.ox = ox; wr.oy = oy; wr.at = out_run; wr.cap = SKT_CAP; wr.c = c; wr.T0 = T0; wr.k = k; wr.zcur = zcur; wr.zprev = zprev;
                     wr(last - mnd);
                     ++out_run;
                 }

@@ -172,7 +172,13 @@ static int sketch_tiled(telr_af_ctx *ctx, const SketchArgs &sa, const int32_t *l
     ta.tile_first = ctx->b_tfirst.as<int32_t>(); ta.tmp_x = ctx->b_tmpx.as<uint64_t>(); ta.tmp_y = ctx->b_tmpy.as<uint32_t>();
     ta.tile_cnt = ctx->b_tcnt.as<int32_t>(); ta.tile_off = ctx->b_toff.as<int64_t>(); ta.mz_off = ctx->b_mzoff.as<int64_t>();
     const int grid = std::max(1, std::min((n_tiles + SKT_WARPS - 1) / SKT_WARPS, ctx->sm_count * 8));
-    if (n_tiles > 0) k_sketch_tiles<<<grid, SKT_WARPS * 32, 0, st>>>(ta);
+    if (n_tiles > 0) {
+        const bool k32 = 2 * sa.k <= 30;
+        if (k32 && sa.w == 10) k_sketch_tiles<true, 10><<<grid, SKT_WARPS * 32, 0, st>>>(ta);          // map-ont
+        else if (!k32 && sa.w == 19) k_sketch_tiles<false, 19><<<grid, SKT_WARPS * 32, 0, st>>>(ta);   // map-hifi
+        else if (k32) k_sketch_tiles<true, 0><<<grid, SKT_WARPS * 32, 0, st>>>(ta);
+        else k_sketch_tiles<false, 0><<<grid, SKT_WARPS * 32, 0, st>>>(ta);
+    }
     k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_tcnt.as<int32_t>(), ctx->b_toff.as<int64_t>(), n_tiles, nullptr);
     int64_t n_mz = 0;
     CK(cudaMemcpyAsync(&n_mz, ctx->b_toff.as<int64_t>() + n_tiles, 8, cudaMemcpyDeviceToHost, st));

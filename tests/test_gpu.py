@@ -53,6 +53,44 @@ def test_sketch_matches_oracle(ctx, w, k, hpc, with_n):
         assert (ox == x[off[i]:off[i + 1]]).all() and (oy == y[off[i]:off[i + 1]]).all(), (len(s), w, k, hpc)
 
 
+def test_sketch_two_pass_kernel_agrees(built, monkeypatch):
+    """TELR_SKETCH_TILES=0: the CTA-per-sequence two-pass kernel (the map-pb path) on the uncompressed presets."""
+    monkeypatch.setenv("TELR_SKETCH_TILES", "0")
+    c = lib.Context(0)
+    try:
+        rng = np.random.default_rng(11)
+        seqs = _seqs(rng, 0, True)
+        seq2, nmask, offs, lens = pack_sequences(seqs)
+        x, y, off = c.sketch(seq2, nmask, offs, lens, 10, 15, 0)
+        for i, s in enumerate(seqs):
+            nt4 = np.array([{65: 0, 67: 1, 71: 2, 84: 3}.get(ch, 4) for ch in s], np.uint8)
+            ox, oy = orc.sketch(nt4, 10, 15, 0)
+            assert (ox == x[off[i]:off[i + 1]]).all() and (oy == y[off[i]:off[i + 1]]).all(), len(s)
+    finally:
+        c.close()
+
+
+def test_sketch_tile_boundaries_and_ambiguous_runs(ctx):
+    """The tile kernel's seams: lengths around multiples of 2048, runs of N across a seam, N at both ends, all-N."""
+    rng = np.random.default_rng(23)
+    seqs = []
+    for ln in (2047, 2048, 2049, 2048 + 14, 2048 + 15, 4095, 4096, 4097, 6144 + 25, 3 * 2048):
+        b = np.array(list(b"ACGT"), np.uint8)[rng.integers(0, 4, ln)]
+        seqs.append(bytes(b))
+        b2 = b.copy(); b2[2040:2060] = ord("N"); seqs.append(bytes(b2))          # a run of N across the first seam
+        b3 = b.copy(); b3[0] = b3[-1] = ord("N"); b3[min(2047, ln - 2)] = ord("N"); seqs.append(bytes(b3))
+        b4 = b.copy(); b4[2048 - 24:2048 - 10] = b4[2048 - 38:2048 - 24]; seqs.append(bytes(b4))   # identical k-mers next to the seam
+    seqs.append(b"N" * 5000)
+    seqs.append(b"ACGT" * 1500)          # period-4 tandem: every window holds identical hashes
+    for w, k in ((10, 15), (19, 19), (5, 11), (10, 19)):      # the four kernel instances: (32-bit key, w=10), (64-bit, w=19), and both run-time-w forms
+        seq2, nmask, offs, lens = pack_sequences(seqs)
+        x, y, off = ctx.sketch(seq2, nmask, offs, lens, w, k, 0)
+        for i, s in enumerate(seqs):
+            nt4 = np.array([{65: 0, 67: 1, 71: 2, 84: 3}.get(ch, 4) for ch in s], np.uint8)
+            ox, oy = orc.sketch(nt4, w, k, 0)
+            assert len(ox) == off[i + 1] - off[i] and (ox == x[off[i]:off[i + 1]]).all() and (oy == y[off[i]:off[i + 1]]).all(), (i, len(s), w, k)
+
+
 def test_sketch_empty_batch(ctx):
     x, y, off = ctx.sketch(np.zeros(0, np.uint32), np.zeros(0, np.uint32), np.zeros(0, np.int64), np.zeros(0, np.int32), 10, 15)
     assert len(x) == 0 and off.tolist() == [0]
