@@ -1,13 +1,16 @@
 // k_sketch.cuh — kernel (a): batched (w,k)-minimizer sketching of reads and contig strands.
 //
-// Replaces mm_sketch() (minimap2 sketch.c) reached from the reference at TELR_te.py:505.
-// Reads are consumed from the 2-bit packed batch with 16-byte vector loads (64 bases per lane);
-// contig strands come from the nt4 byte copies made by k_unpack_contigs.  One CTA walks one sequence
-// in tiles of 2048 steps; every step evaluates, from the w+1 hashes around it, exactly the pushes the
-// sequential ring-buffer algorithm performs at that step (first-window special case, "new minimum",
-// "minimum left the window" with its identical-hash flush), so the emitted list is byte-identical to
-// mm_sketch, including around ambiguous bases.  Two passes: COUNT then WRITE into exact CSR offsets.
-// map-pb's homopolymer compression runs as a per-sequence pre-pass (run ends -> steps).
+// Replaces mm_sketch() (minimap2 sketch.c) reached from the reference at TELR_te.py:505.  Every step evaluates, from the
+// w+1 hashes around it, exactly the pushes the sequential ring-buffer algorithm performs at that step (first-window
+// special case, "new minimum", "minimum left the window" with its identical-hash flush: sk_step_g), so the emitted list
+// is byte-identical to mm_sketch, including around ambiguous bases.
+//
+// Two implementations live here:
+//   * k_sketch_tiles (+ k_hpc_compress for map-pb, + k_sketch_compact): the product path — one warp per tile of 2048
+//     steps, single pass, see the block comment above it;
+//   * k_sketch<COUNT/WRITE>: the first-generation kernel (one CTA per sequence, tiles of 2048 steps behind CTA barriers,
+//     a count pass and a write pass into exact CSR offsets, homopolymer compression as a per-sequence pre-pass), kept as
+//     a second implementation behind TELR_SKETCH_TILES=0.
 #pragma once
 #include <cuda_runtime.h>
 #include <type_traits>
@@ -372,6 +375,10 @@ struct SketchTileArgs {
     const int32_t *tile_first;        // [n_seq + 1] first tile of every sequence
     uint64_t *tmp_x; uint32_t *tmp_y; // [n_tiles * SKT_CAP]
     int32_t *tile_cnt;                // [n_tiles]
+    // homopolymer-compressed presets: the step stream made by k_hpc_compress (one step per run / per ambiguous base)
+    uint8_t *hp_code; int32_t *hp_pos;  // [sum of lengths]: code of the step, position of the run's last base
+    const int64_t *hp_off;            // [n_seq + 1] slice of every sequence in hp_code / hp_pos
+    int32_t *hp_n;                    // [n_seq] steps per sequence
     const int64_t *tile_off;          // [n_tiles + 1] (compact pass)
     int64_t *mz_off;                  // [n_seq + 1]   (compact pass)
     uint64_t *mz_x; uint32_t *mz_y;
@@ -386,22 +393,56 @@ struct SkRec {
 // writes the minimizer of local step jj (jj in [c*32 - w, c*32 + 31]) into the tile's slot
 template <class T> struct SkTileWrite {
     const T *X; uint64_t *ox; uint32_t *oy; int at, cap, c, T0, k; uint32_t zcur, zprev;
+    const int32_t *hpos;       // compressed presets: position of every step's last base (nullptr: step = base)
     __device__ __forceinline__ void operator()(int jj)
     {
         if (at < cap) {
             const T x = X[32 + jj - c * 32];
+            const int pos = hpos ? hpos[T0 + jj] : T0 + jj;
             ox[at] = sizeof(T) == 4 ? ((uint64_t)x << 8 | (uint64_t)k) : (uint64_t)x;
-            oy[at] = (uint32_t)(T0 + jj) << 1 | ((((jj >> 5) == c ? zcur : zprev) >> (jj & 31)) & 1u);
+            oy[at] = (uint32_t)pos << 1 | ((((jj >> 5) == c ? zcur : zprev) >> (jj & 31)) & 1u);
         }
         ++at;
     }
 };
 
+// Homopolymer compression (map-pb): one warp per sequence walks it 32 bases at a time; a base ends a run when it is
+// ambiguous, the last one, or differs from its successor; a ballot ranks the run ends and the warp appends (code, position).
+__global__ void __launch_bounds__(256) k_hpc_compress(const __grid_constant__ SketchTileArgs A)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    const int nw = gridDim.x * (blockDim.x >> 5);
+    SketchArgs L; L.seq2 = A.seq2; L.nmask = A.nmask; L.bytes = A.bytes;
+    for (int seq = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); seq < A.n_seq; seq += nw) {
+        const SeqDesc sd = A.seqs[seq];
+        uint8_t *oc = A.hp_code + A.hp_off[seq]; int32_t *op = A.hp_pos + A.hp_off[seq];
+        int done = 0;
+        int cur = lane < sd.len ? sk_load_code(L, sd, lane) : 4;
+        for (int i0 = 0; i0 < sd.len; i0 += 32) {
+            const int i = i0 + lane;
+            const int nxt_blk = sk_load_code(L, sd, i0 + 32 + lane);          // 4 beyond the end
+            int nxt = __shfl_down_sync(FULL, cur, 1);
+            const int first_next = __shfl_sync(FULL, nxt_blk, 0);
+            if (lane == 31) nxt = first_next;
+            const bool e = i < sd.len && (cur == 4 || i == sd.len - 1 || nxt != cur);
+            const unsigned m = __ballot_sync(FULL, e);
+            if (e) { const int at = done + __popc(m & ((1u << lane) - 1)); oc[at] = (uint8_t)cur; op[at] = i; }
+            done += __popc(m);
+            cur = nxt_blk;
+        }
+        if (lane == 0) A.hp_n[seq] = done;
+    }
+}
+
 // K32: 2k <= 30, the ring holds the bare 30-bit hash (the span is the constant k, so the order is the same).
 // WT: compile-time window length of the instance (0 = run-time w).
-template <bool K32, int WT>
+// HPC: the steps are the runs written by k_hpc_compress (tiles are laid out for the uncompressed length, the surplus ones
+// are empty); the span of a k-mer is the distance between run ends, and a k-mer spanning 256 bases or more is dropped.
+template <bool K32, int WT, bool HPC>
 __global__ void __launch_bounds__(SKT_WARPS * 32) k_sketch_tiles(const __grid_constant__ SketchTileArgs A)
 {
+    static_assert(!(K32 && HPC), "compressed k-mers carry their span in the key");
     typedef typename std::conditional<K32, uint32_t, uint64_t>::type T;
     __shared__ SktWarp<T> SW[SKT_WARPS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -415,9 +456,13 @@ __global__ void __launch_bounds__(SKT_WARPS * 32) k_sketch_tiles(const __grid_co
         int lo = 0, hi = A.n_seq;
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (A.tile_first[mid] <= tile) lo = mid; else hi = mid; }
         const int seq = lo;
-        const SeqDesc sd = A.seqs[seq];
+        SeqDesc sd = A.seqs[seq];
+        const int32_t *hpos = nullptr;
+        if (HPC) { sd.kind = 1; sd.off = A.hp_off[seq]; sd.len = A.hp_n[seq]; hpos = A.hp_pos + sd.off; }
+        const uint8_t *bytes = HPC ? A.hp_code : A.bytes;
         const int T0 = (tile - A.tile_first[seq]) * SKT_TILE;
         const int tn = min(SKT_TILE, sd.len - T0);
+        if (HPC && tn <= 0) { if (lane == 0) A.tile_cnt[tile] = 0; continue; }
         // ---- stage packed codes: stream index q <-> sequence position T0 - SKT_LEAD + q ----
         if (sd.kind == 0) {
             for (int m = lane; m < SKT_CW; m += 32) {
@@ -441,7 +486,7 @@ __global__ void __launch_bounds__(SKT_WARPS * 32) k_sketch_tiles(const __grid_co
 #pragma unroll
                     for (int t = 0; t < 16; ++t) {
                         const int i = i0 + t;
-                        const uint32_t c = (i >= 0 && i < sd.len) ? A.bytes[sd.off + i] : 4u;
+                        const uint32_t c = (i >= 0 && i < sd.len) ? bytes[sd.off + i] : 4u;
                         pk |= (c & 3u) << (2 * t);
                         nb |= (c > 3u ? 1u : 0u) << t;
                     }
@@ -495,7 +540,9 @@ __global__ void __launch_bounds__(SKT_WARPS * 32) k_sketch_tiles(const __grid_co
                     r = ((r >> 1) & 0x5555555555555555ULL) | ((r & 0x5555555555555555ULL) << 1);
                     const uint64_t k0 = r >> (64 - 2 * k), k1 = ~val & mask;
                     z = k0 < k1 ? 0 : 1;
-                    X = (T)(mix64_masked(z ? k1 : k0, mask) << 8 | (uint64_t)k);
+                    int sp = k;
+                    if (HPC) { const int jj = T0 + j; sp = hpos[jj] - (jj - k >= 0 ? hpos[jj - k] : -1); }
+                    if (!HPC || sp < 256) X = (T)(mix64_masked(z ? k1 : k0, mask) << 8 | (uint64_t)sp);
                 }
             }
             zprev = zcur; zcur = __ballot_sync(FULL, z);
@@ -514,7 +561,7 @@ __global__ void __launch_bounds__(SKT_WARPS * 32) k_sketch_tiles(const __grid_co
                     tot = __shfl_sync(FULL, x, 31); pre = x - rec.n;
                 }
                 if (rec.n) {
-                    SkTileWrite<T> wr; wr.X = W.X; wr.ox = ox; wr.oy = oy; wr.at = out_run + pre; wr.cap = SKT_CAP; wr.c = c; wr.T0 = T0; wr.k = k; wr.zcur = zcur; wr.zprev = zprev;
+                    SkTileWrite<T> wr; wr.X = W.X; wr.ox = ox; wr.oy = oy; wr.at = out_run + pre; wr.cap = SKT_CAP; wr.c = c; wr.T0 = T0; wr.k = k; wr.zcur = zcur; wr.zprev = zprev; wr.hpos = hpos;
                     if (rec.n <= 2) { wr(rec.t0); if (rec.n == 2) wr(rec.t1); }
                     else sk_step_g<T, WT>([Xme](int d) { return Xme[-d]; }, j, l, w, k, wr);
                 }
@@ -530,7 +577,7 @@ __global__ void __launch_bounds__(SKT_WARPS * 32) k_sketch_tiles(const __grid_co
                 T mn = MAXV; int mnd = 0;
                 for (int d = w - 1; d >= 0; --d) { const T v = Xl[-d]; if (v <= mn) mn = v, mnd = d; }
                 if (mn != MAXV) {
-                    SkTileWrite<T> wr; wr.X = W.X; wr.ox = ox; wr.oy = oy; wr.at = out_run; wr.cap = SKT_CAP; wr.c = c; wr.T0 = T0; wr.k = k; wr.zcur = zcur; wr.zprev = zprev;
+                    SkTileWrite<T> wr; wr.X = W.X; wr.ox = ox; wr.oy = oy; wr.at = out_run; wr.cap = SKT_CAP; wr.c = c; wr.T0 = T0; wr.k = k; wr.zcur = zcur; wr.zprev = zprev; wr.hpos = hpos;
                     wr(last - mnd);
                     ++out_run;
                 }

@@ -59,6 +59,7 @@ struct telr_af_ctx {
     DevBuf b_lrb, b_cboff, b_ctg, b_descs, b_counts, b_mzoff, b_mzx, b_mzy, b_self, b_tabk, b_tabc, b_hpc, b_hpp, b_hpr;
     DevBuf b_pna, b_pread, b_pls, b_paoff, b_prcap, b_proff, b_pnregs, b_pnca, b_anch, b_regs, b_chws, b_alws, b_work;
     DevBuf b_psb, b_psoff, b_pscr, b_pnu, b_pm;
+    DevBuf b_hpoff, b_hpn;                // compressed step stream: slice per sequence, steps per sequence
     DevBuf b_order, b_wflag, b_woff;      // LPT order of the chunk's problems, work-list filter
     DevBuf b_tfirst, b_tcnt, b_toff, b_tmpx, b_tmpy;     // tile sketch: first tile per sequence, per-tile counts/offsets, per-tile slots
     int sketch_tiles = 1;
@@ -172,12 +173,27 @@ static int sketch_tiled(telr_af_ctx *ctx, const SketchArgs &sa, const int32_t *l
     ta.tile_first = ctx->b_tfirst.as<int32_t>(); ta.tmp_x = ctx->b_tmpx.as<uint64_t>(); ta.tmp_y = ctx->b_tmpy.as<uint32_t>();
     ta.tile_cnt = ctx->b_tcnt.as<int32_t>(); ta.tile_off = ctx->b_toff.as<int64_t>(); ta.mz_off = ctx->b_mzoff.as<int64_t>();
     const int grid = std::max(1, std::min((n_tiles + SKT_WARPS - 1) / SKT_WARPS, ctx->sm_count * 8));
+    std::vector<int64_t> hoff;
+    if (sa.hpc && n_seq > 0) {      // map-pb: the step stream of every sequence (runs), at most its length
+        hoff.resize((size_t)n_seq + 1);
+        int64_t acc = 0;
+        for (int i = 0; i < n_seq; ++i) { hoff[i] = acc; acc += lens[i]; }
+        hoff[n_seq] = acc;
+        ENS(ctx->b_hpc, acc + 64); ENS(ctx->b_hpp, (acc + 16) * 4); ENS(ctx->b_hpoff, (size_t)(n_seq + 1) * 8); ENS(ctx->b_hpn, (size_t)(n_seq + 1) * 4);
+        CK(cudaMemcpyAsync(ctx->b_hpoff.p, hoff.data(), (size_t)(n_seq + 1) * 8, cudaMemcpyHostToDevice, st));
+        ta.hp_code = ctx->b_hpc.as<uint8_t>(); ta.hp_pos = ctx->b_hpp.as<int32_t>(); ta.hp_off = ctx->b_hpoff.as<int64_t>(); ta.hp_n = ctx->b_hpn.as<int32_t>();
+        k_hpc_compress<<<std::max(1, std::min((n_seq + 7) / 8, ctx->sm_count * 8)), 256, 0, st>>>(ta);
+    }
     if (n_tiles > 0) {
         const bool k32 = 2 * sa.k <= 30;
-        if (k32 && sa.w == 10) k_sketch_tiles<true, 10><<<grid, SKT_WARPS * 32, 0, st>>>(ta);          // map-ont
-        else if (!k32 && sa.w == 19) k_sketch_tiles<false, 19><<<grid, SKT_WARPS * 32, 0, st>>>(ta);   // map-hifi
-        else if (k32) k_sketch_tiles<true, 0><<<grid, SKT_WARPS * 32, 0, st>>>(ta);
-        else k_sketch_tiles<false, 0><<<grid, SKT_WARPS * 32, 0, st>>>(ta);
+        if (sa.hpc) {
+            if (sa.w == 10) k_sketch_tiles<false, 10, true><<<grid, SKT_WARPS * 32, 0, st>>>(ta);         // map-pb
+            else k_sketch_tiles<false, 0, true><<<grid, SKT_WARPS * 32, 0, st>>>(ta);
+        }
+        else if (k32 && sa.w == 10) k_sketch_tiles<true, 10, false><<<grid, SKT_WARPS * 32, 0, st>>>(ta);          // map-ont
+        else if (!k32 && sa.w == 19) k_sketch_tiles<false, 19, false><<<grid, SKT_WARPS * 32, 0, st>>>(ta);   // map-hifi
+        else if (k32) k_sketch_tiles<true, 0, false><<<grid, SKT_WARPS * 32, 0, st>>>(ta);
+        else k_sketch_tiles<false, 0, false><<<grid, SKT_WARPS * 32, 0, st>>>(ta);
     }
     k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_tcnt.as<int32_t>(), ctx->b_toff.as<int64_t>(), n_tiles, nullptr);
     int64_t n_mz = 0;
@@ -262,7 +278,7 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
     };
     sa.counts = ctx->b_counts.as<int32_t>();
     int64_t n_mz = 0;
-    if (!o.hpc && ctx->sketch_tiles) {
+    if (ctx->sketch_tiles) {
         std::vector<int32_t> lens((size_t)n_seq);
         for (int r = 0; r < n_reads; ++r) lens[r] = hm.read_len[r0 + r];
         for (int l = 0; l < n_loci; ++l) lens[n_reads + l] = lens[n_reads + n_loci + l] = hm.contig_len[l0 + l];
@@ -589,7 +605,7 @@ int telr_af_destroy(telr_af_ctx *ctx)
                      &ctx->b_alws, &ctx->b_work, &ctx->b_blk, &ctx->b_pblkoff, &ctx->b_pblkcnt, &ctx->b_ctr, &ctx->b_alnout, &ctx->b_cigout, &ctx->b_doff,
                      &ctx->b_big, &ctx->b_biglock, &ctx->b_rbytes, &ctx->b_rboff, &ctx->b_alwork, &ctx->b_alctx, &ctx->b_altask, &ctx->b_alres, &ctx->b_alsz, &ctx->b_aloff,
                      &ctx->b_cigs, &ctx->b_pool, &ctx->b_tlist, &ctx->b_rc, &ctx->b_opt, &ctx->b_idxbig, &ctx->b_psb, &ctx->b_psoff, &ctx->b_pscr, &ctx->b_pnu, &ctx->b_pm,
-                     &ctx->b_tfirst, &ctx->b_tcnt, &ctx->b_toff, &ctx->b_tmpx, &ctx->b_tmpy, &ctx->b_order, &ctx->b_wflag, &ctx->b_woff};
+                     &ctx->b_tfirst, &ctx->b_tcnt, &ctx->b_toff, &ctx->b_tmpx, &ctx->b_tmpy, &ctx->b_order, &ctx->b_wflag, &ctx->b_woff, &ctx->b_hpoff, &ctx->b_hpn};
     for (auto *b : all) b->release();
     for (auto &b : ctx->b_in) b.release();
     for (auto &e : ctx->ev) cudaEventDestroy(e);
@@ -713,7 +729,7 @@ int telr_af_sketch(telr_af_ctx *ctx, const uint32_t *seq2, const uint32_t *nmask
     }
     sa.counts = ctx->b_counts.as<int32_t>();
     int64_t n_mz = 0;
-    if (!hpc && ctx->sketch_tiles) {
+    if (ctx->sketch_tiles) {
         int rc = sketch_tiled(ctx, sa, seq_len, &n_mz, []() {});
         if (rc != TELR_OK) return rc;
         CK(cudaMemcpyAsync(mz_off, ctx->b_mzoff.p, (size_t)(n_seq + 1) * 8, cudaMemcpyDeviceToHost, st));

@@ -54,18 +54,19 @@ def test_sketch_matches_oracle(ctx, w, k, hpc, with_n):
 
 
 def test_sketch_two_pass_kernel_agrees(built, monkeypatch):
-    """TELR_SKETCH_TILES=0: the CTA-per-sequence two-pass kernel (the map-pb path) on the uncompressed presets."""
+    """TELR_SKETCH_TILES=0: the first-generation CTA-per-sequence two-pass kernel, kept as a second implementation."""
     monkeypatch.setenv("TELR_SKETCH_TILES", "0")
     c = lib.Context(0)
     try:
         rng = np.random.default_rng(11)
-        seqs = _seqs(rng, 0, True)
-        seq2, nmask, offs, lens = pack_sequences(seqs)
-        x, y, off = c.sketch(seq2, nmask, offs, lens, 10, 15, 0)
-        for i, s in enumerate(seqs):
-            nt4 = np.array([{65: 0, 67: 1, 71: 2, 84: 3}.get(ch, 4) for ch in s], np.uint8)
-            ox, oy = orc.sketch(nt4, 10, 15, 0)
-            assert (ox == x[off[i]:off[i + 1]]).all() and (oy == y[off[i]:off[i + 1]]).all(), len(s)
+        for w, k, hpc in ((10, 15, 0), (10, 19, 1)):
+            seqs = _seqs(rng, hpc, True)
+            seq2, nmask, offs, lens = pack_sequences(seqs)
+            x, y, off = c.sketch(seq2, nmask, offs, lens, w, k, hpc)
+            for i, s in enumerate(seqs):
+                nt4 = np.array([{65: 0, 67: 1, 71: 2, 84: 3}.get(ch, 4) for ch in s], np.uint8)
+                ox, oy = orc.sketch(nt4, w, k, hpc)
+                assert (ox == x[off[i]:off[i + 1]]).all() and (oy == y[off[i]:off[i + 1]]).all(), (len(s), hpc)
     finally:
         c.close()
 
@@ -82,13 +83,15 @@ def test_sketch_tile_boundaries_and_ambiguous_runs(ctx):
         b4 = b.copy(); b4[2048 - 24:2048 - 10] = b4[2048 - 38:2048 - 24]; seqs.append(bytes(b4))   # identical k-mers next to the seam
     seqs.append(b"N" * 5000)
     seqs.append(b"ACGT" * 1500)          # period-4 tandem: every window holds identical hashes
-    for w, k in ((10, 15), (19, 19), (5, 11), (10, 19)):      # the four kernel instances: (32-bit key, w=10), (64-bit, w=19), and both run-time-w forms
+    seqs.append(b"A" * 300 + b"C" * 300 + b"ACGTTGCA" * 300)     # runs longer than a byte-sized span when compressed
+    # every kernel instance: (32-bit key, w=10), (64-bit, w=19), both run-time-w forms, and the homopolymer-compressed forms
+    for w, k, hpc in ((10, 15, 0), (19, 19, 0), (5, 11, 0), (10, 19, 0), (10, 19, 1), (5, 11, 1)):
         seq2, nmask, offs, lens = pack_sequences(seqs)
-        x, y, off = ctx.sketch(seq2, nmask, offs, lens, w, k, 0)
+        x, y, off = ctx.sketch(seq2, nmask, offs, lens, w, k, hpc)
         for i, s in enumerate(seqs):
             nt4 = np.array([{65: 0, 67: 1, 71: 2, 84: 3}.get(ch, 4) for ch in s], np.uint8)
-            ox, oy = orc.sketch(nt4, w, k, 0)
-            assert len(ox) == off[i + 1] - off[i] and (ox == x[off[i]:off[i + 1]]).all() and (oy == y[off[i]:off[i + 1]]).all(), (i, len(s), w, k)
+            ox, oy = orc.sketch(nt4, w, k, hpc)
+            assert len(ox) == off[i + 1] - off[i] and (ox == x[off[i]:off[i + 1]]).all() and (oy == y[off[i]:off[i + 1]]).all(), (i, len(s), w, k, hpc)
 
 
 def test_sketch_empty_batch(ctx):
