@@ -111,7 +111,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "candidate loci/sec (stage-4 AF)", "value": v, "unit": "loci/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int8/int32 (integer DP), fp32 chain penalty, fp64 AF", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample_loci_per_step": sample, "preset": "map-ont"},
+            "config": {"workload": WORKLOAD, "sample_loci_per_step": sample, "preset": synth.CONFIGS[WORKLOAD]["preset"]},
             "cpu_baseline": {"value": v, "unit": "loci/s", "cores": cores, "kind": "port",
                              "sample": f"{sample} loci of {WORKLOAD} per step; CPU restatement of minimap2 2.22 + samtools depth + TELR AF, not the real binaries",
                              "gcups": cells / dt / 1e9},
@@ -286,7 +286,7 @@ def main():
             "metric": "candidate loci/sec (stage-4 AF) and read-vs-contig GCUPS", "value": value, "unit": "loci/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int8/int32 (integer DP), fp32 chain penalty, fp64 AF", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "loci_per_gpu": per_gpu, "preset": "map-ont", "reads": int(batch.n_reads), "read_bases": int(batch.read_len.astype(np.int64).sum()),
+            "config": {"workload": WORKLOAD, "loci_per_gpu": per_gpu, "preset": synth.CONFIGS[WORKLOAD]["preset"], "reads": int(batch.n_reads), "read_bases": int(batch.read_len.astype(np.int64).sum()),
                        "l2": "inputs larger than L2 (packed batch %.0f MB per GPU)" % (h2d / 1e6), "sharding": "by locus, no collective", "streams_per_gpu": K},
             "gcups": gcups, "dp_cells_per_step": cells[0] // max(args.steps, 1),
             "stage_ms_per_step": {k: stage_ms.get(i, 0.0) / args.steps for i, k in enumerate(["sketch", "seed_chain", "plan", "align_dp", "", "", "depth_af"]) if k},
