@@ -251,9 +251,13 @@ def test_dp_fuzz_matches_oracle(ctx, seed):
 
 
 @pytest.mark.parametrize("cfg,n,kw", [("ont_3k_50x", 10, {}), ("clr_3k_40x", 6, {}), ("hifi_3k_40x", 6, {}),
-                                      ("poly_10k_200x", 2, dict(depth=60)), ("ont_3k_50x", 4, dict(p_n=0.002))])
+                                      ("poly_10k_200x", 2, dict(depth=60)), ("ont_3k_50x", 4, dict(p_n=0.002)),
+                                      # wider samples of the configurations BASELINE.json names (rare paths: z-drop re-runs,
+                                      # inversion probes, long joins, two-pass fills), config 5 at its full 200x depth
+                                      ("ont_30k_30x", 40, {}), ("clr_3k_40x", 20, dict(first=100)), ("poly_10k_200x", 3, {})])
 def test_full_pipeline_matches_oracle(ctx, cfg, n, kw):
-    b = synth.generate(cfg, 0, n, **kw)
+    kw = dict(kw)
+    b = synth.generate(cfg, kw.pop("first", 0), n, **kw)
     r = ctx.run(b, want_depth=True, want_aln=True)
     ro = orc.af_run(b, threads=0)
     util.assert_same_results(r, ro)
