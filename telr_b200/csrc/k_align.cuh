@@ -343,6 +343,9 @@ __device__ void extd2_traceback(const DpTask &T, DpRes &R, const uint8_t *p, uin
 __device__ __forceinline__ int warp_extd2(const Opt &o, const DpTask &T, DpRes &R, DpScratch &S, unsigned long long *cells_acc, int32_t *err)
 {
     if (S.vsm && vec_ok(o, T.qlen, T.tlen, T.w) && vec_dir_bytes(T.qlen, T.tlen, T.w) <= S.dir_cap) {
+#if TELR_LANE_EXT
+        if (T.tlen <= 32 && !(T.flag & KSW_APPROX_MAX)) { if (warp_extd2_lane(o, T, R, S.dir, cells_acc)) return 1; } else
+#endif
         if (warp_extd2_vec(o, T, R, *S.vsm, S.stab, S.dir, cells_acc)) return 1;
     }
     warp_extd2_impl<false>(o, T, R, S, cells_acc, err);      // ambiguous bases or a band wider than the window: state arrays in global memory
