@@ -5,7 +5,7 @@ set -e
 N=${1:-296}
 CFG=${2:-ont_3k_50x}
 mkdir -p telr_b200/_variants
-nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared -DTELR_CENSUS_BUILD=1 \
+nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared -DTELR_CENSUS_BUILD=1 $CENSUS_EXTRA \
      -o telr_b200/_variants/census.so telr_b200/csrc/telr_af.cu
 cp telr_b200/_telr_af.so telr_b200/_variants/product.so
 cp telr_b200/_variants/census.so telr_b200/_telr_af.so
