@@ -456,8 +456,8 @@ __global__ void __launch_bounds__(128) k_al_init(const __grid_constant__ AlignAr
 // them z-drops run as one systolic stream (warp_fill_stream); their direction bytes share the warp's traceback buffer.
 // Returns the number of fills computed (0: the task has to take the single-fill path).  Speculative results that the
 // coroutine does not ask for afterwards are simply dropped.
-__device__ int fill_batch_run(const Opt &o, const AlnCtx &c, const DpTask &task, FillJob *jobs, int max_jobs, uint8_t *dir, int64_t dir_cap, uint32_t *bnd,
-                              uint32_t *bnd_smem, int bnd_smem_pairs)
+__device__ int fill_batch_run(const Opt &o, const FillLut &L, const AlnCtx &c, const DpTask &task, FillJob *jobs, int max_jobs, uint8_t *dir, int64_t dir_cap, uint32_t *bnd,
+                              uint32_t *bnd_smem, int bnd_smem_pairs, uint8_t *b2j)
 {
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
@@ -473,6 +473,7 @@ __device__ int fill_batch_run(const Opt &o, const AlnCtx &c, const DpTask &task,
             const int64_t need = ((int64_t)pk[k].qlen * fill_stride(pk[k].tlen) + 15) & ~(int64_t)15;
             if (off + need > dir_cap) break;
             const int np = (pk[k].qlen + 1) >> 1;
+            if (blk + ((pk[k].tlen + 7) >> 3) > FB_MAX_BLOCKS) break;
             if (k > 0 && (np > np0 + (np0 >> 1) || np < np0 - (np0 >> 1))) break;      // a round lasts as long as the tallest fill: keep heights within 50 %
             jobs[k].q = pk[k].q; jobs[k].t = pk[k].t; jobs[k].qlen = pk[k].qlen; jobs[k].tlen = pk[k].tlen;
             jobs[k].dir = dir + off; jobs[k].blk0 = blk; jobs[k].score = 0;
@@ -493,7 +494,14 @@ __device__ int fill_batch_run(const Opt &o, const AlnCtx &c, const DpTask &task,
     if (n > 0) {
         int np_max = 32;
         for (int k = 0; k < n; ++k) np_max = max(np_max, (jobs[k].qlen + 1) >> 1);
-        warp_fill_stream(o, jobs, n, np_max <= bnd_smem_pairs ? bnd_smem : bnd);     // the hand-over column lives in the idle DP window when it fits
+        const int total = jobs[n - 1].blk0 + ((jobs[n - 1].tlen + 7) >> 3);
+        for (int g = lane; g < total; g += 32) {          // block -> fill
+            int f2 = 0;
+            for (int f = 1; f < n; ++f) if (jobs[f].blk0 <= g) f2 = f;
+            b2j[g] = (uint8_t)f2;
+        }
+        __syncwarp();
+        warp_fill_stream(o, L, jobs, n, np_max <= bnd_smem_pairs ? bnd_smem : bnd, b2j);     // the hand-over column lives in the idle DP window when it fits
     }
     return n;
 }
@@ -502,7 +510,7 @@ __device__ int fill_batch_run(const Opt &o, const AlnCtx &c, const DpTask &task,
 // coroutine + DP + traceback for one problem per warp (persistent warps, dynamic queue, no global barriers).
 // The coroutine state lives in shared memory while the warp owns the problem and is written back for k_al_finish.
 #if TELR_FILL_STREAM
-struct AlWarpSmem { AlnCtx c; DpTask task; DpRes res; int more; FillJob jobs[FB_MAX]; int n_jobs, job_next; };
+struct AlWarpSmem { AlnCtx c; DpTask task; DpRes res; int more; FillJob jobs[FB_MAX]; int n_jobs, job_next; uint8_t b2j[FB_MAX_BLOCKS]; };
 #else
 struct AlWarpSmem { AlnCtx c; DpTask task; DpRes res; int more; };
 #endif
@@ -529,6 +537,10 @@ __global__ void __launch_bounds__(AL_THREADS, AL_BLOCKS_PER_SM) k_al_fused(const
     uint8_t *own_dir = base;
     S.s_state = nullptr; S.s_H = nullptr; S.vsm = A.use_vec ? &DS[wid] : nullptr; S.stab = stab;
     vec_fill_stab(stab, o);
+#if TELR_FILL_STREAM
+    __shared__ FillLut flut;
+    fill_lut_init(flut, o);
+#endif
     for (;;) {
         int wi = 0;
         if (lane == 0) wi = (int)atomicAdd(&A.rc[2], 1ULL);
@@ -567,7 +579,7 @@ __global__ void __launch_bounds__(AL_THREADS, AL_BLOCKS_PER_SM) k_al_fused(const
                 if (hit < 0) {
                     long long tb0 = 0;
                     if (AL_CENSUS(A)) tb0 = clock64();
-                    const int n = fill_batch_run(o, W.c, W.task, W.jobs, A.fill_batch, own_dir, A.dir_cap, S.bnd, reinterpret_cast<uint32_t *>(DS[wid].st), (int)(sizeof(DS[wid].st) / 12));
+                    const int n = fill_batch_run(o, flut, W.c, W.task, W.jobs, A.fill_batch, own_dir, A.dir_cap, S.bnd, reinterpret_cast<uint32_t *>(DS[wid].st), (int)(sizeof(DS[wid].st) / 12), W.b2j);
                     if (lane == 0) { W.n_jobs = n; W.job_next = 0; }
                     if (AL_CENSUS(A) && lane == 0) {
                         atomicAdd(&A.rc[90], (unsigned long long)n); atomicAdd(&A.rc[91], 1ULL); atomicAdd(&A.rc[93], (unsigned long long)(clock64() - tb0));

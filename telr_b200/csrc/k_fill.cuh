@@ -244,13 +244,32 @@ __device__ bool warp_fill_fast(const Opt &o, const DpTask &T, DpRes &R, uint8_t 
 // the same fill one round earlier (bnd[]); every other block is fed by shuffle.  Cells, direction bytes and scores are
 // those of warp_fill_fwd.
 constexpr int FB_MAX = 8;
+constexpr int FB_MAX_BLOCKS = 512;      // blocks per batch (block -> fill table): fills of up to 512 target columns batch 8 deep
 struct FillJob {
     const uint8_t *q, *t;
     uint8_t *dir;
     int32_t qlen, tlen, blk0, score;       // blk0: index of the fill's first block in the stream; score: out
 };
+// boundary values of ksw_extd2's first row / first column, tabulated once per CTA (they only vary up to r = LT + 1)
+constexpr int FB_LUT = 64;
+struct FillLut { uint32_t top[FB_LUT], left[FB_LUT / 2]; int lt; };      // top[r] = pk2(0, f(r)); left[m] = pk2(f(2m), f(2m+1))
+__device__ __forceinline__ void fill_lut_init(FillLut &L, const Opt &o)
+{
+    int q = o.q, e = o.e, q2 = o.q2, e2 = o.e2;
+    if (q2 + e2 < q + e) { int t = q; q = q2; q2 = t; t = e; e = e2; e2 = t; }
+    const int qe = q + e;
+    int LT = e != e2 ? (q2 - q) / (e - e2) - 1 : 0;
+    if (q2 + e2 + LT * e2 > q + e + LT * e) ++LT;
+    const int LD = LT * (e - e2) - (q2 - q) - e2;
+#define BNDF(r) ((r) == 0 ? -qe : (r) < LT ? -e : (r) == LT ? LD : -e2)
+    for (int r = threadIdx.x; r < FB_LUT; r += blockDim.x) L.top[r] = pk2(0, BNDF(r));
+    for (int m = threadIdx.x; m < FB_LUT / 2; m += blockDim.x) L.left[m] = pk2(BNDF(2 * m), BNDF(2 * m + 1));
+#undef BNDF
+    if (threadIdx.x == 0) L.lt = LT;
+    __syncthreads();
+}
 
-__device__ void warp_fill_stream(const Opt &o, FillJob *jobs, int n_jobs, uint32_t *bnd)
+__device__ void warp_fill_stream(const Opt &o, const FillLut &L, FillJob *jobs, int n_jobs, uint32_t *bnd, const uint8_t *b2j)
 {
     constexpr int FC = 8;
     const int lane = threadIdx.x & 31;
@@ -258,12 +277,10 @@ __device__ void warp_fill_stream(const Opt &o, FillJob *jobs, int n_jobs, uint32
     int q = o.q, e = o.e, q2 = o.q2, e2 = o.e2;
     if (q2 + e2 < q + e) { int t = q; q = q2; q2 = t; t = e; e = e2; e2 = t; }
     const int qe = q + e, qe2 = q2 + e2;
-    int LT = e != e2 ? (q2 - q) / (e - e2) - 1 : 0;
-    if (q2 + e2 + LT * e2 > q + e + LT * e) ++LT;
-    const int LD = LT * (e - e2) - (q2 - q) - e2;
-#define BNDF(r) ((r) == 0 ? -qe : (r) < LT ? -e : (r) == LT ? LD : -e2)
+    const int LT = L.lt;
     const uint32_t NE1 = pk1(-e), NQE1 = pk1(-qe), NE2 = pk1(-e2), NQE2 = pk1(-qe2);
     const uint32_t QM1 = pk1(q - 1), Q2M1 = pk1(q2 - 1);
+    const uint32_t UY0 = pk2(0, -qe), UY20 = pk2(0, -qe2), UU0 = pk2(0, -e2);
     const uint32_t TS_MIS = 0x01010101u * ((uint32_t)(-o.b) & 0xffu), TS_FLIP = ((uint32_t)o.a ^ (uint32_t)(-o.b)) & 0xffu;
     // stream geometry
     int total_blocks = 0, NP = 32;
@@ -291,11 +308,13 @@ __device__ void warp_fill_stream(const Opt &o, FillJob *jobs, int n_jobs, uint32
             // ---- finish the block that just ended: u of the fill's last query row (score = boundary + sum of u) ----
             if (live) {
                 int usum = 0;
+                const int nv = tlen - t0;       // valid columns of the block (>= 1)
+                if (qlen & 1) {
 #pragma unroll
-                for (int k = 0; k < FC; ++k) {
-                    if (t0 + k >= tlen) continue;
-                    if (qlen & 1) usum += k == 0 ? lo16(Ufirst) : lo16(Uu[k - 1]);
-                    else usum += hi16(Uu[k]);
+                    for (int k = 0; k < FC; ++k) usum += k < nv ? (k == 0 ? lo16(Ufirst) : lo16(Uu[k - 1])) : 0;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < FC; ++k) usum += k < nv ? hi16(Uu[k]) : 0;
                 }
                 atomicAdd(&jobs[jf].score, usum);
             }
@@ -304,19 +323,24 @@ __device__ void warp_fill_stream(const Opt &o, FillJob *jobs, int n_jobs, uint32
             const int g = (round << 5) + lane;
             live = round < rounds && g < total_blocks;
             if (live) {
-                jf = 0;
-                for (int f = 1; f < n_jobs; ++f) if (jobs[f].blk0 <= g) jf = f;
+                jf = b2j[g];
                 const FillJob J = jobs[jf];
                 const int b = g - J.blk0;
                 Q = J.q; qlen = J.qlen; tlen = J.tlen; npairs = (qlen + 1) >> 1; stride = fill_stride(tlen);
                 t0 = b * FC; first = b == 0; dcol = J.dir + t0;
                 feeds = t0 + FC < tlen;           // a right neighbour of the same fill exists
+                const uint8_t *tp = J.t + t0;
+                const int nv = tlen - t0;
 #pragma unroll
                 for (int k = 0; k < FC; ++k) {
-                    const int tc = t0 + k < tlen ? J.t[t0 + k] : 0;
+                    const int tc = k < nv ? tp[k] : 0;
                     TS[k] = TS_MIS ^ (TS_FLIP << (8 * tc));
-                    const int r = t0 + k;
-                    Uu[k] = pk2(0, BNDF(r)); Uy[k] = pk2(0, -qe); Uy2[k] = pk2(0, -qe2);
+                    Uy[k] = UY0; Uy2[k] = UY20;
+                    Uu[k] = UU0;
+                }
+                if (t0 <= LT) {                   // the top boundary varies only over the first LT + 1 columns
+#pragma unroll
+                    for (int k = 0; k < FC; ++k) Uu[k] = L.top[t0 + k];
                 }
             }
         }
@@ -327,7 +351,7 @@ __device__ void warp_fill_stream(const Opt &o, FillJob *jobs, int n_jobs, uint32
         }
         const bool active = live && m >= 0 && m < npairs;
         if (active) {
-            if (first) { inV = pk2(BNDF(2 * m), BNDF(2 * m + 1)); inX = NQE1; inX2 = NQE2; }
+            if (first) { inV = 2 * m > LT ? NE2 : L.left[m]; inX = NQE1; inX2 = NQE2; }
             else if (lane == 0) { inV = bnd[3 * m]; inX = bnd[3 * m + 1]; inX2 = bnd[3 * m + 2]; }
             const int j = 2 * m;
             const uint32_t q0 = Q[j], q1 = j + 1 < qlen ? Q[j + 1] : 0;
@@ -376,7 +400,7 @@ __device__ void warp_fill_stream(const Opt &o, FillJob *jobs, int n_jobs, uint32
                 pu = nu; py = ny; py2 = ny2; Lv = nv; Lx = nx; Lx2 = nx2;
             }
             outV = __byte_perm(kV, Lv, 0x7610); outX = __byte_perm(kX, Lx, 0x7610); outX2 = __byte_perm(kX2, Lx2, 0x7610);
-            if (t0 < stride) {
+            {
                 uint8_t *r0 = dcol + (int64_t)j * stride, *r1 = r0 + stride;
                 const uint32_t w00 = __byte_perm(W[0], W[1], 0x6420), w01 = __byte_perm(W[2], W[3], 0x6420);
                 const uint32_t w10 = __byte_perm(__byte_perm(W[0], W[1], 0x0753), W[2], 0x5210), w11 = __byte_perm(__byte_perm(W[2], W[3], 0x0753), W[4], 0x5210);
@@ -387,10 +411,10 @@ __device__ void warp_fill_stream(const Opt &o, FillJob *jobs, int n_jobs, uint32
         }
         __syncwarp();       // bnd[] written by lane 31 is read by lane 0 one round later
     }
-#undef BNDF
     __syncwarp();
     if (lane < n_jobs) {
         const int ql = jobs[lane].qlen;
+        const int LD = LT * (e - e2) - (q2 - q) - e2;
         jobs[lane].score += bnd_sum(ql, qe, e, e2, LT, LD);
     }
     __syncwarp();
