@@ -512,8 +512,25 @@ static int run_device(telr_af_ctx *ctx, const telr_af_batch *db, const HostMeta 
     stats->dp_cells = stats->n_dp_tasks = stats->n_anchors = stats->n_minimizers = stats->n_aln_blocks = 0;
     stats->n_aln = stats->n_cigar = 0;
     for (int i = 0; i < 8; ++i) stats->ms_stage[i] = 0.f;
-    // chunk loci by read bases
-    const int64_t budget = ctx->chunk_bases > 0 ? ctx->chunk_bases : (int64_t)384 << 20;
+    // Chunk loci by read bases.  Large chunks amortise the tails of the latency-bound chaining kernels and of the persistent
+    // alignment kernel (config 2 on one B200: 384 Mbase chunks 1924 loci/s, 768 Mbase 1973, one 1.8 Gbase chunk 2007), so the
+    // default takes what the device holds: about 32 B of workspace per read base (sketch slots, minimizers, anchors, chaining
+    // scratch, read bytes) on top of ~28 GB of per-warp alignment scratch, capped at 2 Gbase; equal-sized chunks.
+    int64_t budget = ctx->chunk_bases;
+    if (budget <= 0) {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { total_b = (size_t)64 << 30; cudaGetLastError(); }
+        double usable = 0.8 * (double)total_b;
+        if (ctx->ws_limit > 0 && (double)ctx->ws_limit < usable) usable = (double)ctx->ws_limit;
+        budget = (int64_t)((usable - 28.0 * (1 << 30)) / 32.0);
+        budget = std::max<int64_t>((int64_t)128 << 20, std::min<int64_t>(budget, (int64_t)2048 << 20));
+    }
+    {
+        int64_t total = 0;
+        for (int r = 0; r < (int)hm.read_len.size(); ++r) total += hm.read_len[r];
+        const int64_t n_chunks = std::max<int64_t>(1, (total + budget - 1) / budget);
+        budget = (total + n_chunks - 1) / n_chunks + 1;
+    }
     int l0 = 0;
     while (l0 < n_loci) {
         int l1 = l0; int64_t acc = 0;

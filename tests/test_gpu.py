@@ -364,6 +364,23 @@ def test_chunking_and_rerun_are_identical(built, monkeypatch):
     c1.close(); c2.close()
 
 
+def test_full_size_one_chunk_equals_many(built, monkeypatch):
+    """BASELINE.json configs[1] at its full size (3000 loci, 1.8 Gbase): the default single 1.8-Gbase chunk and 384-Mbase chunks
+    give the same coverage integers, AF values and DP cell count (guards the 64-bit offsets of the large-chunk layout)."""
+    b = synth.generate("ont_3k_50x", 0, 3000)
+    c1 = lib.Context(0)
+    r1 = c1.run(b)
+    c1.close()
+    monkeypatch.setenv("TELR_CHUNK_MBASES", "384")
+    c2 = lib.Context(0)
+    r2 = c2.run(b)
+    c2.close()
+    assert (r1.cov2x == r2.cov2x).all() and r1.c.dp_cells == r2.c.dp_cells and r1.c.n_anchors == r2.c.n_anchors
+    assert np.array_equal(r1.af, r2.af, equal_nan=True)
+    ok = ~np.isnan(r1.af)
+    assert ok.mean() > 0.8 and np.abs(np.minimum(r1.af[ok], 1) - b.meta["truth_af"][ok]).mean() < 0.12
+
+
 def test_get_af_dropin(built, tmp_path):
     """The stage API on files, GPU backend, against the same host code fed by the oracle."""
     b = synth.generate("ont_3k_50x", 0, 4, depth=10)
