@@ -514,32 +514,32 @@ static int run_device(telr_af_ctx *ctx, const telr_af_batch *db, const HostMeta 
     for (int i = 0; i < 8; ++i) stats->ms_stage[i] = 0.f;
     // Chunk loci by read bases.  Large chunks amortise the tails of the latency-bound chaining kernels and of the persistent
     // alignment kernel (config 2 on one B200: 384 Mbase chunks 1924 loci/s, 768 Mbase 1973, one 1.8 Gbase chunk 2007), so the
-    // default takes what the device holds: about 32 B of workspace per read base (sketch slots, minimizers, anchors, chaining
-    // scratch, read bytes) on top of ~28 GB of per-warp alignment scratch, capped at 2 Gbase; equal-sized chunks.
+    // default takes what the device holds: about 80 B of workspace per read base (CIGAR arenas sized for the worst case ~45,
+    // sketch slots 12, alignment blocks 4, minimizers, anchors, chaining scratch, read bytes) on top of ~28 GB of per-warp
+    // alignment scratch, capped at 2 Gbase; equal-sized chunks.  On a 180 GB B200 that is 1.4 Gbase (measured peak 84 GB).
     int64_t budget = ctx->chunk_bases;
     if (budget <= 0) {
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { total_b = (size_t)64 << 30; cudaGetLastError(); }
         double usable = 0.8 * (double)total_b;
         if (ctx->ws_limit > 0 && (double)ctx->ws_limit < usable) usable = (double)ctx->ws_limit;
-        budget = (int64_t)((usable - 28.0 * (1 << 30)) / 32.0);
+        budget = (int64_t)((usable - 28.0 * (1 << 30)) / 80.0);
         budget = std::max<int64_t>((int64_t)128 << 20, std::min<int64_t>(budget, (int64_t)2048 << 20));
     }
-    {
-        int64_t total = 0;
-        for (int r = 0; r < (int)hm.read_len.size(); ++r) total += hm.read_len[r];
-        const int64_t n_chunks = std::max<int64_t>(1, (total + budget - 1) / budget);
-        budget = (total + n_chunks - 1) / n_chunks + 1;
-    }
-    int l0 = 0;
-    while (l0 < n_loci) {
-        int l1 = l0; int64_t acc = 0;
-        while (l1 < n_loci) {
-            int64_t lb = 0;
-            for (int r = hm.lrb[l1]; r < hm.lrb[l1 + 1]; ++r) lb += hm.read_len[r];
-            if (l1 > l0 && acc + lb > budget) break;
-            acc += lb; ++l1;
+    int64_t total = 0;
+    for (int r = 0; r < (int)hm.read_len.size(); ++r) total += hm.read_len[r];
+    const int64_t n_chunks = std::max<int64_t>(1, (total + budget - 1) / budget);
+    int l0 = 0; int64_t cum = 0;
+    for (int64_t ci = 0; l0 < n_loci; ++ci) {
+        // chunk ci ends at the first locus that brings the running total to (ci + 1) / n_chunks of the batch (a single locus
+        // larger than the budget still forms its own chunk)
+        const int64_t target = ci + 1 >= n_chunks ? total : (total * (ci + 1) + n_chunks - 1) / n_chunks;
+        int l1 = l0;
+        while (l1 < n_loci && (l1 == l0 || cum < target)) {
+            for (int r = hm.lrb[l1]; r < hm.lrb[l1 + 1]; ++r) cum += hm.read_len[r];
+            ++l1;
         }
+        while (ci + 1 >= n_chunks && l1 < n_loci) ++l1;      // loci without reads at the end of the batch
         int rc = run_chunk(ctx, o, db, hm, l0, l1, dres, depth_off.data(), stats, d_aln_out, aln_cap, d_cig_out, cig_cap);
         if (rc != TELR_OK) return rc;
         l0 = l1;
