@@ -48,7 +48,7 @@ struct telr_af_ctx {
     cudaStream_t stream = nullptr;
     int last_cuda = 0;
     long long launches = 0;
-    size_t ws_limit = 0;
+    size_t ws_limit = 0, total_mem = (size_t)64 << 30;
     int depth_mode = 1;
     int use_fast = 1, use_vec = 1, census = 0;
     int64_t chunk_bases = 0;
@@ -519,9 +519,7 @@ static int run_device(telr_af_ctx *ctx, const telr_af_batch *db, const HostMeta 
     // alignment scratch, capped at 2 Gbase; equal-sized chunks.  On a 180 GB B200 that is 1.4 Gbase (measured peak 84 GB).
     int64_t budget = ctx->chunk_bases;
     if (budget <= 0) {
-        size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { total_b = (size_t)64 << 30; cudaGetLastError(); }
-        double usable = 0.8 * (double)total_b;
+        double usable = 0.8 * (double)ctx->total_mem;
         if (ctx->ws_limit > 0 && (double)ctx->ws_limit < usable) usable = (double)ctx->ws_limit;
         budget = (int64_t)((usable - 28.0 * (1 << 30)) / 80.0);
         budget = std::max<int64_t>((int64_t)128 << 20, std::min<int64_t>(budget, (int64_t)2048 << 20));
@@ -588,7 +586,7 @@ int telr_af_create(telr_af_ctx **out, int device, size_t workspace_bytes)
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return TELR_ENODEV;
     if (prop.major != 10) { fprintf(stderr, "[telr_af] device %d is sm_%d%d; this library is built for sm_100a only\n", device, prop.major, prop.minor); return TELR_ENODEV; }
     telr_af_ctx *ctx = new telr_af_ctx();
-    ctx->device = device; ctx->sm_count = prop.multiProcessorCount; ctx->ws_limit = workspace_bytes;
+    ctx->device = device; ctx->sm_count = prop.multiProcessorCount; ctx->ws_limit = workspace_bytes; ctx->total_mem = prop.totalGlobalMem;
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return TELR_ECUDA; }
     for (auto &e : ctx->ev) cudaEventCreate(&e);
     const char *dm = getenv("TELR_DEPTH_MODE");
