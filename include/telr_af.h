@@ -154,6 +154,12 @@ int telr_af_version(void);
 long long telr_af_launch_count(const telr_af_ctx *ctx);  /* kernels launched by this ctx so far */
 void *telr_af_stream(const telr_af_ctx *ctx);            /* the ctx's cudaStream_t (for event timing by the caller) */
 
+/* Host helper (no device needed): how telr_af_run cuts a batch into chunks of loci for a budget of read bases per chunk
+ * (the reference processes one locus per minimap2 process, TELR_te.py:640-647; here a chunk is what one pass of the device
+ * pipeline holds).  cuts[0..n] = first locus of every chunk and n_loci; returns n (>= 0) or a negative TELR_E* code. */
+int telr_af_plan_chunks(const int32_t *read_len, const int32_t *locus_read_begin, int32_t n_loci, int64_t budget_bases,
+                        int32_t *cuts, int32_t cap);
+
 /* Host helper: ASCII -> 2-bit + N mask (one sequence; dst offsets in bases, multiple of 64). */
 int telr_pack_seq(const char *ascii, int32_t len, int64_t dst_off, uint32_t *seq2, uint32_t *nmask);
 /* Host helper: X31 string hash of a read name (minimap2 __ac_X31_hash_string) */

@@ -208,6 +208,32 @@ static int sketch_tiled(telr_af_ctx *ctx, const SketchArgs &sa, const int32_t *l
     return TELR_OK;
 }
 
+// Cuts a batch into chunks of loci of about equal read bases: n = ceil(total / budget) chunks, chunk i ends at the first locus
+// that brings the running total to (i + 1) / n of the batch.  A locus is never split, so a single locus above the budget forms
+// its own chunk; trailing loci without reads join the last chunk.  cuts = [0, ..., n_loci].
+static void plan_chunks(const int32_t *read_len, const int32_t *lrb, int n_loci, int64_t budget, std::vector<int32_t> &cuts)
+{
+    cuts.clear(); cuts.push_back(0);
+    if (n_loci <= 0) return;
+    if (budget < 1) budget = 1;
+    int64_t total = 0;
+    for (int r = lrb[0]; r < lrb[n_loci]; ++r) total += read_len[r];
+    const int64_t n_chunks = std::max<int64_t>(1, (total + budget - 1) / budget);
+    int l0 = 0; int64_t cum = 0;
+    for (int64_t ci = 0; l0 < n_loci; ++ci) {
+        const bool last = ci + 1 >= n_chunks;
+        const int64_t target = last ? total : (total * (ci + 1) + n_chunks - 1) / n_chunks;
+        int l1 = l0;
+        while (l1 < n_loci && (l1 == l0 || cum < target)) {
+            for (int r = lrb[l1]; r < lrb[l1 + 1]; ++r) cum += read_len[r];
+            ++l1;
+        }
+        if (last && cum >= total) l1 = n_loci;
+        cuts.push_back(l1);
+        l0 = l1;
+    }
+}
+
 struct HostMeta {       // host copies of the small per-read / per-locus arrays
     std::vector<int32_t> read_len, lrb, contig_len;
 };
@@ -524,23 +550,12 @@ static int run_device(telr_af_ctx *ctx, const telr_af_batch *db, const HostMeta 
         budget = (int64_t)((usable - 28.0 * (1 << 30)) / 80.0);
         budget = std::max<int64_t>((int64_t)128 << 20, std::min<int64_t>(budget, (int64_t)2048 << 20));
     }
-    int64_t total = 0;
-    for (int r = 0; r < (int)hm.read_len.size(); ++r) total += hm.read_len[r];
-    const int64_t n_chunks = std::max<int64_t>(1, (total + budget - 1) / budget);
-    int l0 = 0; int64_t cum = 0;
-    for (int64_t ci = 0; l0 < n_loci; ++ci) {
-        // chunk ci ends at the first locus that brings the running total to (ci + 1) / n_chunks of the batch (a single locus
-        // larger than the budget still forms its own chunk)
-        const int64_t target = ci + 1 >= n_chunks ? total : (total * (ci + 1) + n_chunks - 1) / n_chunks;
-        int l1 = l0;
-        while (l1 < n_loci && (l1 == l0 || cum < target)) {
-            for (int r = hm.lrb[l1]; r < hm.lrb[l1 + 1]; ++r) cum += hm.read_len[r];
-            ++l1;
-        }
-        while (ci + 1 >= n_chunks && l1 < n_loci) ++l1;      // loci without reads at the end of the batch
+    std::vector<int32_t> cuts;
+    plan_chunks(hm.read_len.data(), hm.lrb.data(), n_loci, budget, cuts);
+    for (size_t ci = 0; ci + 1 < cuts.size(); ++ci) {
+        const int l0 = cuts[ci], l1 = cuts[ci + 1];
         int rc = run_chunk(ctx, o, db, hm, l0, l1, dres, depth_off.data(), stats, d_aln_out, aln_cap, d_cig_out, cig_cap);
         if (rc != TELR_OK) return rc;
-        l0 = l1;
     }
     return TELR_OK;
 }
@@ -936,6 +951,16 @@ extern "C" int telr_af_dp(telr_af_ctx *ctx, int32_t preset, int32_t n_tasks, con
 }
 
 // ---- host helpers ------------------------------------------------------------------------------
+extern "C" int telr_af_plan_chunks(const int32_t *read_len, const int32_t *locus_read_begin, int32_t n_loci, int64_t budget_bases, int32_t *cuts, int32_t cap)
+{
+    if (!read_len || !locus_read_begin || n_loci < 0 || !cuts) return TELR_EINVAL;
+    std::vector<int32_t> c;
+    plan_chunks(read_len, locus_read_begin, n_loci, budget_bases, c);
+    if ((int)c.size() > cap) return TELR_ECAP;
+    for (size_t i = 0; i < c.size(); ++i) cuts[i] = c[i];
+    return (int)c.size() - 1;
+}
+
 extern "C" int telr_pack_seq(const char *s, int32_t len, int64_t off, uint32_t *seq2, uint32_t *nmask)
 {
     if ((off & 63) || len < 0) return TELR_EINVAL;

@@ -44,7 +44,7 @@ assert DPTASK_DTYPE.itemsize == C.sizeof(DpTask) and DPOUT_DTYPE.itemsize == C.s
 
 EXPORTS = ["telr_af_create", "telr_af_destroy", "telr_af_run", "telr_af_run_device", "telr_af_sketch", "telr_af_depth_af",
            "telr_af_dp", "telr_af_strerror", "telr_af_last_cuda", "telr_af_version", "telr_af_launch_count", "telr_af_stream",
-           "telr_pack_seq", "telr_name_hash"]
+           "telr_pack_seq", "telr_name_hash", "telr_af_plan_chunks"]
 
 
 def lib():
@@ -74,11 +74,25 @@ def lib():
         L.telr_af_stream.restype = C.c_void_p
         L.telr_af_stream.argtypes = [C.c_void_p]
         L.telr_name_hash.argtypes = [C.c_char_p]
+        L.telr_af_plan_chunks.restype = C.c_int
+        L.telr_af_plan_chunks.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32]
         for fn in ("telr_af_create", "telr_af_destroy", "telr_af_run", "telr_af_run_device", "telr_af_sketch",
                    "telr_af_depth_af", "telr_af_dp", "telr_af_last_cuda", "telr_af_version", "telr_pack_seq"):
             getattr(L, fn).restype = C.c_int
         _LIB = L
     return _LIB
+
+
+def plan_chunks(read_len, locus_read_begin, budget_bases):
+    """Chunks of loci telr_af_run processes together for a budget of read bases per chunk: [0, ..., n_loci] (host only)."""
+    read_len = np.ascontiguousarray(read_len, np.int32)
+    lrb = np.ascontiguousarray(locus_read_begin, np.int32)
+    n_loci = len(lrb) - 1
+    cuts = np.zeros(n_loci + 2, np.int32)
+    n = lib().telr_af_plan_chunks(read_len.ctypes.data, lrb.ctypes.data, n_loci, int(budget_bases), cuts.ctypes.data, len(cuts))
+    if n < 0:
+        raise TelrError(n, "telr_af_plan_chunks")
+    return cuts[: n + 1]
 
 
 class Result:

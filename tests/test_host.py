@@ -24,6 +24,33 @@ def test_cabi_exports_every_declared_symbol(built):
     assert lib.lib().telr_af_strerror(-4).decode().startswith("no sm_100")
 
 
+def test_chunk_planner(built):
+    """How telr_af_run cuts a batch into chunks of loci (host logic, no device): whole loci, equal shares, edge cases."""
+    rng = np.random.default_rng(5)
+    n_loci = 200
+    per = rng.integers(0, 80, n_loci)
+    per[[3, 50, 199]] = 0                                           # loci without reads, also at the very end
+    lrb = np.concatenate([[0], np.cumsum(per)]).astype(np.int32)
+    read_len = rng.integers(1000, 30000, int(lrb[-1])).astype(np.int32)
+    locus_bases = np.add.reduceat(np.concatenate([read_len, [0]]).astype(np.int64), lrb[:-1]) * (per > 0)
+    total = int(read_len.astype(np.int64).sum())
+    assert int(locus_bases.sum()) == total
+    for budget in (1, 10_000, 3_000_000, total // 3, total // 2 + 1, total, 10 * total):
+        cuts = lib.plan_chunks(read_len, lrb, budget)
+        assert cuts[0] == 0 and cuts[-1] == n_loci and (np.diff(cuts) >= 1).all()
+        n_want = max(1, -(-total // budget))
+        sizes = np.array([int(locus_bases[a:b].sum()) for a, b in zip(cuts[:-1], cuts[1:])])
+        if budget >= int(locus_bases.max()):
+            assert len(sizes) <= n_want + 1
+            assert sizes.max() <= total / n_want + locus_bases.max()     # a chunk overshoots its share by less than one locus
+        if budget >= total:
+            assert len(sizes) == 1
+    # a single locus above the budget is one chunk; an empty batch has no chunks
+    assert lib.plan_chunks(np.array([5000, 7000], np.int32), np.array([0, 2], np.int32), 100).tolist() == [0, 1]
+    assert lib.plan_chunks(np.zeros(0, np.int32), np.array([0], np.int32), 100).tolist() == [0]
+    assert lib.plan_chunks(np.zeros(0, np.int32), np.array([0, 0, 0], np.int32), 100).tolist() == [0, 2]
+
+
 def test_no_device_fails_loudly(built):
     import torch
     if torch.cuda.is_available():
