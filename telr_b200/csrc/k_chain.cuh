@@ -199,14 +199,21 @@ __device__ void chain_dp_warp(const Opt &o, int n, const Anchor *a, ChainScratch
             const bool is_new = valid && sc > pm;
             const bool is_skip = valid && !is_new && tj;
             // skip counter: N_k = max(N_{k-1} + d_k, 0)  ==  P_k - min(-N_0, min_{m<=k} P_m)
-            int P = is_skip ? 1 : (is_new ? -1 : 0);
+            // prefix sum of (+1 skip, -1 new) from two ballots; the prefix minimum is only needed lane by lane when the
+            // counter can pass the limit inside this block of 32 candidates, otherwise one warp reduction gives the carry
+            const unsigned skm = __ballot_sync(FULL, is_skip), nwm = __ballot_sync(FULL, is_new), le = (2u << lane) - 1u;
+            const int P = __popc(skm & le) - __popc(nwm & le);
+            int N; unsigned brk = 0;
+            if (n_skip + __popc(skm) <= o.max_chain_skip) {
+                const int Mall = __reduce_min_sync(FULL, P);
+                N = P - (Mall < -n_skip ? Mall : -n_skip);      // exact on lane 31, which is the only lane that uses it
+            } else {
+                int M = P;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(FULL, P, d); if (lane >= d) P += y; }
-            int M = P;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(FULL, M, d); if (lane >= d) M = M < y ? M : y; }
-            const int N = P - (M < -n_skip ? M : -n_skip);
-            const unsigned brk = __ballot_sync(FULL, is_skip && N > o.max_chain_skip);
+                for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(FULL, M, d); if (lane >= d) M = M < y ? M : y; }
+                N = P - (M < -n_skip ? M : -n_skip);
+                brk = __ballot_sync(FULL, is_skip && N > o.max_chain_skip);
+            }
             const int bl = brk ? __ffs(brk) - 1 : 32;
             const unsigned newm = __ballot_sync(FULL, is_new) & (bl >= 32 ? FULL : ((1u << bl) - 1));
             if (newm) {
@@ -358,14 +365,19 @@ __device__ void chain_rmq_warp(const Opt &o, int n, const Anchor *a, ChainScratc
                     const int32_t pm = exc > max_f ? exc : max_f;
                     const bool is_new = valid && scj > pm;
                     const bool is_skip = valid && !is_new && tj;
-                    int P = is_skip ? 1 : (is_new ? -1 : 0);
+                    const unsigned skm = __ballot_sync(FULL, is_skip), nwm = __ballot_sync(FULL, is_new), le = (2u << lane) - 1u;
+                    const int P = __popc(skm & le) - __popc(nwm & le);
+                    int N; unsigned brk = 0;
+                    if (n_skip + __popc(skm) <= o.max_chain_skip) {
+                        const int Mall = __reduce_min_sync(FULL, P);
+                        N = P - (Mall < -n_skip ? Mall : -n_skip);
+                    } else {
+                        int M = P;
 #pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) { int yv = __shfl_up_sync(FULL, P, d); if (lane >= d) P += yv; }
-                    int M = P;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) { int yv = __shfl_up_sync(FULL, M, d); if (lane >= d) M = M < yv ? M : yv; }
-                    const int N = P - (M < -n_skip ? M : -n_skip);
-                    const unsigned brk = __ballot_sync(FULL, is_skip && N > o.max_chain_skip);
+                        for (int d = 1; d < 32; d <<= 1) { int yv = __shfl_up_sync(FULL, M, d); if (lane >= d) M = M < yv ? M : yv; }
+                        N = P - (M < -n_skip ? M : -n_skip);
+                        brk = __ballot_sync(FULL, is_skip && N > o.max_chain_skip);
+                    }
                     const int bl = brk ? __ffs(brk) - 1 : 32;
                     const unsigned newm = __ballot_sync(FULL, is_new) & (bl >= 32 ? FULL : ((1u << bl) - 1));
                     if (newm) {
