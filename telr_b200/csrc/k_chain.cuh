@@ -64,6 +64,7 @@ struct ChainArgs {
     int32_t *prob_nu, *prob_m;      // chains found; anchors to re-chain (0 = no re-chaining)
     int32_t n_prob;
     IdxBig *idx_big;                // [gridDim.x] global-memory index slices for long contigs
+    uint8_t *locus_bad;             // [n_loci] set when a contig exceeds IDX_BIG_MAXMZ minimizers: the locus is reported as unsupported (-4), the batch goes on
 };
 
 __device__ __forceinline__ void prob_carve(const ChainArgs &A, int p, int n_a, ChainScratch &cs, HitScratch &hs, int *cap_regs)
@@ -507,7 +508,7 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const __grid_constant__ Ch
         const int64_t cb = A.mz_off[cseq];
         const int n_c = (int)(A.mz_off[cseq + 1] - cb);
         if (n_c > IDX_BIG_MAXMZ || (n_c > IDX_MAXMZ && !A.idx_big)) {
-            if (tid == 0) atomicOr(A.err, 16);
+            if (tid == 0) { if (A.locus_bad) A.locus_bad[l] = 1; else atomicOr(A.err, 16); }
             for (int r = tid; r < nr; r += CH_THREADS) {
                 int pidx = 2 * rb + strand * nr + r;
                 if (A.mode == 0) A.prob_na[pidx] = 0, A.prob_read[pidx] = rb + r, A.prob_ls[pidx] = item;

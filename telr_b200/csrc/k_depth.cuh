@@ -27,6 +27,9 @@ struct DepthArgs {
     int32_t *depth; const int64_t *depth_off;     // optional output: fw then rc per locus
     int32_t *cov2x; double *af;
     int32_t max_len;
+    // contigs whose depth row does not fit the shared-memory row (smem_ints entries) use a per-CTA row in global memory
+    int32_t smem_ints; int32_t *grow; int64_t grow_stride;
+    const uint8_t *locus_bad;     // optional: 1 = locus outside the implemented scope (reported as -4 / NaN, never fails the batch)
 };
 
 __device__ int dp_block_sum(int v, int *ws)
@@ -89,7 +92,7 @@ __device__ __forceinline__ bool af_ratio(int te2, int fl2, double *r)
 
 __global__ void __launch_bounds__(DP_THREADS) k_depth_af(const __grid_constant__ DepthArgs A)
 {
-    extern __shared__ __align__(16) int32_t sd[];      // [max_len + 2]
+    extern __shared__ __align__(16) int32_t sd_smem[];      // [min(max_len + 2, smem_ints)]
     __shared__ int ws[40];
     __shared__ int cov[8];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -97,11 +100,12 @@ __global__ void __launch_bounds__(DP_THREADS) k_depth_af(const __grid_constant__
         const int L = A.contig_len[l];
         const int ts = A.te_start[l], te = A.te_end[l];
         const int rb = A.locus_read_begin[l], nr = A.locus_read_begin[l + 1] - rb;
-        if (L <= 0) {
-            if (tid < 8) A.cov2x[(int64_t)l * 8 + tid] = -2;
+        if (L <= 0 || (A.locus_bad && A.locus_bad[l])) {
+            if (tid < 8) A.cov2x[(int64_t)l * 8 + tid] = L <= 0 ? -2 : -4;
             if (tid == 0) A.af[l] = nan("");
             continue;
         }
+        int32_t *sd = (L + 2 <= A.smem_ints) ? sd_smem : A.grow + (int64_t)blockIdx.x * A.grow_stride;
         for (int strand = 0; strand < 2; ++strand) {
             for (int i = tid; i <= L; i += DP_THREADS) sd[i] = 0;
             __syncthreads();

@@ -10,6 +10,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #include "../../include/telr_af.h"
@@ -45,7 +47,7 @@ struct DevBuf {
 
 struct telr_af_ctx {
     int device = 0, sm_count = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;      // copy_stream: host->device upload of the packed bases, chunk by chunk, under the kernels of earlier chunks
     int last_cuda = 0;
     long long launches = 0;
     size_t ws_limit = 0, total_mem = (size_t)64 << 30;
@@ -67,7 +69,7 @@ struct telr_af_ctx {
     int al_blocks = AL_BLOCKS_PER_SM;    // resident k_al_fused CTAs per SM this context asks for (fewer leaves room for a second context's kernels)
     DevBuf b_rbytes, b_rboff, b_alwork, b_alctx, b_altask, b_alres, b_alsz, b_aloff, b_cigs, b_pool, b_tlist, b_rc, b_opt, b_idxbig;
     int64_t pool_cap = (int64_t)6144 << 20;
-    DevBuf b_blk, b_pblkoff, b_pblkcnt, b_ctr, b_alnout, b_cigout, b_doff, b_big, b_biglock;
+    DevBuf b_blk, b_pblkoff, b_pblkcnt, b_ctr, b_alnout, b_cigout, b_doff, b_big, b_biglock, b_grow, b_lbad;
     int n_big = 8; int64_t big_cap = (int64_t)208 << 20;
     cudaEvent_t ev[10];
 };
@@ -183,27 +185,27 @@ static int sketch_tiled(telr_af_ctx *ctx, const SketchArgs &sa, const int32_t *l
         ENS(ctx->b_hpc, acc + 64); ENS(ctx->b_hpp, (acc + 16) * 4); ENS(ctx->b_hpoff, (size_t)(n_seq + 1) * 8); ENS(ctx->b_hpn, (size_t)(n_seq + 1) * 4);
         CK(cudaMemcpyAsync(ctx->b_hpoff.p, hoff.data(), (size_t)(n_seq + 1) * 8, cudaMemcpyHostToDevice, st));
         ta.hp_code = ctx->b_hpc.as<uint8_t>(); ta.hp_pos = ctx->b_hpp.as<int32_t>(); ta.hp_off = ctx->b_hpoff.as<int64_t>(); ta.hp_n = ctx->b_hpn.as<int32_t>();
-        k_hpc_compress<<<std::max(1, std::min((n_seq + 7) / 8, ctx->sm_count * 8)), 256, 0, st>>>(ta);
+        { ++ctx->launches; k_hpc_compress<<<std::max(1, std::min((n_seq + 7) / 8, ctx->sm_count * 8)), 256, 0, st>>>(ta); }
     }
     if (n_tiles > 0) {
         const bool k32 = 2 * sa.k <= 30;
         if (sa.hpc) {
-            if (sa.w == 10) k_sketch_tiles<false, 10, true><<<grid, SKT_WARPS * 32, 0, st>>>(ta);         // map-pb
-            else k_sketch_tiles<false, 0, true><<<grid, SKT_WARPS * 32, 0, st>>>(ta);
+            if (sa.w == 10) { ++ctx->launches; k_sketch_tiles<false, 10, true><<<grid, SKT_WARPS * 32, 0, st>>>(ta); }         // map-pb
+            else { ++ctx->launches; k_sketch_tiles<false, 0, true><<<grid, SKT_WARPS * 32, 0, st>>>(ta); }
         }
-        else if (k32 && sa.w == 10) k_sketch_tiles<true, 10, false><<<grid, SKT_WARPS * 32, 0, st>>>(ta);          // map-ont
-        else if (!k32 && sa.w == 19) k_sketch_tiles<false, 19, false><<<grid, SKT_WARPS * 32, 0, st>>>(ta);   // map-hifi
-        else if (k32) k_sketch_tiles<true, 0, false><<<grid, SKT_WARPS * 32, 0, st>>>(ta);
-        else k_sketch_tiles<false, 0, false><<<grid, SKT_WARPS * 32, 0, st>>>(ta);
+        else if (k32 && sa.w == 10) { ++ctx->launches; k_sketch_tiles<true, 10, false><<<grid, SKT_WARPS * 32, 0, st>>>(ta); }          // map-ont
+        else if (!k32 && sa.w == 19) { ++ctx->launches; k_sketch_tiles<false, 19, false><<<grid, SKT_WARPS * 32, 0, st>>>(ta); }   // map-hifi
+        else if (k32) { ++ctx->launches; k_sketch_tiles<true, 0, false><<<grid, SKT_WARPS * 32, 0, st>>>(ta); }
+        else { ++ctx->launches; k_sketch_tiles<false, 0, false><<<grid, SKT_WARPS * 32, 0, st>>>(ta); }
     }
-    k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_tcnt.as<int32_t>(), ctx->b_toff.as<int64_t>(), n_tiles, nullptr);
+    { ++ctx->launches; k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_tcnt.as<int32_t>(), ctx->b_toff.as<int64_t>(), n_tiles, nullptr); }
     int64_t n_mz = 0;
     CK(cudaMemcpyAsync(&n_mz, ctx->b_toff.as<int64_t>() + n_tiles, 8, cudaMemcpyDeviceToHost, st));
     host_overlap();
     CK(cudaStreamSynchronize(st));     // tf[] must outlive its upload; n_mz sizes the CSR arrays
     ENS(ctx->b_mzx, (n_mz + 1) * 8); ENS(ctx->b_mzy, (n_mz + 1) * 4);
     ta.mz_x = ctx->b_mzx.as<uint64_t>(); ta.mz_y = ctx->b_mzy.as<uint32_t>();
-    k_sketch_compact<<<std::max(1, std::min((n_tiles + 7) / 8, ctx->sm_count * 8)), 256, 0, st>>>(ta);
+    { ++ctx->launches; k_sketch_compact<<<std::max(1, std::min((n_tiles + 7) / 8, ctx->sm_count * 8)), 256, 0, st>>>(ta); }
     *n_mz_out = n_mz;
     return TELR_OK;
 }
@@ -232,6 +234,27 @@ static void plan_chunks(const int32_t *read_len, const int32_t *lrb, int n_loci,
         cuts.push_back(l1);
         l0 = l1;
     }
+}
+
+// Launches k_depth_af: the depth row of a contig strand lives in shared memory when it fits (216 KB = 55 296 positions),
+// otherwise in a per-CTA row of global memory, so that any contig length is served (the reference runs samtools on any contig).
+static int launch_depth(telr_af_ctx *ctx, DepthArgs &da, int n_loci, int max_len)
+{
+    const int cap_ints = 54 * 1024;
+    const int want = max_len + 8;
+    da.smem_ints = want < cap_ints ? want : cap_ints;
+    int grid = std::max(1, std::min(n_loci, ctx->sm_count * 4));
+    da.grow = nullptr; da.grow_stride = 0;
+    if (want > cap_ints) {
+        grid = std::max(1, std::min(n_loci, ctx->sm_count));
+        da.grow_stride = ((int64_t)want + 63) & ~63LL;
+        ENS(ctx->b_grow, (size_t)da.grow_stride * grid * 4);
+        da.grow = ctx->b_grow.as<int32_t>();
+    }
+    const size_t dp_smem = (size_t)da.smem_ints * 4;
+    CK(cudaFuncSetAttribute(k_depth_af, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dp_smem));
+    { ++ctx->launches; k_depth_af<<<grid, DP_THREADS, dp_smem, ctx->stream>>>(da); }
+    return TELR_OK;
 }
 
 struct HostMeta {       // host copies of the small per-read / per-locus arrays
@@ -274,10 +297,39 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
     const int64_t *read_off = db->read_off + r0; const int32_t *read_len = db->read_len + r0; const uint32_t *read_hash = db->read_hash + r0;
     const int64_t *contig_off = db->contig_off + l0; const int32_t *contig_len = db->contig_len + l0;
 
+    // ---- (e)+(f) depth, medians, AF (also the whole pipeline of a chunk without reads: zero coverage everywhere) ----
+    auto run_depth = [&]() -> int {
+        DepthArgs da; memset(&da, 0, sizeof(da));
+        da.n_loci = n_loci; da.mode = ctx->depth_mode; da.contig_len = contig_len; da.te_start = db->te_start + l0; da.te_end = db->te_end + l0;
+        da.locus_read_begin = ctx->b_lrb.as<int32_t>(); da.prob_blk_off = ctx->b_pblkoff.as<int64_t>(); da.prob_blk_cnt = ctx->b_pblkcnt.as<int32_t>();
+        da.blocks = ctx->b_blk.as<int2>(); da.flank_len = db->flank_len; da.flank_off = db->flank_off; da.te_len = db->te_len; da.te_off = db->te_off;
+        da.cov2x = dres->cov2x + (int64_t)l0 * 8; da.af = dres->af + l0; da.max_len = max_tlen;
+        if (dres->depth) {
+            std::vector<int64_t> doff(n_loci + 1);
+            for (int l = 0; l < n_loci; ++l) doff[l] = h_depth_off[l0 + l];
+            ENS(ctx->b_doff, (n_loci + 1) * 8);
+            CK(cudaMemcpyAsync(ctx->b_doff.p, doff.data(), (size_t)n_loci * 8, cudaMemcpyHostToDevice, st));
+            CK(cudaStreamSynchronize(st));
+            da.depth = dres->depth; da.depth_off = ctx->b_doff.as<int64_t>();
+        }
+        da.locus_bad = ctx->b_lbad.as<uint8_t>();
+        return launch_depth(ctx, da, n_loci, max_tlen);
+    };
+    ENS(ctx->b_lbad, (size_t)n_loci + 64);
+    CK(cudaMemsetAsync(ctx->b_lbad.p, 0, (size_t)n_loci + 64, st));
+    if (n_reads == 0) {     // nothing to align: every window has depth 0 (the reference writes 0 coverages and freq None)
+        ENS(ctx->b_pblkoff, 64); ENS(ctx->b_pblkcnt, 64); ENS(ctx->b_blk, 64);
+        int rc = run_depth();
+        if (rc != TELR_OK) return rc;
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        return TELR_OK;
+    }
+
     CK(cudaEventRecord(ctx->ev[0], st));
-    k_unpack_contigs<<<std::min(n_loci, sm * 8), 256, 0, st>>>(db->seq2, db->nmask, n_loci, contig_off, contig_len, ctx->b_cboff.as<int64_t>(), ctx->b_ctg.as<uint8_t>());
+    { ++ctx->launches; k_unpack_contigs<<<std::min(n_loci, sm * 8), 256, 0, st>>>(db->seq2, db->nmask, n_loci, contig_off, contig_len, ctx->b_cboff.as<int64_t>(), ctx->b_ctg.as<uint8_t>()); }
     ENS(ctx->b_descs, (size_t)n_seq * sizeof(SeqDesc)); ENS(ctx->b_counts, (size_t)(n_seq + 1) * 4); ENS(ctx->b_mzoff, (size_t)(n_seq + 2) * 8);
-    k_build_descs<<<(n_seq + 255) / 256, 256, 0, st>>>(n_reads, n_loci, read_off, read_len, ctx->b_cboff.as<int64_t>(), contig_len, ctx->b_descs.as<SeqDesc>());
+    { ++ctx->launches; k_build_descs<<<(n_seq + 255) / 256, 256, 0, st>>>(n_reads, n_loci, read_off, read_len, ctx->b_cboff.as<int64_t>(), contig_len, ctx->b_descs.as<SeqDesc>()); }
     // ---- (a) sketch ----
     SketchArgs sa; memset(&sa, 0, sizeof(sa));
     sa.seq2 = db->seq2; sa.nmask = db->nmask; sa.bytes = ctx->b_ctg.as<uint8_t>(); sa.seqs = ctx->b_descs.as<SeqDesc>();
@@ -313,14 +365,14 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
         if (rc != TELR_OK) return rc;
         ENS(ctx->b_self, (n_mz + 1) * 2);
     } else {
-        k_sketch<false><<<sk_grid, SK_THREADS, 0, st>>>(sa);
-        k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_counts.as<int32_t>(), ctx->b_mzoff.as<int64_t>(), n_seq, nullptr);
+        { ++ctx->launches; k_sketch<false><<<sk_grid, SK_THREADS, 0, st>>>(sa); }
+        { ++ctx->launches; k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_counts.as<int32_t>(), ctx->b_mzoff.as<int64_t>(), n_seq, nullptr); }
         CK(cudaMemcpyAsync(&n_mz, ctx->b_mzoff.as<int64_t>() + n_seq, 8, cudaMemcpyDeviceToHost, st));
         make_order();
         CK(cudaStreamSynchronize(st));
         ENS(ctx->b_mzx, (n_mz + 1) * 8); ENS(ctx->b_mzy, (n_mz + 1) * 4); ENS(ctx->b_self, (n_mz + 1) * 2);
         sa.offs = ctx->b_mzoff.as<int64_t>(); sa.mz_x = ctx->b_mzx.as<uint64_t>(); sa.mz_y = ctx->b_mzy.as<uint32_t>();
-        k_sketch<true><<<sk_grid, SK_THREADS, 0, st>>>(sa);
+        { ++ctx->launches; k_sketch<true><<<sk_grid, SK_THREADS, 0, st>>>(sa); }
     }
     CK(cudaEventRecord(ctx->ev[1], st));
     ENS(ctx->b_order, (size_t)(n_prob + 1) * 4);
@@ -331,8 +383,8 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
         int grid = std::min(n_reads, sm * 4);
         if (grid < 1) grid = 1;
         ENS(ctx->b_tabk, tab * grid * 8); ENS(ctx->b_tabc, tab * grid * 4);
-        k_self_count<<<grid, 256, 0, st>>>(n_reads, ctx->b_mzoff.as<int64_t>(), ctx->b_mzx.as<uint64_t>(), ctx->b_self.as<uint16_t>(),
-                                           ctx->b_tabk.as<uint64_t>(), ctx->b_tabc.as<uint32_t>(), tab);
+        { ++ctx->launches; k_self_count<<<grid, 256, 0, st>>>(n_reads, ctx->b_mzoff.as<int64_t>(), ctx->b_mzx.as<uint64_t>(), ctx->b_self.as<uint16_t>(),
+                                           ctx->b_tabk.as<uint64_t>(), ctx->b_tabc.as<uint32_t>(), tab); }
     }
     // ---- (b)+(c) index, seeds, chains ----
     ENS(ctx->b_pna, (size_t)(n_prob + 1) * 4); ENS(ctx->b_pread, (size_t)(n_prob + 1) * 4); ENS(ctx->b_pls, (size_t)(n_prob + 1) * 4);
@@ -350,14 +402,15 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
     const int ch_grid = std::min(2 * n_loci, sm);
     ENS(ctx->b_idxbig, sizeof(IdxBig) * (size_t)ch_grid);
     ca.idx_big = ctx->b_idxbig.as<IdxBig>();
+    ca.locus_bad = ctx->b_lbad.as<uint8_t>();
     const size_t ch_smem = sizeof(IdxSmem);
     CK(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch_smem));
-    k_chain<<<ch_grid, CH_THREADS, ch_smem, st>>>(ca);
-    k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_pna.as<int32_t>(), ctx->b_paoff.as<int64_t>(), n_prob, ctr + C_MAXNA);
+    { ++ctx->launches; k_chain<<<ch_grid, CH_THREADS, ch_smem, st>>>(ca); }
+    { ++ctx->launches; k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_pna.as<int32_t>(), ctx->b_paoff.as<int64_t>(), n_prob, ctr + C_MAXNA); }
     ENS(ctx->b_psb, (size_t)(n_prob + 1) * 4); ENS(ctx->b_psoff, (size_t)(n_prob + 2) * 8); ENS(ctx->b_pnu, (size_t)(n_prob + 1) * 4); ENS(ctx->b_pm, (size_t)(n_prob + 1) * 4);
-    k_reg_caps<<<(n_prob + 255) / 256, 256, 0, st>>>(n_prob, ctx->b_pna.as<int32_t>(), ctx->b_prcap.as<int32_t>(), ctx->b_psb.as<int32_t>());
-    k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_prcap.as<int32_t>(), ctx->b_proff.as<int64_t>(), n_prob, nullptr);
-    k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_psb.as<int32_t>(), ctx->b_psoff.as<int64_t>(), n_prob, nullptr);
+    { ++ctx->launches; k_reg_caps<<<(n_prob + 255) / 256, 256, 0, st>>>(n_prob, ctx->b_pna.as<int32_t>(), ctx->b_prcap.as<int32_t>(), ctx->b_psb.as<int32_t>()); }
+    { ++ctx->launches; k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_prcap.as<int32_t>(), ctx->b_proff.as<int64_t>(), n_prob, nullptr); }
+    { ++ctx->launches; k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_psb.as<int32_t>(), ctx->b_psoff.as<int64_t>(), n_prob, nullptr); }
     int64_t tot_na = 0, tot_rcap = 0, max_na = 0, tot_scr = 0;
     CK(cudaMemcpyAsync(&tot_na, ctx->b_paoff.as<int64_t>() + n_prob, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&tot_rcap, ctx->b_proff.as<int64_t>() + n_prob, 8, cudaMemcpyDeviceToHost, st));
@@ -381,23 +434,23 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
     ca.warp_scratch = ctx->b_chws.as<uint8_t>(); ca.warp_scratch_stride = ch_stride; ca.max_na = (int)max_na;
     ca.prob_scratch = ctx->b_pscr.as<uint8_t>(); ca.prob_soff = ctx->b_psoff.as<int64_t>();
     ca.prob_nu = ctx->b_pnu.as<int32_t>(); ca.prob_m = ctx->b_pm.as<int32_t>(); ca.n_prob = n_prob;
-    k_chain<<<ch_grid, CH_THREADS, ch_smem, st>>>(ca);
+    { ++ctx->launches; k_chain<<<ch_grid, CH_THREADS, ch_smem, st>>>(ca); }
     {
         const int tpb = tp_blocks<TP_CHAIN>(n_prob, 128), wg = std::max(1, std::min((n_prob + 7) / 8, sm * 8));
-        k_chain_sort<<<tpb, 128, 0, st>>>(ca);
-        k_chain_dp<<<wg, 256, 0, st>>>(ca);
-        k_chain_bt<<<tpb, 128, 0, st>>>(ca);
-        k_chain_rmq<<<wg, 256, 0, st>>>(ca);
-        k_chain_regs<<<tpb, 128, 0, st>>>(ca);
+        { ++ctx->launches; k_chain_sort<<<tpb, 128, 0, st>>>(ca); }
+        { ++ctx->launches; k_chain_dp<<<wg, 256, 0, st>>>(ca); }
+        { ++ctx->launches; k_chain_bt<<<tpb, 128, 0, st>>>(ca); }
+        { ++ctx->launches; k_chain_rmq<<<wg, 256, 0, st>>>(ca); }
+        { ++ctx->launches; k_chain_regs<<<tpb, 128, 0, st>>>(ca); }
     }
     CK(cudaEventRecord(ctx->ev[2], st));
     // ---- (d) alignment ----
     ENS(ctx->b_work, (size_t)(n_prob + 1) * 4);
     ENS(ctx->b_wflag, (size_t)(n_prob + 1) * 4); ENS(ctx->b_woff, (size_t)(n_prob + 2) * 8);
-    k_work_flags<<<(n_prob + 255) / 256, 256, 0, st>>>(n_prob, ctx->b_order.as<int32_t>(), ctx->b_pnregs.as<int32_t>(), ctx->b_wflag.as<int32_t>());
-    k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_wflag.as<int32_t>(), ctx->b_woff.as<int64_t>(), n_prob, nullptr);
-    k_work_scatter<<<(n_prob + 255) / 256, 256, 0, st>>>(n_prob, ctx->b_order.as<int32_t>(), ctx->b_wflag.as<int32_t>(), ctx->b_woff.as<int64_t>(),
-                                                         ctx->b_work.as<int32_t>(), ctr + C_NWORK);
+    { ++ctx->launches; k_work_flags<<<(n_prob + 255) / 256, 256, 0, st>>>(n_prob, ctx->b_order.as<int32_t>(), ctx->b_pnregs.as<int32_t>(), ctx->b_wflag.as<int32_t>()); }
+    { ++ctx->launches; k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_wflag.as<int32_t>(), ctx->b_woff.as<int64_t>(), n_prob, nullptr); }
+    { ++ctx->launches; k_work_scatter<<<(n_prob + 255) / 256, 256, 0, st>>>(n_prob, ctx->b_order.as<int32_t>(), ctx->b_wflag.as<int32_t>(), ctx->b_woff.as<int64_t>(),
+                                                         ctx->b_work.as<int32_t>(), ctr + C_NWORK); }
     int64_t n_work64 = 0;
     CK(cudaMemcpyAsync(&n_work64, ctr + C_NWORK, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -425,7 +478,7 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
         rbo[n_reads] = acc;
         ENS(ctx->b_rboff, (size_t)(n_reads + 1) * 8); ENS(ctx->b_rbytes, acc + 64);
         CK(cudaMemcpyAsync(ctx->b_rboff.p, rbo.data(), (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
-        k_unpack_reads<<<std::max(1, std::min(n_reads, sm * 16)), 128, 0, st>>>(n_reads, db->seq2, db->nmask, read_off, read_len, ctx->b_rboff.as<int64_t>(), ctx->b_rbytes.as<uint8_t>());
+        { ++ctx->launches; k_unpack_reads<<<std::max(1, std::min(n_reads, sm * 16)), 128, 0, st>>>(n_reads, db->seq2, db->nmask, read_off, read_len, ctx->b_rboff.as<int64_t>(), ctx->b_rbytes.as<uint8_t>()); }
         aa.read_bytes = ctx->b_rbytes.as<uint8_t>(); aa.rbyte_off = ctx->b_rboff.as<int64_t>();
     }
     const int nwk = std::max(n_work, 1);
@@ -457,40 +510,23 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
     CK(cudaEventRecord(ctx->ev[3], st));
     if (n_work > 0) {
         const int tb = (n_work + 127) / 128;
-        k_al_sizes<<<tb, 128, 0, st>>>(aa, ctx->b_alsz.as<int32_t>());
-        k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_alsz.as<int32_t>(), ctx->b_aloff.as<int64_t>(), n_work, nullptr);
+        { ++ctx->launches; k_al_sizes<<<tb, 128, 0, st>>>(aa, ctx->b_alsz.as<int32_t>()); }
+        { ++ctx->launches; k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_alsz.as<int32_t>(), ctx->b_aloff.as<int64_t>(), n_work, nullptr); }
         int64_t cig_total = 0;
         CK(cudaMemcpyAsync(&cig_total, ctx->b_aloff.as<int64_t>() + n_work, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         ENS(ctx->b_cigs, (size_t)(cig_total + 16) * 4);
         aa.cigs = ctx->b_cigs.as<uint32_t>();
         CK(cudaMemsetAsync(ctx->b_rc.p, 0, 1024, st));
-        k_al_offsets<<<tb, 128, 0, st>>>(aa, ctx->b_aloff.as<int64_t>());
-        k_al_init<<<tb, 128, 0, st>>>(aa);
+        { ++ctx->launches; k_al_offsets<<<tb, 128, 0, st>>>(aa, ctx->b_aloff.as<int64_t>()); }
+        { ++ctx->launches; k_al_init<<<tb, 128, 0, st>>>(aa); }
         CK(cudaFuncSetAttribute(k_al_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(AL_WARPS * sizeof(VecSmem))));
-        k_al_fused<<<al_grid, AL_THREADS, AL_WARPS * sizeof(VecSmem), st>>>(aa);
-        k_al_regfin<<<std::max(1, std::min((n_work + 7) / 8, sm * 8)), 256, 0, st>>>(aa);
-        k_al_finish<<<tp_blocks<TP_FINISH>(n_work, 128), 128, 0, st>>>(aa);
+        { ++ctx->launches; k_al_fused<<<al_grid, AL_THREADS, AL_WARPS * sizeof(VecSmem), st>>>(aa); }
+        { ++ctx->launches; k_al_regfin<<<std::max(1, std::min((n_work + 7) / 8, sm * 8)), 256, 0, st>>>(aa); }
+        { ++ctx->launches; k_al_finish<<<tp_blocks<TP_FINISH>(n_work, 128), 128, 0, st>>>(aa); }
     }
     CK(cudaEventRecord(ctx->ev[4], st));
-    // ---- (e)+(f) depth, medians, AF ----
-    DepthArgs da; memset(&da, 0, sizeof(da));
-    da.n_loci = n_loci; da.mode = ctx->depth_mode; da.contig_len = contig_len; da.te_start = db->te_start + l0; da.te_end = db->te_end + l0;
-    da.locus_read_begin = ctx->b_lrb.as<int32_t>(); da.prob_blk_off = ctx->b_pblkoff.as<int64_t>(); da.prob_blk_cnt = ctx->b_pblkcnt.as<int32_t>();
-    da.blocks = ctx->b_blk.as<int2>(); da.flank_len = db->flank_len; da.flank_off = db->flank_off; da.te_len = db->te_len; da.te_off = db->te_off;
-    da.cov2x = dres->cov2x + (int64_t)l0 * 8; da.af = dres->af + l0; da.max_len = max_tlen;
-    if (dres->depth) {
-        std::vector<int64_t> doff(n_loci + 1);
-        for (int l = 0; l < n_loci; ++l) doff[l] = h_depth_off[l0 + l];
-        ENS(ctx->b_doff, (n_loci + 1) * 8);
-        CK(cudaMemcpyAsync(ctx->b_doff.p, doff.data(), (size_t)n_loci * 8, cudaMemcpyHostToDevice, st));
-        CK(cudaStreamSynchronize(st));
-        da.depth = dres->depth; da.depth_off = ctx->b_doff.as<int64_t>();
-    }
-    const size_t dp_smem = ((size_t)max_tlen + 8) * 4;
-    if (dp_smem > 220 * 1024) return TELR_EUNSUPPORTED;
-    CK(cudaFuncSetAttribute(k_depth_af, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dp_smem));
-    k_depth_af<<<std::min(n_loci, sm * 4), DP_THREADS, dp_smem, st>>>(da);
+    { int rc = run_depth(); if (rc != TELR_OK) return rc; }
     CK(cudaEventRecord(ctx->ev[5], st));
     int64_t hc[C_SLOTS];
     CK(cudaMemcpyAsync(hc, ctr, sizeof(hc), cudaMemcpyDeviceToHost, st));
@@ -518,7 +554,6 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
     }
     stats->dp_cells += hc[C_CELLS]; stats->n_dp_tasks += hc[C_TASKS]; stats->n_anchors += hc[C_ANCH]; stats->n_minimizers += n_mz;
     stats->n_aln_blocks += hc[C_NBLK];
-    ctx->launches += 22 + (n_work > 0 ? 7 : 0);   // unpack, descs, sketch x2, scan x4, self_count, chain x2 + sort/dp/bt/rmq/regs, reg_caps, worklist, align, depth_af
     if (d_aln_out) { stats->n_aln = hc[C_NALN]; stats->n_cigar = hc[C_NCIG]; }
     float ms;
     static const int pairs[5][3] = {{0, 1, 0}, {1, 2, 1}, {2, 3, 2}, {3, 4, 3}, {4, 5, 6}};
@@ -526,8 +561,94 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
     return TELR_OK;
 }
 
+// Chunk loci by read bases.  Large chunks amortise the tails of the latency-bound chaining kernels and of the persistent
+// alignment kernel (config 2 on one B200: 384 Mbase chunks 1924 loci/s, 768 Mbase 1973, one 1.8 Gbase chunk 2007), so the
+// default takes what the device holds: about 80 B of workspace per read base (CIGAR arenas sized for the worst case ~45,
+// sketch slots 12, alignment blocks 4, minimizers, anchors, chaining scratch, read bytes) on top of ~28 GB of per-warp
+// alignment scratch, capped at 2 Gbase; equal-sized chunks.  On a 180 GB B200 that is 1.4 Gbase (measured peak 84 GB).
+static int64_t chunk_budget(const telr_af_ctx *ctx)
+{
+    int64_t budget = ctx->chunk_bases;
+    if (budget <= 0) {
+        double usable = 0.8 * (double)ctx->total_mem;
+        if (ctx->ws_limit > 0 && (double)ctx->ws_limit < usable) usable = (double)ctx->ws_limit;
+        budget = (int64_t)((usable - 28.0 * (1 << 30)) / 80.0);
+        budget = std::max<int64_t>((int64_t)128 << 20, std::min<int64_t>(budget, (int64_t)2048 << 20));
+    }
+    return budget;
+}
+
+// Host -> device upload of the packed bases behind the kernels: a host thread copies, chunk after chunk, the base range the
+// chunk's loci cover (seq2 + nmask) on the ctx's copy stream and records one event per chunk; the compute stream waits for
+// the event of the chunk it is about to process.  Pageable caller memory is fine (the driver stages it; that blocks only the
+// uploader thread).  Ranges must advance monotonically with the chunks (they do for every batch packed locus by locus);
+// otherwise the whole batch goes up with chunk 0.
+struct Uploader {
+    telr_af_ctx *ctx = nullptr;
+    const telr_af_batch *hb = nullptr;
+    uint32_t *d_seq2 = nullptr, *d_nmask = nullptr;
+    std::vector<int64_t> lo, hi;                 // base range uploaded for chunk i
+    std::vector<cudaEvent_t> ev;
+    std::atomic<int> recorded{0};                // events recorded so far
+    std::atomic<int> failed{0};
+    std::thread th;
+
+    int start(telr_af_ctx *c, const telr_af_batch *b, const HostMeta &hm, const std::vector<int32_t> &cuts, uint32_t *ds, uint32_t *dn)
+    {
+        ctx = c; hb = b; d_seq2 = ds; d_nmask = dn;
+        const int nc = (int)cuts.size() - 1;
+        lo.assign(nc, 0); hi.assign(nc, 0);
+        bool mono = true; int64_t prev_hi = 0, prev_lo = 0;
+        for (int ci = 0; ci < nc; ++ci) {
+            int64_t a = INT64_MAX, z = 0;
+            for (int l = cuts[ci]; l < cuts[ci + 1]; ++l) {
+                if (hm.contig_len[l] > 0) { a = std::min<int64_t>(a, b->contig_off[l]); z = std::max<int64_t>(z, b->contig_off[l] + (((int64_t)hm.contig_len[l] + 63) & ~63LL)); }
+            }
+            for (int r = hm.lrb[cuts[ci]]; r < hm.lrb[cuts[ci + 1]]; ++r) { a = std::min<int64_t>(a, b->read_off[r]); z = std::max<int64_t>(z, b->read_off[r] + (((int64_t)hm.read_len[r] + 63) & ~63LL)); }
+            if (a == INT64_MAX) a = z = prev_hi;
+            a &= ~63LL; z = std::min<int64_t>((z + 63) & ~63LL, b->n_bases);
+            if (a < prev_lo || z < prev_hi) mono = false;
+            lo[ci] = std::max(a, prev_hi); hi[ci] = std::max(z, lo[ci]);
+            prev_lo = a; prev_hi = std::max(prev_hi, z);
+        }
+        if (!mono && nc > 0) { for (int ci = 0; ci < nc; ++ci) lo[ci] = hi[ci] = b->n_bases; lo[0] = 0; }
+        ev.resize(nc);
+        for (auto &e : ev) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return TELR_ECUDA;
+        th = std::thread([this]() { this->run(); });
+        return TELR_OK;
+    }
+    void run()
+    {
+        if (cudaSetDevice(ctx->device) != cudaSuccess) { failed = 1; recorded = (int)ev.size(); return; }
+        for (size_t ci = 0; ci < ev.size(); ++ci) {
+            const int64_t a = lo[ci], z = hi[ci];
+            if (z > a && !failed) {
+                if (cudaMemcpyAsync(d_seq2 + a / 16, hb->seq2 + a / 16, (size_t)(z - a) / 4, cudaMemcpyHostToDevice, ctx->copy_stream) != cudaSuccess ||
+                    cudaMemcpyAsync(d_nmask + a / 32, hb->nmask + a / 32, (size_t)(z - a) / 8, cudaMemcpyHostToDevice, ctx->copy_stream) != cudaSuccess) failed = 1;
+            }
+            if (cudaEventRecord(ev[ci], ctx->copy_stream) != cudaSuccess) failed = 1;
+            recorded.store((int)ci + 1, std::memory_order_release);
+        }
+    }
+    // make the compute stream wait for chunk ci's bases
+    int wait(int ci)
+    {
+        while (recorded.load(std::memory_order_acquire) <= ci) std::this_thread::yield();
+        if (failed) return TELR_ECUDA;
+        return cudaStreamWaitEvent(ctx->stream, ev[ci], 0) == cudaSuccess ? TELR_OK : TELR_ECUDA;
+    }
+    void finish()
+    {
+        if (th.joinable()) th.join();
+        for (auto &e : ev) cudaEventDestroy(e);
+        ev.clear();
+    }
+    ~Uploader() { finish(); }
+};
+
 static int run_device(telr_af_ctx *ctx, const telr_af_batch *db, const HostMeta &hm, telr_af_result *dres, telr_af_result *stats,
-                      int32_t *d_aln_out, int64_t aln_cap, uint32_t *d_cig_out, int64_t cig_cap)
+                      int32_t *d_aln_out, int64_t aln_cap, uint32_t *d_cig_out, int64_t cig_cap,
+                      const std::vector<int32_t> *cuts_in = nullptr, Uploader *up = nullptr)
 {
     Opt o;
     if (db->preset < 0 || db->preset > 2) return TELR_EINVAL;
@@ -538,22 +659,12 @@ static int run_device(telr_af_ctx *ctx, const telr_af_batch *db, const HostMeta 
     stats->dp_cells = stats->n_dp_tasks = stats->n_anchors = stats->n_minimizers = stats->n_aln_blocks = 0;
     stats->n_aln = stats->n_cigar = 0;
     for (int i = 0; i < 8; ++i) stats->ms_stage[i] = 0.f;
-    // Chunk loci by read bases.  Large chunks amortise the tails of the latency-bound chaining kernels and of the persistent
-    // alignment kernel (config 2 on one B200: 384 Mbase chunks 1924 loci/s, 768 Mbase 1973, one 1.8 Gbase chunk 2007), so the
-    // default takes what the device holds: about 80 B of workspace per read base (CIGAR arenas sized for the worst case ~45,
-    // sketch slots 12, alignment blocks 4, minimizers, anchors, chaining scratch, read bytes) on top of ~28 GB of per-warp
-    // alignment scratch, capped at 2 Gbase; equal-sized chunks.  On a 180 GB B200 that is 1.4 Gbase (measured peak 84 GB).
-    int64_t budget = ctx->chunk_bases;
-    if (budget <= 0) {
-        double usable = 0.8 * (double)ctx->total_mem;
-        if (ctx->ws_limit > 0 && (double)ctx->ws_limit < usable) usable = (double)ctx->ws_limit;
-        budget = (int64_t)((usable - 28.0 * (1 << 30)) / 80.0);
-        budget = std::max<int64_t>((int64_t)128 << 20, std::min<int64_t>(budget, (int64_t)2048 << 20));
-    }
     std::vector<int32_t> cuts;
-    plan_chunks(hm.read_len.data(), hm.lrb.data(), n_loci, budget, cuts);
+    if (cuts_in) cuts = *cuts_in;
+    else plan_chunks(hm.read_len.data(), hm.lrb.data(), n_loci, chunk_budget(ctx), cuts);
     for (size_t ci = 0; ci + 1 < cuts.size(); ++ci) {
         const int l0 = cuts[ci], l1 = cuts[ci + 1];
+        if (up) { int rc = up->wait((int)ci); if (rc != TELR_OK) return rc; }
         int rc = run_chunk(ctx, o, db, hm, l0, l1, dres, depth_off.data(), stats, d_aln_out, aln_cap, d_cig_out, cig_cap);
         if (rc != TELR_OK) return rc;
     }
@@ -602,7 +713,8 @@ int telr_af_create(telr_af_ctx **out, int device, size_t workspace_bytes)
     if (prop.major != 10) { fprintf(stderr, "[telr_af] device %d is sm_%d%d; this library is built for sm_100a only\n", device, prop.major, prop.minor); return TELR_ENODEV; }
     telr_af_ctx *ctx = new telr_af_ctx();
     ctx->device = device; ctx->sm_count = prop.multiProcessorCount; ctx->ws_limit = workspace_bytes; ctx->total_mem = prop.totalGlobalMem;
-    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return TELR_ECUDA; }
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return TELR_ECUDA; }
     for (auto &e : ctx->ev) cudaEventCreate(&e);
     const char *dm = getenv("TELR_DEPTH_MODE");
     if (dm) ctx->depth_mode = atoi(dm) ? 1 : 0;
@@ -636,7 +748,7 @@ int telr_af_destroy(telr_af_ctx *ctx)
     DevBuf *all[] = {&ctx->b_cov, &ctx->b_af, &ctx->b_depth, &ctx->b_lrb, &ctx->b_cboff, &ctx->b_ctg, &ctx->b_descs, &ctx->b_counts, &ctx->b_mzoff,
                      &ctx->b_mzx, &ctx->b_mzy, &ctx->b_self, &ctx->b_tabk, &ctx->b_tabc, &ctx->b_hpc, &ctx->b_hpp, &ctx->b_hpr, &ctx->b_pna, &ctx->b_pread,
                      &ctx->b_pls, &ctx->b_paoff, &ctx->b_prcap, &ctx->b_proff, &ctx->b_pnregs, &ctx->b_pnca, &ctx->b_anch, &ctx->b_regs, &ctx->b_chws,
-                     &ctx->b_alws, &ctx->b_work, &ctx->b_blk, &ctx->b_pblkoff, &ctx->b_pblkcnt, &ctx->b_ctr, &ctx->b_alnout, &ctx->b_cigout, &ctx->b_doff,
+                     &ctx->b_alws, &ctx->b_work, &ctx->b_blk, &ctx->b_pblkoff, &ctx->b_pblkcnt, &ctx->b_ctr, &ctx->b_alnout, &ctx->b_cigout, &ctx->b_doff, &ctx->b_grow, &ctx->b_lbad,
                      &ctx->b_big, &ctx->b_biglock, &ctx->b_rbytes, &ctx->b_rboff, &ctx->b_alwork, &ctx->b_alctx, &ctx->b_altask, &ctx->b_alres, &ctx->b_alsz, &ctx->b_aloff,
                      &ctx->b_cigs, &ctx->b_pool, &ctx->b_tlist, &ctx->b_rc, &ctx->b_opt, &ctx->b_idxbig, &ctx->b_psb, &ctx->b_psoff, &ctx->b_pscr, &ctx->b_pnu, &ctx->b_pm,
                      &ctx->b_tfirst, &ctx->b_tcnt, &ctx->b_toff, &ctx->b_tmpx, &ctx->b_tmpy, &ctx->b_order, &ctx->b_wflag, &ctx->b_woff, &ctx->b_hpoff, &ctx->b_hpn};
@@ -644,6 +756,7 @@ int telr_af_destroy(telr_af_ctx *ctx)
     for (auto &b : ctx->b_in) b.release();
     for (auto &e : ctx->ev) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
     return TELR_OK;
 }
@@ -660,15 +773,19 @@ int telr_af_run(telr_af_ctx *ctx, const telr_af_batch *hb, telr_af_result *hr)
     int rc = validate_host_meta(hb, hm);
     if (rc) return rc;
     if (hb->n_bases % 64) return TELR_EINVAL;
-    // ---- H2D ----
+    // ---- H2D: the small index arrays now, the packed bases chunk by chunk behind the kernels (Uploader) ----
     telr_af_batch db = *hb;
     const void *src[10] = {hb->seq2, hb->nmask, hb->read_off, hb->read_len, hb->read_hash, hb->locus_read_begin, hb->contig_off, hb->contig_len, hb->te_start, hb->te_end};
     const size_t bytes[10] = {(size_t)hb->n_bases / 4, (size_t)hb->n_bases / 8, (size_t)hb->n_reads * 8, (size_t)hb->n_reads * 4, (size_t)hb->n_reads * 4,
                               (size_t)(hb->n_loci + 1) * 4, (size_t)hb->n_loci * 8, (size_t)hb->n_loci * 4, (size_t)hb->n_loci * 4, (size_t)hb->n_loci * 4};
     for (int i = 0; i < 10; ++i) {
         ENS(ctx->b_in[i], bytes[i] + 64);
-        if (bytes[i]) CK(cudaMemcpyAsync(ctx->b_in[i].p, src[i], bytes[i], cudaMemcpyHostToDevice, st));
+        if (i >= 2 && bytes[i]) CK(cudaMemcpyAsync(ctx->b_in[i].p, src[i], bytes[i], cudaMemcpyHostToDevice, st));
     }
+    std::vector<int32_t> cuts;
+    plan_chunks(hm.read_len.data(), hm.lrb.data(), hb->n_loci, chunk_budget(ctx), cuts);
+    Uploader up;
+    if (up.start(ctx, hb, hm, cuts, ctx->b_in[0].as<uint32_t>(), ctx->b_in[1].as<uint32_t>()) != TELR_OK) return TELR_ECUDA;
     db.seq2 = ctx->b_in[0].as<uint32_t>(); db.nmask = ctx->b_in[1].as<uint32_t>(); db.read_off = ctx->b_in[2].as<int64_t>();
     db.read_len = ctx->b_in[3].as<int32_t>(); db.read_hash = ctx->b_in[4].as<uint32_t>(); db.locus_read_begin = ctx->b_in[5].as<int32_t>();
     db.contig_off = ctx->b_in[6].as<int64_t>(); db.contig_len = ctx->b_in[7].as<int32_t>(); db.te_start = ctx->b_in[8].as<int32_t>();
@@ -684,7 +801,8 @@ int telr_af_run(telr_af_ctx *ctx, const telr_af_batch *hb, telr_af_result *hr)
         ENS(ctx->b_alnout, (size_t)hr->aln_cap * 64 + 64); ENS(ctx->b_cigout, (size_t)hr->cigar_cap * 4 + 64);
         d_aln = ctx->b_alnout.as<int32_t>(); d_cig = ctx->b_cigout.as<uint32_t>();
     }
-    rc = run_device(ctx, &db, hm, &dres, hr, d_aln, hr->aln_cap, d_cig, hr->cigar_cap);
+    rc = run_device(ctx, &db, hm, &dres, hr, d_aln, hr->aln_cap, d_cig, hr->cigar_cap, &cuts, &up);
+    up.finish();
     if (rc) return rc;
     // ---- D2H ----
     CK(cudaMemcpyAsync(hr->cov2x, dres.cov2x, (size_t)hb->n_loci * 32, cudaMemcpyDeviceToHost, st));
@@ -770,15 +888,15 @@ int telr_af_sketch(telr_af_ctx *ctx, const uint32_t *seq2, const uint32_t *nmask
         CK(cudaStreamSynchronize(st));
         if (n_mz > mz_cap) return TELR_ECAP;
     } else {
-        k_sketch<false><<<grid, SK_THREADS, 0, st>>>(sa);
-        k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_counts.as<int32_t>(), ctx->b_mzoff.as<int64_t>(), n_seq, nullptr);
+        { ++ctx->launches; k_sketch<false><<<grid, SK_THREADS, 0, st>>>(sa); }
+        { ++ctx->launches; k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_counts.as<int32_t>(), ctx->b_mzoff.as<int64_t>(), n_seq, nullptr); }
         CK(cudaMemcpyAsync(mz_off, ctx->b_mzoff.p, (size_t)(n_seq + 1) * 8, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         n_mz = mz_off[n_seq];
         if (n_mz > mz_cap) return TELR_ECAP;
         ENS(ctx->b_mzx, (n_mz + 1) * 8); ENS(ctx->b_mzy, (n_mz + 1) * 4);
         sa.offs = ctx->b_mzoff.as<int64_t>(); sa.mz_x = ctx->b_mzx.as<uint64_t>(); sa.mz_y = ctx->b_mzy.as<uint32_t>();
-        k_sketch<true><<<grid, SK_THREADS, 0, st>>>(sa);
+        { ++ctx->launches; k_sketch<true><<<grid, SK_THREADS, 0, st>>>(sa); }
     }
     std::vector<uint32_t> y32(n_mz + 1);
     CK(cudaMemcpyAsync(mz_x, ctx->b_mzx.p, (size_t)n_mz * 8, cudaMemcpyDeviceToHost, st));
@@ -827,10 +945,7 @@ int telr_af_depth_af(telr_af_ctx *ctx, int32_t n_loci, const int32_t *contig_len
     da.flank_len = flank_len; da.flank_off = flank_off; da.te_len = te_len; da.te_off = te_off;
     da.depth = ctx->b_depth.as<int32_t>(); da.depth_off = ctx->b_doff.as<int64_t>();
     da.cov2x = ctx->b_cov.as<int32_t>(); da.af = ctx->b_af.as<double>(); da.max_len = max_len;
-    const size_t dp_smem = ((size_t)max_len + 8) * 4;
-    if (dp_smem > 220 * 1024) return TELR_EUNSUPPORTED;
-    CK(cudaFuncSetAttribute(k_depth_af, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dp_smem));
-    k_depth_af<<<std::min(n_loci, ctx->sm_count * 4), DP_THREADS, dp_smem, st>>>(da);
+    { int rc = launch_depth(ctx, da, n_loci, max_len); if (rc != TELR_OK) return rc; }
     CK(cudaMemcpyAsync(cov2x, ctx->b_cov.p, (size_t)n_loci * 32, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(af, ctx->b_af.p, (size_t)n_loci * 8, cudaMemcpyDeviceToHost, st));
     if (depth) CK(cudaMemcpyAsync(depth, ctx->b_depth.p, (size_t)doff[n_loci] * 4, cudaMemcpyDeviceToHost, st));
@@ -937,7 +1052,7 @@ extern "C" int telr_af_dp(telr_af_ctx *ctx, int32_t preset, int32_t n_tasks, con
     A.cells = (unsigned long long *)(ctr + C_CELLS);
     CK(cudaFuncSetAttribute(k_dp_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(AL_WARPS * sizeof(VecSmem))));
     CK(cudaEventRecord(ctx->ev[0], st));
-    k_dp_stage<<<grid, AL_THREADS, AL_WARPS * sizeof(VecSmem), st>>>(A);
+    { ++ctx->launches; k_dp_stage<<<grid, AL_THREADS, AL_WARPS * sizeof(VecSmem), st>>>(A); }
     CK(cudaEventRecord(ctx->ev[1], st));
     int64_t hc[C_SLOTS];
     CK(cudaMemcpyAsync(hc, ctr, sizeof(hc), cudaMemcpyDeviceToHost, st));

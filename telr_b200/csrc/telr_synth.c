@@ -152,7 +152,10 @@ typedef struct {
     int32_t *rlen, *rtruth; int32_t n_reads, m_reads;
     uint8_t *contig; int32_t clen, te_s, te_e;
     float af;
+    uint32_t *p2, *pn; int64_t pbases;   /* the locus packed on its own (contig, then reads; 64-base aligned): keeps the peak footprint at 0.375 B/base */
 } locus_t;
+
+static void pack_into(const uint8_t *s, int32_t len, int64_t off, uint32_t *seq2, uint32_t *nmask);
 
 static void gen_locus(const telr_synth_cfg *c, const te_t *fam, int32_t gid, locus_t *o)
 {
@@ -230,6 +233,23 @@ static void gen_locus(const telr_synth_cfg *c, const te_t *fam, int32_t gid, loc
         o->n_reads++;
     }
     free(tmp); free(alt); free(ref);
+    {   /* pack now and drop the byte arrays */
+        int64_t nb = ((int64_t)o->clen + 63) / 64 * 64;
+        for (int32_t k = 0; k < o->n_reads; ++k) nb += ((int64_t)o->rlen[k] + 63) / 64 * 64;
+        o->pbases = nb;
+        o->p2 = (uint32_t *)calloc((size_t)(nb / 16) + 4, 4);
+        o->pn = (uint32_t *)calloc((size_t)(nb / 32) + 4, 4);
+        int64_t o2 = 0, so = 0;
+        pack_into(o->contig, o->clen, o2, o->p2, o->pn);
+        o2 += ((int64_t)o->clen + 63) / 64 * 64;
+        for (int32_t k = 0; k < o->n_reads; ++k) {
+            pack_into(o->seq.b + so, o->rlen[k], o2, o->p2, o->pn);
+            so += o->rlen[k];
+            o2 += ((int64_t)o->rlen[k] + 63) / 64 * 64;
+        }
+        free(o->contig); free(o->seq.b);
+        o->contig = NULL; memset(&o->seq, 0, sizeof(o->seq));
+    }
 }
 
 static void pack_into(const uint8_t *s, int32_t len, int64_t off, uint32_t *seq2, uint32_t *nmask)
@@ -259,13 +279,27 @@ void telr_synth_default(telr_synth_cfg *c)
 }
 
 /* read names are "L%06d_R%04d" (global locus id, read index within locus) */
+static int synth_generate(const telr_synth_cfg *c, int32_t first_locus, const int32_t *ids, int32_t n_loci, telr_synth_out *out);
+
 int telr_synth_generate(const telr_synth_cfg *c, int32_t first_locus, int32_t n_loci, telr_synth_out *out)
 {
+    return synth_generate(c, first_locus, NULL, n_loci, out);
+}
+
+/* the loci ids[0..n) (global locus ids, any order): what one device of a multi-GPU partition owns */
+int telr_synth_generate_list(const telr_synth_cfg *c, const int32_t *ids, int32_t n_loci, telr_synth_out *out)
+{
+    return synth_generate(c, 0, ids, n_loci, out);
+}
+
+static int synth_generate(const telr_synth_cfg *c, int32_t first_locus, const int32_t *ids, int32_t n_loci, telr_synth_out *out)
+{
     te_t *fam = (te_t *)calloc((size_t)c->n_families, sizeof(te_t));
-    locus_t *L = (locus_t *)calloc((size_t)n_loci, sizeof(locus_t));
+    locus_t *L = (locus_t *)calloc((size_t)(n_loci > 0 ? n_loci : 1), sizeof(locus_t));
     gen_families(c, fam);
+#define GID(l) (ids ? ids[l] : first_locus + (l))
 #pragma omp parallel for schedule(dynamic, 4)
-    for (int32_t l = 0; l < n_loci; ++l) gen_locus(c, fam, first_locus + l, &L[l]);
+    for (int32_t l = 0; l < n_loci; ++l) gen_locus(c, fam, GID(l), &L[l]);
     memset(out, 0, sizeof(*out));
     out->n_loci = n_loci;
     int64_t nb = 0; int32_t nr = 0;
@@ -275,8 +309,8 @@ int telr_synth_generate(const telr_synth_cfg *c, int32_t first_locus, int32_t n_
         nr += L[l].n_reads;
     }
     out->n_reads = nr; out->n_bases = nb;
-    out->seq2 = (uint32_t *)calloc((size_t)(nb / 16) + 4, 4);
-    out->nmask = (uint32_t *)calloc((size_t)(nb / 32) + 4, 4);
+    out->seq2 = (uint32_t *)malloc(((size_t)(nb / 16) + 4) * 4);
+    out->nmask = (uint32_t *)malloc(((size_t)(nb / 32) + 4) * 4);
     out->read_off = (int64_t *)malloc((size_t)(nr + 1) * 8);
     out->read_len = (int32_t *)malloc((size_t)(nr + 1) * 4);
     out->read_hash = (uint32_t *)malloc((size_t)(nr + 1) * 4);
@@ -299,7 +333,7 @@ int telr_synth_generate(const telr_synth_cfg *c, int32_t first_locus, int32_t n_
         off += ((int64_t)L[l].clen + 63) / 64 * 64;
         for (int32_t k = 0; k < L[l].n_reads; ++k) {
             char name[64];
-            snprintf(name, sizeof(name), "L%06d_R%04d", first_locus + l, k);
+            snprintf(name, sizeof(name), "L%06d_R%04d", GID(l), k);
             out->read_off[ri] = off; out->read_len[ri] = L[l].rlen[k];
             out->read_hash[ri] = x31(name); out->read_truth[ri] = L[l].rtruth[k];
             off += ((int64_t)L[l].rlen[k] + 63) / 64 * 64;
@@ -309,17 +343,11 @@ int telr_synth_generate(const telr_synth_cfg *c, int32_t first_locus, int32_t n_
     out->locus_read_begin[n_loci] = ri;
 #pragma omp parallel for schedule(dynamic, 4)
     for (int32_t l = 0; l < n_loci; ++l) {
-        int64_t o2 = loff[l];
-        pack_into(L[l].contig, L[l].clen, o2, out->seq2, out->nmask);
-        o2 += ((int64_t)L[l].clen + 63) / 64 * 64;
-        int64_t so = 0;
-        for (int32_t k = 0; k < L[l].n_reads; ++k) {
-            pack_into(L[l].seq.b + so, L[l].rlen[k], o2, out->seq2, out->nmask);
-            so += L[l].rlen[k];
-            o2 += ((int64_t)L[l].rlen[k] + 63) / 64 * 64;
-        }
-        free(L[l].contig); free(L[l].seq.b); free(L[l].rlen); free(L[l].rtruth);
+        memcpy(out->seq2 + loff[l] / 16, L[l].p2, (size_t)(L[l].pbases / 16) * 4);
+        memcpy(out->nmask + loff[l] / 32, L[l].pn, (size_t)(L[l].pbases / 32) * 4);
+        free(L[l].p2); free(L[l].pn); free(L[l].rlen); free(L[l].rtruth);
     }
+#undef GID
     free(loff); free(L);
     for (int f = 0; f < c->n_families; ++f) free(fam[f].seq);
     free(fam);

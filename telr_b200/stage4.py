@@ -69,7 +69,7 @@ def read_fasta(path):
 
 def median_str(cov2x: int, n: int) -> str:
     """str(statistics.median(values)) given 2*median and the number of values (int for odd n, float for even n)."""
-    if cov2x == -1:
+    if cov2x == -1 or cov2x == -4:      # -4: locus outside the implemented scope (contig with > 65 536 minimizers), reported like a missing window
         return "None"
     if cov2x < 0:
         raise statistics.StatisticsError("no median for empty data")   # the reference dies here too (TELR_te.py:882)
@@ -149,19 +149,30 @@ def run_batch(batch: Batch, devices=None, **kw):
     return cov, af, None
 
 
-def partition_loci(batch: Batch, n: int):
-    """Longest-processing-time-first assignment of loci to n shards by read bases x contig length."""
+def locus_costs(batch: Batch) -> np.ndarray:
+    """Cost estimate of every locus for the partitioner: read bases + contig length."""
     lrb = batch.locus_read_begin
     csum = np.concatenate([[0], np.cumsum(batch.read_len.astype(np.int64))])
-    cost = (csum[lrb[1:]] - csum[lrb[:-1]]) + batch.contig_len.astype(np.int64)
+    return (csum[lrb[1:]] - csum[lrb[:-1]]) + batch.contig_len.astype(np.int64)
+
+
+def partition_costs(cost, n: int):
+    """Longest-processing-time-first assignment of items to n shards; every shard is returned in ascending item order."""
+    import heapq
+    cost = np.asarray(cost, np.int64)
     order = np.argsort(-cost, kind="stable")
-    loads = [0] * n
+    heap = [(0, k) for k in range(n)]
     shards = [[] for _ in range(n)]
     for l in order:
-        k = min(range(n), key=lambda i: loads[i])
+        load, k = heapq.heappop(heap)
         shards[k].append(int(l))
-        loads[k] += int(cost[l])
+        heapq.heappush(heap, (load + int(cost[l]), k))
     return [sorted(s) for s in shards]
+
+
+def partition_loci(batch: Batch, n: int):
+    """Longest-processing-time-first assignment of loci to n shards by read bases + contig length."""
+    return partition_costs(locus_costs(batch), n)
 
 
 def get_af(out, sample_name, bam, raw_reads, contig_te_annotation, contig_dir, vcf_parsed, flank_intervel_size, flank_offset,
@@ -250,6 +261,8 @@ def get_af(out, sample_name, bam, raw_reads, contig_te_annotation, contig_dir, v
         cov2x, af = np.zeros((0, 8), np.int32), np.zeros(0)
     logging.info("Local realignment finished in " + format_time(time.time() - start_time))
     del empty
+    for j in np.nonzero((cov2x == -4).any(axis=1))[0]:
+        logging.warning("%s: contig outside the implemented scope of the GPU path, coverage reported as None", loci[live[int(j)]][0])
 
     # ---- .freq / .revcomp.freq, then the AF block exactly as the reference parses them back ----
     pos_of = {i: j for j, i in enumerate(live)}
@@ -278,10 +291,9 @@ def get_af(out, sample_name, bam, raw_reads, contig_te_annotation, contig_dir, v
                 if strand:
                     freq = combine_af(te_flank_ratio(d["te_5p_cov"], d["flank_5p_cov"]), te_flank_ratio(d["te_5p_cov_rc"], d["flank_5p_cov_rc"]))
                     g = af[j]                       # device value before clamp/round; must agree with the Python formula
-                    if freq is None:
-                        assert math.isnan(g), (name, g)
-                    else:
-                        assert abs(round(1 if g > 1 else g, 3) - freq) < 1e-9, (name, g, freq)
+                    ok = math.isnan(g) if freq is None else (not math.isnan(g) and abs(round(1 if g > 1 else g, 3) - freq) < 1e-9)
+                    if not ok:
+                        raise RuntimeError(f"{name}: device AF {g!r} disagrees with the reference formula {freq!r}")
                     d["freq"] = freq
     logging.info("Allele frequency estimation finished in " + format_time(time.time() - start_time))
     return te_freq

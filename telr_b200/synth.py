@@ -48,6 +48,8 @@ def _lib():
         _LIB = C.CDLL(path)
         _LIB.telr_synth_generate.argtypes = [C.POINTER(SynthCfg), C.c_int32, C.c_int32, C.POINTER(SynthOut)]
         _LIB.telr_synth_generate.restype = C.c_int
+        _LIB.telr_synth_generate_list.argtypes = [C.POINTER(SynthCfg), C.c_void_p, C.c_int32, C.POINTER(SynthOut)]
+        _LIB.telr_synth_generate_list.restype = C.c_int
         _LIB.telr_synth_default.argtypes = [C.POINTER(SynthCfg)]
         _LIB.telr_synth_free.argtypes = [C.POINTER(SynthOut)]
     return _LIB
@@ -79,15 +81,21 @@ def make_cfg(name: str, **over) -> tuple[SynthCfg, str]:
     return cfg, preset
 
 
-def generate(name: str, first_locus: int = 0, n_loci: int | None = None, total_loci: int | None = None, **over) -> Batch:
-    """Generate loci [first_locus, first_locus+n_loci) of configuration ``name`` (``total_loci`` widens the job)."""
+def generate(name: str, first_locus: int = 0, n_loci: int | None = None, total_loci: int | None = None, loci=None, **over) -> Batch:
+    """Generate loci [first_locus, first_locus+n_loci) of configuration ``name`` (``total_loci`` widens the job), or the
+    explicit list ``loci`` of global locus ids (every locus has its own RNG stream, so any subset comes out identical)."""
     cfg, preset = make_cfg(name, **over)
     if total_loci is not None:
         cfg.n_loci_total = int(total_loci)
-    if n_loci is None:
-        n_loci = cfg.n_loci_total - first_locus
     out = SynthOut()
-    rc = _lib().telr_synth_generate(C.byref(cfg), first_locus, n_loci, C.byref(out))
+    if loci is not None:
+        ids = np.ascontiguousarray(loci, np.int32)
+        first_locus, n_loci = (int(ids[0]) if len(ids) else 0), len(ids)
+        rc = _lib().telr_synth_generate_list(C.byref(cfg), ids.ctypes.data, len(ids), C.byref(out))
+    else:
+        if n_loci is None:
+            n_loci = cfg.n_loci_total - first_locus
+        rc = _lib().telr_synth_generate(C.byref(cfg), first_locus, n_loci, C.byref(out))
     if rc != 0:
         raise MemoryError("telr_synth_generate failed")
     try:

@@ -418,3 +418,25 @@ def test_full_size_properties(ctx):
     assert (r2.depth == r.depth).all() and (r2.cov2x == r.cov2x).all()
     ok = ~np.isnan(r.af)
     assert ok.mean() > 0.8 and np.abs(np.minimum(r.af[ok], 1) - b.meta["truth_af"][ok]).mean() < 0.12      # estimates track the simulated truth
+
+
+def test_loci_without_any_read(ctx):
+    """n_loci > 0 and n_reads == 0 (every shard of a partition may look like this): zero coverage, AF None, no launch error."""
+    from telr_b200.batch import Batch
+    b = synth.generate("ont_3k_50x", 0, 3, depth=6)
+    none = np.zeros(0, np.int64)
+    b0 = Batch(b.preset, b.seq2, b.nmask, none, none.astype(np.int32), none.astype(np.uint32), np.zeros(4, np.int32),
+               b.contig_off.copy(), b.contig_len.copy(), b.te_start.copy(), b.te_end.copy())
+    r = ctx.run(b0, want_depth=True)
+    ro = orc.af_run(b0, threads=0, want_aln=False)
+    assert (r.cov2x == ro.cov2x).all() and (r.depth == 0).all() and np.isnan(r.af).all()
+
+
+def test_contig_longer_than_the_shared_memory_depth_row(ctx):
+    """A 70 kb local assembly (ordinary for Flye): the depth row moves to global memory, nothing fails, results equal the oracle."""
+    b = synth.generate("ont_3k_50x", 0, 2, depth=5, te_min=64000, te_max=65000, te_median=64500, n_families=2)
+    assert int(b.contig_len.max()) > 60000
+    r = ctx.run(b, want_depth=True, want_aln=True)
+    ro = orc.af_run(b, threads=0)
+    util.assert_same_results(r, ro)
+    assert r.c.dp_cells == ro.c.dp_cells
