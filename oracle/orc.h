@@ -46,6 +46,14 @@ typedef struct orc_opt {
 
 void orc_opt_preset(orc_opt_t *o, int preset);
 
+/* Reach counters of the stated deviations from upstream: how often an input reaches a spot where this
+ * restatement knowingly differs from minimap2 2.22.  0 = query minimizers dropped by the plain `n > mid_occ` filter (upstream:
+ * mm_seed_select may rescue some), 1 = RMQ queries whose best priority is tied, 2 = banded DP calls whose traceback path
+ * comes within one cell of a band-limited edge (16-lane band rounding), 3 = ksw_ll calls with a tied maximum, 4 = index
+ * buckets with more than 64 entries (unstable radix sort order), 5 = banded DP calls, 6 = RMQ queries, 7 = ksw_ll calls. */
+extern int64_t orc_dev[8];
+void orc_dev_counters(int64_t out[8], int reset);
+
 /* [UP] mm_sketch (sketch.c). seq: nt4 codes (0..3, 4 = ambiguous). Returns #minimizers (may exceed cap: then truncated). */
 int64_t orc_sketch(const uint8_t *seq, int32_t len, int32_t w, int32_t k, int32_t hpc,
                    uint64_t *x, uint64_t *y, int64_t cap);

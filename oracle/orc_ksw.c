@@ -55,9 +55,9 @@ static int apply_zdrop(orc_ez_t *ez, int32_t H, int r, int t, int zdrop, int e)
 
 /* [UP] ksw2.h ksw_backtrack (is_rot = 1, min_intron_len = 0) */
 static void backtrack(orc_ez_t *ez, int is_rev, const uint8_t *p, const int64_t *poff, const int *off,
-                      const int *off_end, int i0, int j0)
+                      const int *off_end, int i0, int j0, int qlen, int tlen)
 {
-    int i = i0, j = j0, r, state = 0;
+    int i = i0, j = j0, r, state = 0, near_edge = 0;
     uint32_t tmp;
     ez->n_cigar = 0;
     while (i >= 0 && j >= 0) {
@@ -65,6 +65,10 @@ static void backtrack(orc_ez_t *ez, int is_rev, const uint8_t *p, const int64_t 
         r = i + j;
         if (i < off[r]) force_state = 2;
         if (i > off_end[r]) force_state = 1;
+        {   /* deviation counter: the path is within one cell of an edge that the band (not a sequence end) set */
+            int lo = r - qlen + 1 > 0 ? r - qlen + 1 : 0, hi = r < tlen - 1 ? r : tlen - 1;
+            if ((off[r] > lo && i <= off[r] + 1) || (off_end[r] < hi && i >= off_end[r] - 1)) near_edge = 1;
+        }
         tmp = force_state < 0 ? p[poff[r] + (i - off[r])] : 0;
         if (state == 0) state = tmp & 7;
         else if (!(tmp >> (state + 2) & 1)) state = 0;
@@ -76,6 +80,10 @@ static void backtrack(orc_ez_t *ez, int is_rev, const uint8_t *p, const int64_t 
     }
     if (i >= 0) push_cigar(ez, 2, i + 1);
     if (j >= 0) push_cigar(ez, 1, j + 1);
+    if (near_edge) {
+#pragma omp atomic
+        ++orc_dev[2];
+    }
     if (!is_rev)
         for (i = 0; i < ez->n_cigar >> 1; ++i)
             tmp = ez->cigar[i], ez->cigar[i] = ez->cigar[ez->n_cigar - 1 - i], ez->cigar[ez->n_cigar - 1 - i] = tmp;
@@ -98,6 +106,10 @@ void orc_ksw_extd2(int qlen, const uint8_t *query, int tlen, const uint8_t *targ
     if (q2 + e2 < q + e) t = q, q = q2, q2 = t, t = e, e = e2, e2 = t;
     qe = q + e, qe2 = q2 + e2;
     if (w < 0) w = tlen > qlen ? tlen : qlen;
+    if (w < (tlen > qlen ? tlen : qlen)) {
+#pragma omp atomic
+        ++orc_dev[5];
+    }
     {   /* -min_sc > 2*(q+e): no mismatch would ever be seen */
         int min_sc = -sc_b < -sc_ambi ? -sc_b : -sc_ambi;
         if (-min_sc > 2 * (q + e)) return;
@@ -238,12 +250,12 @@ void orc_ksw_extd2(int qlen, const uint8_t *query, int tlen, const uint8_t *targ
     {
         int rev_cigar = !!(flag & ORC_KSW_REV_CIGAR);
         if (!ez->zdropped && !(flag & ORC_KSW_EXTZ_ONLY)) {
-            backtrack(ez, rev_cigar, p, poff, off, off_end, tlen - 1, qlen - 1);
+            backtrack(ez, rev_cigar, p, poff, off, off_end, tlen - 1, qlen - 1, qlen, tlen);
         } else if (!ez->zdropped && (flag & ORC_KSW_EXTZ_ONLY) && ez->mqe + end_bonus > ez->max) {
             ez->reach_end = 1;
-            backtrack(ez, rev_cigar, p, poff, off, off_end, ez->mqe_t, qlen - 1);
+            backtrack(ez, rev_cigar, p, poff, off, off_end, ez->mqe_t, qlen - 1, qlen, tlen);
         } else if (ez->max_t >= 0 && ez->max_q >= 0) {
-            backtrack(ez, rev_cigar, p, poff, off, off_end, ez->max_t, ez->max_q);
+            backtrack(ez, rev_cigar, p, poff, off, off_end, ez->max_t, ez->max_q, qlen, tlen);
         }
     }
     free(p); free(poff); free(off);
@@ -256,7 +268,7 @@ void orc_ksw_extd2(int qlen, const uint8_t *query, int tlen, const uint8_t *targ
 int orc_ksw_ll(int qlen, const uint8_t *query, int tlen, const uint8_t *target,
                int sc_a, int sc_b, int sc_ambi, int gapo, int gape, int *qe_, int *te_)
 {
-    int i, j, gmax = 0, gqe = -1, gte = -1, gapoe = gapo + gape;
+    int i, j, gmax = 0, gqe = -1, gte = -1, gapoe = gapo + gape, best = 0, n_best = 0;
     int32_t *H, *E;
     if (qe_) *qe_ = -1;
     if (te_) *te_ = -1;
@@ -275,6 +287,7 @@ int orc_ksw_ll(int qlen, const uint8_t *query, int tlen, const uint8_t *target,
             if (h < 0) h = 0;
             H[j + 1] = h;
             if (h > imax) imax = h, iqe = j;
+            if (h > best) best = h, n_best = 1; else if (h == best) ++n_best;
             eij -= gape; if (eij < h - gapoe) eij = h - gapoe; if (eij < 0) eij = 0;
             E[j + 1] = eij;
             f -= gape; if (f < h - gapoe) f = h - gapoe; if (f < 0) f = 0;
@@ -282,6 +295,14 @@ int orc_ksw_ll(int qlen, const uint8_t *query, int tlen, const uint8_t *target,
         if (imax > gmax) gmax = imax, gte = i, gqe = iqe;
     }
     free(H); free(E);
+    {
+#pragma omp atomic
+        ++orc_dev[7];
+    }
+    if (best > 0 && n_best > 1) {
+#pragma omp atomic
+        ++orc_dev[3];
+    }
     if (qe_) *qe_ = gqe;
     if (te_) *te_ = gte;
     return gmax;

@@ -63,6 +63,14 @@ typedef struct {
     int32_t mid_occ, n_keys;
 } idx_t;
 
+int64_t orc_dev[8];
+void orc_dev_counters(int64_t out[8], int reset)
+{
+    int i;
+    for (i = 0; i < 8; ++i) { if (out) out[i] = orc_dev[i]; if (reset) orc_dev[i] = 0; }
+}
+#define DEV_COUNT(k) do { _Pragma("omp atomic") ++orc_dev[k]; } while (0)
+
 static void idx_build(idx_t *mi, const orc_opt_t *opt, const uint8_t *seq, int32_t len)
 {
     int64_t cap = len + 16, n, i;
@@ -85,8 +93,10 @@ static void idx_build(idx_t *mi, const orc_opt_t *opt, const uint8_t *seq, int32
         free(fill);
     }
     for (i = 0; i < nb; ++i)            /* worker_post: radix_sort_128x per bucket */
-        if (mi->boff[i + 1] - mi->boff[i] > 1)
+        if (mi->boff[i + 1] - mi->boff[i] > 1) {
+            if (mi->boff[i + 1] - mi->boff[i] > 64) DEV_COUNT(4);
             orc_radix_sort_128x(mi->a + mi->boff[i], mi->a + mi->boff[i + 1]);
+        }
     free(x); free(y);
     /* mm_idx_cal_max_occ + mm_mapopt_update */
     {
@@ -167,7 +177,7 @@ static orc128_t *collect_seed_hits(const idx_t *mi, int qlen, int64_t n_mz, cons
     for (i = 0; i < n_mz; ++i) {
         int t;
         idx_get(mi, mx[i] >> 8, &t);
-        if (t > mi->mid_occ) continue;      /* flt (deviation (1): no mm_seed_select rescue) */
+        if (t > mi->mid_occ) { DEV_COUNT(0); continue; }      /* flt (deviation (1): no mm_seed_select rescue) */
         cap += t;
     }
     a = (orc128_t *)malloc((size_t)(cap + 1) * 16);
@@ -427,6 +437,7 @@ static orc128_t *lchain_rmq(int max_dist, int max_dist_inner, int bw, int max_ch
             int32_t lo_y = (int32_t)a[i].y - max_dist, hi_y = (int32_t)a[i].y;
             int64_t best = -1;
             double best_pri = 0.0;
+            int tied = 0;
             for (j = st < i0 ? st : i0; j < i0; ++j) {
                 int32_t yj = (int32_t)a[j].y;
                 double pri;
@@ -434,12 +445,15 @@ static orc128_t *lchain_rmq(int max_dist, int max_dist_inner, int bw, int max_ch
                 if (yj < lo_y || (yj == lo_y && j < INT32_MAX)) continue;
                 if (yj > hi_y || (yj == hi_y && j > 0)) continue;
                 pri = -(f[j] + 0.5 * chn_pen_gap * ((int32_t)a[j].x + (int32_t)a[j].y));
+                if (best >= 0 && pri == best_pri) tied = 1; else if (best < 0 || pri < best_pri) tied = 0;
                 if (best < 0 || pri < best_pri ||
                     (pri == best_pri && (yj > (int32_t)a[best].y || (yj == (int32_t)a[best].y && j > best))))
                     best = j, best_pri = pri;
             }
             if (best >= 0) {
                 int32_t sc, exact, width, n_skip = 0;
+                DEV_COUNT(6);
+                if (tied) DEV_COUNT(1);
                 j = best;
                 sc = f[j] + comput_sc_simple(&a[i], &a[j], chn_pen_gap, chn_pen_skip, &exact, &width);
                 if (width <= bw && sc > max_f) max_f = sc, max_j = j;

@@ -43,6 +43,7 @@ typedef struct telr_synth_out {
     int32_t *contig_len, *te_start, *te_end;
     float *truth_af;
     int32_t *read_truth;       /* 1 = TE-bearing read */
+    int32_t *read_origin;      /* [n_reads][4]: start on its haplotype, source length, reverse-complemented, context length (haplotype coordinate of the breakpoint) */
 } telr_synth_out;
 
 typedef struct { uint64_t s[4]; } rng_t;
@@ -149,7 +150,7 @@ static void mutate(rng_t *r, const telr_synth_cfg *c, const uint8_t *src, int32_
 
 typedef struct {
     bytes_t seq;             /* all reads of the locus concatenated (nt4) then nothing else */
-    int32_t *rlen, *rtruth; int32_t n_reads, m_reads;
+    int32_t *rlen, *rtruth, *rorig; int32_t n_reads, m_reads;
     uint8_t *contig; int32_t clen, te_s, te_e;
     float af;
     uint32_t *p2, *pn; int64_t pbases;   /* the locus packed on its own (contig, then reads; 64-base aligned): keeps the peak footprint at 0.375 B/base */
@@ -197,7 +198,7 @@ static void gen_locus(const telr_synth_cfg *c, const te_t *fam, int32_t gid, loc
     int32_t nr = rng_poisson(&r, lam);
     if (nr < 1) nr = 1;
     o->n_reads = 0; o->m_reads = nr;
-    o->rlen = (int32_t *)malloc((size_t)nr * 4); o->rtruth = (int32_t *)malloc((size_t)nr * 4);
+    o->rlen = (int32_t *)malloc((size_t)nr * 4); o->rtruth = (int32_t *)malloc((size_t)nr * 4); o->rorig = (int32_t *)malloc((size_t)nr * 16);
     memset(&o->seq, 0, sizeof(o->seq));
     double mu_ln = log(c->mean_len) - 0.5 * c->sigma_len * c->sigma_len;
     uint8_t *tmp = (uint8_t *)malloc((size_t)c->max_len + 16);
@@ -230,6 +231,7 @@ static void gen_locus(const telr_synth_cfg *c, const te_t *fam, int32_t gid, loc
         if (o->seq.n == n0) bpush(&o->seq, 0);
         o->rlen[o->n_reads] = (int32_t)(o->seq.n - n0);
         o->rtruth[o->n_reads] = has_te;
+        o->rorig[4 * o->n_reads] = start; o->rorig[4 * o->n_reads + 1] = len; o->rorig[4 * o->n_reads + 2] = rc; o->rorig[4 * o->n_reads + 3] = ctx;
         o->n_reads++;
     }
     free(tmp); free(alt); free(ref);
@@ -315,6 +317,7 @@ static int synth_generate(const telr_synth_cfg *c, int32_t first_locus, const in
     out->read_len = (int32_t *)malloc((size_t)(nr + 1) * 4);
     out->read_hash = (uint32_t *)malloc((size_t)(nr + 1) * 4);
     out->read_truth = (int32_t *)malloc((size_t)(nr + 1) * 4);
+    out->read_origin = (int32_t *)malloc((size_t)(nr + 1) * 16);
     out->locus_read_begin = (int32_t *)malloc((size_t)(n_loci + 1) * 4);
     out->contig_off = (int64_t *)malloc((size_t)(n_loci + 1) * 8);
     out->contig_len = (int32_t *)malloc((size_t)(n_loci + 1) * 4);
@@ -336,6 +339,7 @@ static int synth_generate(const telr_synth_cfg *c, int32_t first_locus, const in
             snprintf(name, sizeof(name), "L%06d_R%04d", GID(l), k);
             out->read_off[ri] = off; out->read_len[ri] = L[l].rlen[k];
             out->read_hash[ri] = x31(name); out->read_truth[ri] = L[l].rtruth[k];
+            memcpy(out->read_origin + 4 * (size_t)ri, L[l].rorig + 4 * k, 16);
             off += ((int64_t)L[l].rlen[k] + 63) / 64 * 64;
             ++ri;
         }
@@ -345,7 +349,7 @@ static int synth_generate(const telr_synth_cfg *c, int32_t first_locus, const in
     for (int32_t l = 0; l < n_loci; ++l) {
         memcpy(out->seq2 + loff[l] / 16, L[l].p2, (size_t)(L[l].pbases / 16) * 4);
         memcpy(out->nmask + loff[l] / 32, L[l].pn, (size_t)(L[l].pbases / 32) * 4);
-        free(L[l].p2); free(L[l].pn); free(L[l].rlen); free(L[l].rtruth);
+        free(L[l].p2); free(L[l].pn); free(L[l].rlen); free(L[l].rtruth); free(L[l].rorig);
     }
 #undef GID
     free(loff); free(L);
@@ -356,7 +360,7 @@ static int synth_generate(const telr_synth_cfg *c, int32_t first_locus, const in
 
 void telr_synth_free(telr_synth_out *o)
 {
-    free(o->seq2); free(o->nmask); free(o->read_off); free(o->read_len); free(o->read_hash); free(o->read_truth);
+    free(o->seq2); free(o->nmask); free(o->read_off); free(o->read_len); free(o->read_hash); free(o->read_truth); free(o->read_origin);
     free(o->locus_read_begin); free(o->contig_off); free(o->contig_len); free(o->te_start); free(o->te_end);
     free(o->truth_af);
     memset(o, 0, sizeof(*o));

@@ -35,7 +35,7 @@ class SynthOut(C.Structure):
         ("read_hash", C.POINTER(C.c_uint32)), ("locus_read_begin", C.POINTER(C.c_int32)),
         ("contig_off", C.POINTER(C.c_int64)), ("contig_len", C.POINTER(C.c_int32)),
         ("te_start", C.POINTER(C.c_int32)), ("te_end", C.POINTER(C.c_int32)),
-        ("truth_af", C.POINTER(C.c_float)), ("read_truth", C.POINTER(C.c_int32)),
+        ("truth_af", C.POINTER(C.c_float)), ("read_truth", C.POINTER(C.c_int32)), ("read_origin", C.POINTER(C.c_int32)),
     ]
 
 
@@ -109,7 +109,8 @@ def generate(name: str, first_locus: int = 0, n_loci: int | None = None, total_l
             arr(out.locus_read_begin, nl + 1, np.int32), arr(out.contig_off, nl, np.int64),
             arr(out.contig_len, nl, np.int32), arr(out.te_start, nl, np.int32), arr(out.te_end, nl, np.int32),
             meta={"config": name, "first_locus": first_locus,
-                  "truth_af": arr(out.truth_af, nl, np.float32), "read_truth": arr(out.read_truth, nr, np.int32)},
+                  "truth_af": arr(out.truth_af, nl, np.float32), "read_truth": arr(out.read_truth, nr, np.int32),
+                  "read_origin": arr(out.read_origin, 4 * nr, np.int32).reshape(-1, 4)},
         )
     finally:
         _lib().telr_synth_free(C.byref(out))

@@ -364,13 +364,33 @@ def test_chunking_and_rerun_are_identical(built, monkeypatch):
     c1.close(); c2.close()
 
 
-def test_full_size_one_chunk_equals_many(built, monkeypatch):
-    """BASELINE.json configs[1] at its full size (3000 loci, 1.8 Gbase): the default single 1.8-Gbase chunk and 384-Mbase chunks
-    give the same coverage integers, AF values and DP cell count (guards the 64-bit offsets of the large-chunk layout)."""
+@pytest.fixture(scope="module")
+def full_config2(built):
+    """BASELINE.json configs[1] at its full size (3000 loci, 1.8 Gbase) through the default chunking, run once per session."""
     b = synth.generate("ont_3k_50x", 0, 3000)
-    c1 = lib.Context(0)
-    r1 = c1.run(b)
-    c1.close()
+    c = lib.Context(0)
+    r = c.run(b)
+    c.close()
+    return b, r
+
+
+def _random_sample_vs_oracle(b, r, n, seed):
+    """`n` random loci of a full-size GPU result against the oracle run on exactly those loci (coverage integers bit-exact,
+    AF within 1e-9 relative): large-offset paths (64-bit arenas, 0.9-Gbase chunks) checked against the CPU restatement."""
+    idx = np.sort(np.random.default_rng(seed).choice(b.n_loci, n, replace=False))
+    ro = orc.af_run(b.subset(idx), threads=0, want_depth=False, want_aln=False)
+    bad = np.nonzero((r.cov2x[idx] != ro.cov2x).any(1))[0]
+    assert len(bad) == 0, (idx[bad][:5], r.cov2x[idx[bad]][:5], ro.cov2x[bad][:5])
+    ga = r.af[idx]
+    assert np.array_equal(np.isnan(ga), np.isnan(ro.af))
+    ok = ~np.isnan(ro.af)
+    assert np.all(np.abs(ga[ok] - ro.af[ok]) <= 1e-9 * np.abs(ro.af[ok]))
+
+
+def test_full_size_one_chunk_equals_many(full_config2, monkeypatch):
+    """Full config 2: the default chunking and 384-Mbase chunks give the same coverage integers, AF values and DP cell count
+    (guards the 64-bit offsets of the large-chunk layout)."""
+    b, r1 = full_config2
     monkeypatch.setenv("TELR_CHUNK_MBASES", "384")
     c2 = lib.Context(0)
     r2 = c2.run(b)
@@ -379,6 +399,60 @@ def test_full_size_one_chunk_equals_many(built, monkeypatch):
     assert np.array_equal(r1.af, r2.af, equal_nan=True)
     ok = ~np.isnan(r1.af)
     assert ok.mean() > 0.8 and np.abs(np.minimum(r1.af[ok], 1) - b.meta["truth_af"][ok]).mean() < 0.12
+
+
+def test_full_size_random_sample_matches_oracle_config2(full_config2):
+    b, r = full_config2
+    _random_sample_vs_oracle(b, r, 200, 20221103)
+
+
+def test_full_size_random_sample_matches_oracle_config4(built):
+    """BASELINE.json configs[3] at its full size (30 000 loci, 10.8 Gbase, the north-star batch) on one GPU: 200 random loci
+    of the result against the oracle."""
+    b = synth.generate("ont_30k_30x", 0, 30000)
+    c = lib.Context(0)
+    r = c.run(b)
+    c.close()
+    assert (r.cov2x[:, 0] != -2).all()
+    _random_sample_vs_oracle(b, r, 200, 20221105)
+    ok = ~np.isnan(r.af)
+    assert ok.mean() > 0.8 and np.abs(np.minimum(r.af[ok], 1) - b.meta["truth_af"][ok]).mean() < 0.15
+
+
+@pytest.mark.parametrize("cfg", ["ont_3k_50x", "clr_3k_40x", "hifi_3k_40x"])
+def test_reads_align_to_their_simulated_origin(ctx, cfg):
+    """Truth check independent of the oracle: the primary alignment of a simulated read on the forward contig lies on the
+    stretch of the contig the read was drawn from, on the strand it was drawn from (>= 99 % of the reads that share
+    at least 500 bases with the contig)."""
+    b = synth.generate(cfg, 40, 40)
+    r = ctx.run(b, want_aln=True)
+    org = b.meta["read_origin"]
+    locus_of_read = np.repeat(np.arange(b.n_loci), np.diff(b.locus_read_begin))
+    prim = {}
+    for a in r.alns:
+        if a["strand"] == 0 and (a["flag"] & 0x900) == 0:
+            prim[int(a["read"])] = a
+    n_exp = n_ok = 0
+    for rd in range(b.n_reads):
+        l = locus_of_read[rd]
+        L, ts, te = int(b.contig_len[l]), int(b.te_start[l]), int(b.te_end[l])
+        start, ln, rc, ctx_len = (int(v) for v in org[rd])
+        has_te = int(b.meta["read_truth"][rd])
+        # haplotype coordinates -> forward-contig coordinates (polishing indels move them by a few bases at most)
+        if has_te:
+            segs = [(start - ctx_len + ts, start + ln - ctx_len + ts)]
+        else:
+            segs = [(start - ctx_len + ts, min(start + ln, ctx_len) - ctx_len + ts), (max(start, ctx_len) - ctx_len + te, start + ln - ctx_len + te)]
+        segs = [(max(s, 0), min(e, L)) for s, e in segs]
+        segs = [(s, e) for s, e in segs if e - s >= 500]
+        if not segs:
+            continue
+        n_exp += 1
+        a = prim.get(rd)
+        if a is None or int(a["rev"]) != rc:
+            continue
+        n_ok += any(min(int(a["re"]), e) - max(int(a["rs"]), s) >= 0.8 * min(e - s, int(a["re"]) - int(a["rs"])) for s, e in segs)
+    assert n_exp > 0.8 * b.n_reads and n_ok >= 0.99 * n_exp, (n_ok, n_exp, b.n_reads)
 
 
 def test_get_af_dropin(built, tmp_path):
