@@ -81,7 +81,13 @@ struct AlignArgs {
     int64_t *prob_blk_off; int32_t *prob_blk_cnt;
     int32_t *aln_out; unsigned long long *n_aln; int64_t aln_cap;
     uint32_t *cig_out; unsigned long long *n_cig; int64_t cig_out_cap;
+    // task queues of k_al_queue: one ring per role (0 gap fills, 1 everything else, 2 gap fills of the 12-column instance), entries = work item + 1
+    int32_t *q_ring[3]; int32_t q_cap; int32_t ext_per8, wide_per8;
+    int32_t *q_state;            // AQ_* counters
 };
+constexpr int AQ_ROLES = 3;
+constexpr int AQ_MAX_SM = 1024;        // per-SM role words follow the counters in q_state
+enum { AQ_HEAD0 = 0, AQ_TAIL0 = 3, AQ_AVAIL0 = 6, AQ_DONE = 9, AQ_START = 10, AQ_STEAL = 11, AQ_SLOTS = 16 };
 
 __device__ __forceinline__ int dp_base(const uint8_t *p, int step, int comp, int i)
 {
@@ -510,9 +516,9 @@ __device__ int fill_batch_run(const Opt &o, const FillLut &L, const AlnCtx &c, c
 // coroutine + DP + traceback for one problem per warp (persistent warps, dynamic queue, no global barriers).
 // The coroutine state lives in shared memory while the warp owns the problem and is written back for k_al_finish.
 #if TELR_FILL_STREAM
-struct AlWarpSmem { AlnCtx c; DpTask task; DpRes res; int more; FillJob jobs[FB_MAX]; int n_jobs, job_next; uint8_t b2j[FB_MAX_BLOCKS]; };
+struct AlWarpSmem { AlnCtx c; DpTask task; DpRes res; int more, role; FillJob jobs[FB_MAX]; int n_jobs, job_next; uint8_t b2j[FB_MAX_BLOCKS]; };
 #else
-struct AlWarpSmem { AlnCtx c; DpTask task; DpRes res; int more; };
+struct AlWarpSmem { AlnCtx c; DpTask task; DpRes res; int more, role; };
 #endif
 
 __global__ void __launch_bounds__(AL_THREADS, AL_BLOCKS_PER_SM) k_al_fused(const __grid_constant__ AlignArgs A)
@@ -672,6 +678,233 @@ __global__ void __launch_bounds__(AL_THREADS, AL_BLOCKS_PER_SM) k_al_fused(const
             for (int i = lane; i < (int)(sizeof(AlnCtx) / 4); i += 32) dst[i] = src[i];
         }
         __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Task-type-specialised form of the same kernel.  k_al_fused lets every warp run whatever its read needs next, so the 16 warps
+// of an SM sit in different loops and the hot code (fill forward 14 KB + fill traceback 7 KB + windowed DP 13 KB) sits at the
+// 32 KB instruction-cache capacity; every specialised loop body added to it made the whole kernel slower (profiles/README.md).
+// Here an SM has a ROLE -- gap fills, or everything else (extensions, exact re-runs, local probes) -- and the problems move
+// between the roles through two device-wide rings: a warp executes the pending DP request of a problem, advances the
+// problem's coroutine (its state lives in global memory between visits), keeps the problem while the next request belongs to
+// its own role, and otherwise publishes it on the other role's ring.  A problem is in at most one ring at a time, so a ring of
+// n_work + 1 slots can never overflow.  Workers whose ring is empty start fresh problems (longest read first), then help the
+// other role; the kernel ends when every problem has finished.  No global barrier anywhere.
+__device__ __forceinline__ int aq_role_of(const AlignArgs &A, const DpTask &T)
+{
+    if (!(T.kind == 0 && A.use_fast && fill_fast_ok(T))) return 1;
+#if TELR_FILL_FC12
+    if (A.wide_per8 > 0 && fill_width(T.tlen) == 12) return 2;         // 257..384 target columns: one pass of the 12-column instance, on its own SMs
+#endif
+    return 0;
+}
+
+// lane 0 only.  The caller has written the problem's state to global memory (all lanes) and synchronised the warp.
+__device__ __forceinline__ void aq_push(const AlignArgs &A, int role, int wi)
+{
+    __threadfence();                                                     // release: state before the ring entry
+    const unsigned t = (unsigned)atomicAdd(&A.q_state[AQ_TAIL0 + role], 1);
+    atomicExch(&A.q_ring[role][t % (unsigned)A.q_cap], wi + 1);
+    atomicAdd(&A.q_state[AQ_AVAIL0 + role], 1);
+}
+// lane 0 only; -1 when the ring is empty
+__device__ __forceinline__ int aq_pop(const AlignArgs &A, int role)
+{
+    if (*(volatile int32_t *)&A.q_state[AQ_AVAIL0 + role] <= 0) return -1;
+    if (atomicSub(&A.q_state[AQ_AVAIL0 + role], 1) <= 0) { atomicAdd(&A.q_state[AQ_AVAIL0 + role], 1); return -1; }
+    const unsigned h = (unsigned)atomicAdd(&A.q_state[AQ_HEAD0 + role], 1);
+    int32_t *slot = &A.q_ring[role][h % (unsigned)A.q_cap];
+    int v;
+    while ((v = atomicExch(slot, 0)) == 0) __nanosleep(32);               // its pusher holds the ticket and is about to write
+    return v - 1;
+}
+
+#if TELR_FILL_STREAM
+#define AQ_FLUT_PARAM , const FillLut &flut
+#define AQ_FLUT_ARG , flut
+#else
+#define AQ_FLUT_PARAM
+#define AQ_FLUT_ARG
+#endif
+__device__ __forceinline__ void aq_exec(const AlignArgs &A, const Opt &o, AlWarpSmem &W, DpScratch &S, uint8_t *own_dir, VecSmem &vs AQ_FLUT_PARAM)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+#if TELR_FILL_STREAM
+    if (W.task.kind == 0 && A.fill_batch && A.use_fast && fill_fast_ok(W.task)) {
+        // the pending batch holds this very fill?  otherwise start a new batch with it
+        int hit = -1;
+        if (W.job_next < W.n_jobs) {
+            const FillJob &J = W.jobs[W.job_next];
+            if (J.q == W.task.q && J.t == W.task.t && J.qlen == W.task.qlen && J.tlen == W.task.tlen) hit = W.job_next;
+        }
+        if (hit < 0) {
+            const int n = fill_batch_run(o, flut, W.c, W.task, W.jobs, A.fill_batch, own_dir, A.dir_cap, S.bnd, reinterpret_cast<uint32_t *>(vs.st), (int)(sizeof(vs.st) / 12), W.b2j);
+            if (lane == 0) { W.n_jobs = n; W.job_next = 0; }
+            __syncwarp();
+            hit = n > 0 ? 0 : -1;
+        }
+        if (hit >= 0) {
+            const FillJob &J = W.jobs[hit];
+            if (lane == 0) {
+                res_reset(W.res); W.res.score = J.score;
+                atomicAdd(A.stat_cells, (unsigned long long)J.qlen * (unsigned long long)J.tlen);
+            }
+            __syncwarp();
+            fill_traceback(W.task, W.res, J.dir, S.ezcig, S.ezcap, A.err, *reinterpret_cast<TbSmem *>(vs.H));
+            if (lane == 0) W.job_next = hit + 1;
+            __syncwarp();
+            return;
+        }
+    }
+    if (lane == 0) W.n_jobs = 0;        // anything else invalidates what was computed ahead
+    __syncwarp();
+#endif
+    if (W.task.kind == 0) {
+        const bool fast = A.use_fast && fill_fast_ok(W.task);
+        const int64_t need = fast ? (int64_t)W.task.qlen * fill_stride(W.task.tlen) : vec_dir_bytes(W.task.qlen, W.task.tlen, W.task.w);
+        int big_slot = -1;
+        S.dir = own_dir; S.dir_cap = A.dir_cap;
+        if (need > A.dir_cap && need <= A.big_cap && A.n_big > 0) {
+            if (lane == 0) {        // take one of the shared large traceback buffers (holders never wait on anything)
+                unsigned ns = 64;
+                for (int sl = (blockIdx.x * AL_WARPS + (threadIdx.x >> 5)) % A.n_big;; sl = (sl + 1) % A.n_big) {
+                    if (atomicCAS(&A.big_lock[sl], 0, 1) == 0) { big_slot = sl; break; }
+                    __nanosleep(ns);
+                    if (ns < 4096) ns <<= 1;
+                }
+                __threadfence();
+            }
+            big_slot = __shfl_sync(FULL, big_slot, 0);
+            S.dir = A.big + (int64_t)big_slot * A.big_cap; S.dir_cap = A.big_cap;
+        }
+        bool done_fast = false;
+        if (fast && need <= S.dir_cap) done_fast = warp_fill_fast(o, W.task, W.res, S.dir, S.bnd, A.stat_cells, A.wide_per8 > 0);
+        int vec = 0;
+        if (!done_fast) vec = warp_extd2(o, W.task, W.res, S, A.stat_cells, A.err);
+        __syncwarp();
+        if (done_fast) fill_traceback(W.task, W.res, S.dir, S.ezcig, S.ezcap, A.err, *reinterpret_cast<TbSmem *>(vs.H));
+        if (lane == 0) {
+            if (!done_fast) { if (vec) extd2_traceback_vec(W.task, W.res, S.dir, S.ezcig, S.ezcap, A.err); else extd2_traceback(W.task, W.res, S.dir, S.ezcig, S.ezcap, A.err); }
+            if (big_slot >= 0) { __threadfence(); atomicExch(&A.big_lock[big_slot], 0); }
+        }
+    } else {
+        warp_ll(o, W.task, W.res, S, A.stat_cells);
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(AL_THREADS, AL_BLOCKS_PER_SM) k_al_queue(const __grid_constant__ AlignArgs A)
+{
+    __shared__ AlWarpSmem WS[AL_WARPS];
+    __shared__ uint2 stab[256];
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    VecSmem *DS = reinterpret_cast<VecSmem *>(dyn_smem);
+    const Opt &o = A.o;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned FULL = 0xffffffffu;
+    AlWarpSmem &W = WS[wid];
+    uint8_t *base = A.warp_scratch + (size_t)(blockIdx.x * AL_WARPS + wid) * A.warp_scratch_stride;
+    const size_t maxT = ((size_t)A.max_tlen + 64) & ~(size_t)15;
+    DpScratch S;
+    S.u = (int8_t *)base; base += maxT; S.v = (int8_t *)base; base += maxT; S.x = (int8_t *)base; base += maxT;
+    S.y = (int8_t *)base; base += maxT; S.x2 = (int8_t *)base; base += maxT; S.y2 = (int8_t *)base; base += maxT;
+    S.H = (int32_t *)base; base += maxT * 4;
+    S.ll = (int32_t *)base; base += maxT * 4 * 6;
+    S.bnd = (uint32_t *)base; base += (((size_t)A.max_qlen + 64) & ~(size_t)15) * 6;
+    base = (uint8_t *)(((uintptr_t)base + 255) & ~(uintptr_t)255);
+    uint8_t *own_dir = base;
+    S.s_state = nullptr; S.s_H = nullptr; S.vsm = A.use_vec ? &DS[wid] : nullptr; S.stab = stab;
+    vec_fill_stab(stab, o);
+#if TELR_FILL_STREAM
+    __shared__ FillLut flut;
+    fill_lut_init(flut, o);
+#endif
+    unsigned smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    // The role belongs to the SM (all its warps run one loop); it starts from a fixed interleave and MOVES when the SM's ring
+    // runs dry: a warp that finds neither work for its role nor a fresh problem re-assigns its SM to the role with the longest
+    // backlog, so any mix of fills and extensions (presets, coverage, read lengths) balances itself without two loops sharing
+    // an instruction cache for longer than the hand-over.
+    int32_t *sm_role = A.q_state + AQ_SLOTS + (smid & (AQ_MAX_SM - 1));
+    if (threadIdx.x == 0)
+        atomicCAS(sm_role, 0, 1 + ((int)(smid & 7u) < A.ext_per8 ? 1 : (int)(smid & 7u) < A.ext_per8 + A.wide_per8 ? 2 : 0));
+    __syncthreads();
+    unsigned idle_ns = 64;
+    for (;;) {
+        // ---- take a problem: the SM's ring, then a fresh problem, then move the SM to the longest ring ----
+        int wi = -1, fresh = 0;
+        if (lane == 0) {
+            int role = *(volatile int32_t *)sm_role - 1;
+            wi = aq_pop(A, role);
+            if (wi < 0 && *(volatile int32_t *)&A.q_state[AQ_START] < A.n_work) {
+                const int t = atomicAdd(&A.q_state[AQ_START], 1);
+                if (t < A.n_work) { wi = t; fresh = 1; }
+            }
+            if (wi < 0) {
+                int best = -1, best_n = 0;
+                for (int r = 0; r < AQ_ROLES; ++r) {
+                    const int n = *(volatile int32_t *)&A.q_state[AQ_AVAIL0 + r];
+                    if (r != role && n > best_n) best = r, best_n = n;
+                }
+                if (best >= 0) {
+                    wi = aq_pop(A, best);
+                    if (wi >= 0) { atomicExch(sm_role, best + 1); atomicAdd(&A.q_state[AQ_STEAL], 1); role = best; }
+                }
+            }
+            if (wi < 0 && *(volatile int32_t *)&A.q_state[AQ_DONE] >= A.n_work) wi = -2;
+            if (wi >= 0 && !fresh) __threadfence();                     // acquire: the previous owner's writes
+            W.role = role;
+        }
+        wi = __shfl_sync(FULL, wi, 0); fresh = __shfl_sync(FULL, fresh, 0);
+        if (wi == -2) break;
+        if (wi < 0) { __nanosleep(idle_ns); if (idle_ns < 2048) idle_ns <<= 1; continue; }
+        idle_ns = 64;
+        {   // coroutine state (and, for a queued problem, its pending request): global -> shared
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(&A.actx[wi]);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(&W.c);
+            for (int i = lane; i < (int)(sizeof(AlnCtx) / 4); i += 32) dst[i] = __ldcg(src + i);
+            if (!fresh) {
+                const uint32_t *ts = reinterpret_cast<const uint32_t *>(&A.tasks[wi]);
+                uint32_t *td = reinterpret_cast<uint32_t *>(&W.task);
+                for (int i = lane; i < (int)(sizeof(DpTask) / 4); i += 32) td[i] = __ldcg(ts + i);
+            }
+        }
+        if (lane == 0) { res_reset(W.res); W.res.cigar = A.cigs + A.work[wi].ez_off; }
+#if TELR_FILL_STREAM
+        if (lane == 0) { W.n_jobs = 0; W.job_next = 0; }
+#endif
+        S.ezcig = A.cigs + A.work[wi].ez_off; S.ezcap = A.work[wi].ez_cap;
+        __syncwarp();
+        int have_task = !fresh;
+        for (;;) {
+            if (have_task) aq_exec(A, o, W, S, own_dir, DS[wid] AQ_FLUT_ARG);
+            if (lane == 0) {
+                W.more = aln_next(W.c, W.res, W.task) ? 1 : 0;
+                if (W.more) W.more = 1 + aq_role_of(A, W.task);
+            }
+            __syncwarp();
+            const int more = W.more;
+            if (more && more - 1 == W.role) { have_task = 1; continue; }
+            {   // the problem leaves this warp: coroutine state (and the request it waits for) shared -> global
+                uint32_t *dst = reinterpret_cast<uint32_t *>(&A.actx[wi]);
+                const uint32_t *src = reinterpret_cast<const uint32_t *>(&W.c);
+                for (int i = lane; i < (int)(sizeof(AlnCtx) / 4); i += 32) dst[i] = src[i];
+                if (more) {
+                    uint32_t *td = reinterpret_cast<uint32_t *>(&A.tasks[wi]);
+                    const uint32_t *ts = reinterpret_cast<const uint32_t *>(&W.task);
+                    for (int i = lane; i < (int)(sizeof(DpTask) / 4); i += 32) td[i] = ts[i];
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                if (more) aq_push(A, more - 1, wi);
+                else { __threadfence(); atomicAdd(&A.q_state[AQ_DONE], 1); }
+            }
+            __syncwarp();
+            break;
+        }
     }
 }
 

@@ -18,6 +18,9 @@
 
 namespace telr {
 
+#ifndef TELR_FILL_FC12
+#define TELR_FILL_FC12 1
+#endif
 constexpr int FC_MAX = 12;            // columns per lane: 8 (256-column passes) or 12 (384-column passes)
 
 // prmt.b32 in default mode: selector nibble bit 3 replicates the sign of the selected byte (__byte_perm drops that bit)
@@ -215,7 +218,7 @@ __device__ void warp_fill_fwd(const Opt &o, const DpTask &T, DpRes &R, uint8_t *
 }
 
 // forward pass; returns false (nothing written) when an ambiguous base is present
-__device__ bool warp_fill_fast(const Opt &o, const DpTask &T, DpRes &R, uint8_t *dir, uint32_t *bnd, unsigned long long *cells_acc)
+__device__ bool warp_fill_fast(const Opt &o, const DpTask &T, DpRes &R, uint8_t *dir, uint32_t *bnd, unsigned long long *cells_acc, bool wide_ok = false)
 {
     const int lane = threadIdx.x & 31;
     {   // ambiguous bases take the general path (their score is not match/mismatch)
@@ -225,12 +228,13 @@ __device__ bool warp_fill_fast(const Opt &o, const DpTask &T, DpRes &R, uint8_t 
         if (__any_sync(0xffffffffu, n)) return false;
     }
     if (o.a > 127 || o.b > 127) return false;            // score tables are int8
-#if defined(TELR_FILL_FC12) && TELR_FILL_FC12
-    if (fill_width(T.tlen) == 12) warp_fill_fwd<12>(o, T, R, dir, bnd, cells_acc);
+#if TELR_FILL_FC12
+    // the 12-column instance halves the passes of 257..384-column fills but doubles the hot code: it pays only where it has SMs
+    // of its own (k_al_queue, role 2); sharing an instruction cache with the 8-column instance it costs 35 % (profiles/README.md)
+    if (wide_ok && fill_width(T.tlen) == 12) warp_fill_fwd<12>(o, T, R, dir, bnd, cells_acc);
     else
 #endif
-    warp_fill_fwd<8>(o, T, R, dir, bnd, cells_acc);     // a second instantiation (12 columns per lane) halves the passes of 257..384-column fills but
-                                                         // doubles the hot code: measured slower end to end (instruction-cache misses), so it stays off
+    warp_fill_fwd<8>(o, T, R, dir, bnd, cells_acc);
     return true;
 }
 

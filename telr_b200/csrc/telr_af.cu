@@ -66,6 +66,12 @@ struct telr_af_ctx {
     DevBuf b_tfirst, b_tcnt, b_toff, b_tmpx, b_tmpy;     // tile sketch: first tile per sequence, per-tile counts/offsets, per-tile slots
     int sketch_tiles = 1;
     int fill_batch = 0;                  // -DTELR_FILL_STREAM=1 builds: gap fills of a read computed ahead as one systolic stream (TELR_FILL_BATCH)
+    // TELR_AL_QUEUE=1 selects the role-specialised alignment kernel k_al_queue (ext_per8 / wide_per8: eighths of the SMs that start in the
+    // extension role / the 12-column gap-fill role).  Measured (profiles/README.md, round 2): it removes the instruction-cache penalty of extra
+    // loop bodies as designed, but end to end it is within +-1.5 % of k_al_fused on map-ont and 18 % slower on map-pb / map-hifi, so the
+    // fused kernel stays the default.
+    int al_queue = 0, ext_per8 = 2, wide_per8 = 2;
+    DevBuf b_qring, b_qstate;
     int al_blocks = AL_BLOCKS_PER_SM;    // resident k_al_fused CTAs per SM this context asks for (fewer leaves room for a second context's kernels)
     DevBuf b_rbytes, b_rboff, b_alwork, b_alctx, b_altask, b_alres, b_alsz, b_aloff, b_cigs, b_pool, b_tlist, b_rc, b_opt, b_idxbig;
     int64_t pool_cap = (int64_t)6144 << 20;
@@ -520,8 +526,18 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
         CK(cudaMemsetAsync(ctx->b_rc.p, 0, 1024, st));
         { ++ctx->launches; k_al_offsets<<<tb, 128, 0, st>>>(aa, ctx->b_aloff.as<int64_t>()); }
         { ++ctx->launches; k_al_init<<<tb, 128, 0, st>>>(aa); }
-        CK(cudaFuncSetAttribute(k_al_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(AL_WARPS * sizeof(VecSmem))));
-        { ++ctx->launches; k_al_fused<<<al_grid, AL_THREADS, AL_WARPS * sizeof(VecSmem), st>>>(aa); }
+        if (ctx->al_queue) {
+            aa.q_cap = n_work + 1; aa.ext_per8 = ctx->ext_per8; aa.wide_per8 = ctx->wide_per8;
+            ENS(ctx->b_qring, (size_t)AQ_ROLES * aa.q_cap * 4); ENS(ctx->b_qstate, (AQ_SLOTS + AQ_MAX_SM) * 4);
+            CK(cudaMemsetAsync(ctx->b_qring.p, 0, (size_t)AQ_ROLES * aa.q_cap * 4, st));
+            CK(cudaMemsetAsync(ctx->b_qstate.p, 0, (AQ_SLOTS + AQ_MAX_SM) * 4, st));
+            aa.q_ring[0] = ctx->b_qring.as<int32_t>(); aa.q_ring[1] = aa.q_ring[0] + aa.q_cap; aa.q_ring[2] = aa.q_ring[1] + aa.q_cap; aa.q_state = ctx->b_qstate.as<int32_t>();
+            CK(cudaFuncSetAttribute(k_al_queue, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(AL_WARPS * sizeof(VecSmem))));
+            { ++ctx->launches; k_al_queue<<<al_grid, AL_THREADS, AL_WARPS * sizeof(VecSmem), st>>>(aa); }
+        } else {
+            CK(cudaFuncSetAttribute(k_al_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(AL_WARPS * sizeof(VecSmem))));
+            { ++ctx->launches; k_al_fused<<<al_grid, AL_THREADS, AL_WARPS * sizeof(VecSmem), st>>>(aa); }
+        }
         { ++ctx->launches; k_al_regfin<<<std::max(1, std::min((n_work + 7) / 8, sm * 8)), 256, 0, st>>>(aa); }
         { ++ctx->launches; k_al_finish<<<tp_blocks<TP_FINISH>(n_work, 128), 128, 0, st>>>(aa); }
     }
@@ -736,6 +752,12 @@ int telr_af_create(telr_af_ctx **out, int device, size_t workspace_bytes)
     if (pm) ctx->pool_cap = (int64_t)atoll(pm) << 20;
     const char *dc = getenv("TELR_DIR_MB");
     if (dc) ctx->dir_cap = (int64_t)atoll(dc) << 20;
+    const char *aq = getenv("TELR_AL_QUEUE");
+    if (aq) ctx->al_queue = atoi(aq) ? 1 : 0;
+    const char *e8 = getenv("TELR_AL_EXT8");
+    if (e8 && atoi(e8) >= 0 && atoi(e8) <= 8) ctx->ext_per8 = atoi(e8);
+    const char *w8 = getenv("TELR_AL_WIDE8");
+    if (w8 && atoi(w8) >= 0 && atoi(w8) + ctx->ext_per8 <= 8) ctx->wide_per8 = atoi(w8);
     *out = ctx;
     return TELR_OK;
 }
@@ -751,7 +773,7 @@ int telr_af_destroy(telr_af_ctx *ctx)
                      &ctx->b_alws, &ctx->b_work, &ctx->b_blk, &ctx->b_pblkoff, &ctx->b_pblkcnt, &ctx->b_ctr, &ctx->b_alnout, &ctx->b_cigout, &ctx->b_doff, &ctx->b_grow, &ctx->b_lbad,
                      &ctx->b_big, &ctx->b_biglock, &ctx->b_rbytes, &ctx->b_rboff, &ctx->b_alwork, &ctx->b_alctx, &ctx->b_altask, &ctx->b_alres, &ctx->b_alsz, &ctx->b_aloff,
                      &ctx->b_cigs, &ctx->b_pool, &ctx->b_tlist, &ctx->b_rc, &ctx->b_opt, &ctx->b_idxbig, &ctx->b_psb, &ctx->b_psoff, &ctx->b_pscr, &ctx->b_pnu, &ctx->b_pm,
-                     &ctx->b_tfirst, &ctx->b_tcnt, &ctx->b_toff, &ctx->b_tmpx, &ctx->b_tmpy, &ctx->b_order, &ctx->b_wflag, &ctx->b_woff, &ctx->b_hpoff, &ctx->b_hpn};
+                     &ctx->b_tfirst, &ctx->b_tcnt, &ctx->b_toff, &ctx->b_tmpx, &ctx->b_tmpy, &ctx->b_order, &ctx->b_wflag, &ctx->b_woff, &ctx->b_hpoff, &ctx->b_hpn, &ctx->b_qring, &ctx->b_qstate};
     for (auto *b : all) b->release();
     for (auto &b : ctx->b_in) b.release();
     for (auto &e : ctx->ev) cudaEventDestroy(e);
@@ -1035,7 +1057,7 @@ extern "C" int telr_af_dp(telr_af_ctx *ctx, int32_t preset, int32_t n_tasks, con
     int maxQ = 0, maxT = 0;
     for (int i = 0; i < n_tasks; ++i) { maxQ = std::max(maxQ, tasks[i].qlen); maxT = std::max(maxT, tasks[i].tlen); }
     A.maxQ = (maxQ + 64) & ~15; A.maxT = (maxT + 64) & ~15; A.dir_cap = ctx->dir_cap;
-    A.use_fast = ctx->use_fast; A.use_vec = ctx->use_vec;
+    A.use_fast = ctx->use_fast ? (ctx->al_queue && ctx->wide_per8 > 0 ? 2 : 1) : 0; A.use_vec = ctx->use_vec;
     A.stride = ((size_t)A.maxT * (6 + 4 + 24) + (size_t)(A.maxQ + A.maxT) * 4 + (size_t)A.maxQ * 6 + 512 + (size_t)A.dir_cap + 255) & ~(size_t)255;
     const int grid = std::max(1, std::min((n_tasks + AL_WARPS - 1) / AL_WARPS, ctx->sm_count * AL_BLOCKS_PER_SM));
     ENS(ctx->b_alws, A.stride * (size_t)grid * AL_WARPS);

@@ -264,6 +264,22 @@ def test_full_pipeline_matches_oracle(ctx, cfg, n, kw):
     assert r.c.dp_cells == ro.c.dp_cells and r.c.n_anchors == ro.c.n_anchors
 
 
+@pytest.mark.parametrize("cfg,n,env", [("ont_3k_50x", 8, {"TELR_AL_QUEUE": "1"}), ("clr_3k_40x", 5, {"TELR_AL_QUEUE": "1", "TELR_AL_EXT8": "5", "TELR_AL_WIDE8": "0"}),
+                                       ("hifi_3k_40x", 5, {"TELR_AL_QUEUE": "1", "TELR_AL_EXT8": "0", "TELR_AL_WIDE8": "4"})])
+def test_role_specialised_alignment_kernel_matches_oracle(built, monkeypatch, cfg, n, env):
+    """k_al_queue (SM roles + device-wide task rings, optional: TELR_AL_QUEUE=1) gives the results of the default fused kernel:
+    every problem migrates between warps through global memory, the 12-column fill instance runs in its own role."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    b = synth.generate(cfg, 20, n)
+    c = lib.Context(0)
+    r = c.run(b, want_depth=True, want_aln=True)
+    c.close()
+    ro = orc.af_run(b, threads=0)
+    util.assert_same_results(r, ro)
+    assert r.c.dp_cells == ro.c.dp_cells
+
+
 def test_config1_repo_fixture(ctx):
     """BASELINE.json configs[0]: the locus built from the reference's test FASTAs (map-pb)."""
     b = util.load_config1()
