@@ -21,9 +21,8 @@ import time
 
 import numpy as np
 
-from . import lib
-from .bamio import BamIndex
-from .batch import Batch, PRESETS, name_hash, pack_sequences
+from . import gather, lib
+from .batch import Batch, PRESETS
 
 _COMP = bytes.maketrans(b"ACGTacgtNnUuRYKMSWBDHVrykmswbdhv", b"TGCAtgcaNnAaYRMKSWVHDByrmkswvhdb")
 
@@ -182,38 +181,42 @@ def get_af(out, sample_name, bam, raw_reads, contig_te_annotation, contig_dir, v
     presets = "map-ont" if presets == "ont" else "map-pb"         # TELR_te.py:595-598
 
     # ---- prep_assembly_inputs(read_type="all"): reads in the +-1 kb breakpoint window of every locus ----
+    # native gather (telr_io): BAI window queries, one streaming pass over the raw reads, packing straight into the batch
     telr_reads_dir = os.path.join(out, "telr_reads")
     os.makedirs(telr_reads_dir, exist_ok=True)
     window = 1000
-    bam_idx = BamIndex(bam)
-    raw = dict(read_fasta(raw_reads))
-    rows, locus_reads = [], []
-    with open(vcf_parsed) as fh, open(vcf_parsed + ".new", "w") as new:
+    rows, chroms, begs, ends, names_l, contigs = [], [], [], [], [], []
+    with open(vcf_parsed) as fh:
         for line in fh:
             entry = line.replace("\n", "").split("\t")
             bp = round((int(entry[1]) + int(entry[2])) / 2)        # banker's rounding, as the reference
-            names = sorted(set(bam_idx.fetch(entry[0], max(bp - window, 0), bp + window)))
-            new.write(line.replace("\n", "") + "\t" + str(len(names)) + "\n")
             rows.append(entry)
-            locus_reads.append(names)
-    loci = []
-    for entry, names in zip(rows, locus_reads):
-        contig_name = "_".join(entry[0:3])
-        with open(os.path.join(telr_reads_dir, contig_name + ".reads.fa"), "wb") as fa:
-            for n in names:
-                if n not in raw:
-                    raise KeyError(n)                              # SeqIO.index(...).get_raw raises KeyError
-                fa.write(b">" + n.encode() + b"\n" + raw[n] + b"\n")
+            chroms.append(entry[0]); begs.append(max(bp - window, 0)); ends.append(bp + window)
+            names_l.append("_".join(entry[0:3]))
+    for contig_name in names_l:
         contig = os.path.join(contig_dir, contig_name + ".cns.ctg1.fa")
         if not os.path.isfile(contig):
             print(contig_name + " no assembly")
-            loci.append(None)
+            contigs.append(None)
             continue
         recs = read_fasta(contig)
         with open(os.path.join(contig_dir, contig_name + ".cns.ctg1.revcomp.fa"), "w") as fo:
             for rid, seq in recs:
                 fo.write(">" + rid + "\n" + seq.translate(_COMP)[::-1].decode() + "\n")
-        loci.append((contig_name, recs[0][1] if recs else b"", names))
+        contigs.append(recs[0][1] if recs and len(recs[0][1]) > 0 else None)
+    if not os.path.isfile(bam + ".bai") and not os.path.isfile(os.path.splitext(bam)[0] + ".bai"):
+        gather.index_bam(bam)                                      # TELR indexes its BAM in stage 1; tolerate a missing .bai
+    write_reads = os.environ.get("TELR_B200_WRITE_READS", "1") != "0"
+    t_g = time.time()
+    g = gather.gather(bam, raw_reads, chroms, begs, ends, contigs, reads_dir=telr_reads_dir if write_reads else None,
+                      locus_names=names_l, threads=int(thread) if thread else 0)
+    logging.info("Read gather: %d windows, %d unique reads, %d BGZF blocks, BAM %.2f s, raw reads %.2f s (%d scanned), pack %.2f s, "
+                 "read files %.2f s (total %.2f s)", len(rows), g.timing["unique_reads"], g.timing["bgzf_blocks"], g.timing["bam_s"],
+                 g.timing["reads_s"], g.timing["reads_scanned"], g.timing["pack_s"], g.timing["write_s"], time.time() - t_g)
+    with open(vcf_parsed + ".new", "w") as new:
+        for entry, n in zip(rows, g.n_names):
+            new.write("\t".join(entry) + "\t" + str(int(n)) + "\n")
+    loci = [None if c is None else (nm, c) for nm, c in zip(names_l, contigs)]
 
     logging.info("Perform local realignment...")
     start_time = time.time()
@@ -226,29 +229,13 @@ def get_af(out, sample_name, bam, raw_reads, contig_te_annotation, contig_dir, v
             if os.path.isfile(contig) and os.stat(contig).st_size != 0:
                 coords[entry[0]] = (int(entry[1]), int(entry[2]))
 
-    # ---- pack the batch ----
-    live = [i for i, l in enumerate(loci) if l is not None and len(l[1]) > 0]
-    seqs, rlen_hash = [], []
-    lrb = [0]
-    for i in live:
-        name, ctg, names = loci[i]
-        seqs.append(ctg)
-        for n in names:
-            seqs.append(raw[n])
-            rlen_hash.append(name_hash(n))
-        lrb.append(len(rlen_hash))
-    L = lib.lib()
-    seq2, nmask, offs, lens = pack_sequences(seqs, L)
-    is_ctg = np.zeros(len(seqs), bool)
-    k = 0
-    for j, i in enumerate(live):
-        is_ctg[k] = True
-        k += 1 + (lrb[j + 1] - lrb[j])
+    # ---- the batch: arrays of the native gather + TE coordinates ----
+    live = [int(i) for i in g.live_index]
+    lrb = g.locus_read_begin
     te_s = np.array([coords.get(loci[i][0], (-1, -1))[0] for i in live], np.int32)
     te_e = np.array([coords.get(loci[i][0], (-1, -1))[1] for i in live], np.int32)
-    batch = Batch(PRESETS[presets], seq2, nmask, offs[~is_ctg].copy(), lens[~is_ctg].copy(), np.array(rlen_hash, np.uint32),
-                  np.array(lrb, np.int32), offs[is_ctg].copy(), lens[is_ctg].copy(), te_s, te_e,
-                  int(flank_intervel_size), int(flank_offset), int(te_interval_size or 0), int(te_offset))
+    batch = Batch(PRESETS[presets], g.seq2, g.nmask, g.read_off, g.read_len, g.read_hash, lrb, g.contig_off, g.contig_len, te_s, te_e,
+                  int(flank_intervel_size), int(flank_offset), int(te_interval_size or 0), int(te_offset), meta={"owner": g})      # the arrays are views of g's buffers
     empty = [j for j in range(len(live)) if lrb[j + 1] == lrb[j]]
     if batch.n_loci:
         try:

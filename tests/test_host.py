@@ -8,7 +8,7 @@ import re
 import numpy as np
 import pytest
 
-from telr_b200 import bamio, lib, stage4, synth
+from telr_b200 import bamio, gather, lib, stage4, synth
 from telr_b200.batch import Batch, PRESETS, name_hash, pack_sequences
 from tests import orc, util
 
@@ -22,6 +22,16 @@ def test_cabi_exports_every_declared_symbol(built):
     assert declared == set(lib.EXPORTS)
     assert lib.lib().telr_af_version() >= 100
     assert lib.lib().telr_af_strerror(-4).decode().startswith("no sm_100")
+
+
+def test_io_library_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(util.ROOT, "include", "telr_io.h")).read()
+    declared = set(re.findall(r"\b(telr_[a-z_0-9]+)\s*\(", hdr))
+    L = C.CDLL(gather.SO_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert declared == set(gather.EXPORTS)
+    assert gather.lib().telr_io_strerror(-5).decode().startswith("BAM index")
 
 
 def test_chunk_planner(built):
@@ -99,6 +109,124 @@ def test_bam_roundtrip_and_fetch(tmp_path):
     assert sorted(idx.fetch("chrA", 0, 5000)) == ["r1", "r2", "r3"]
     with pytest.raises(ValueError):
         list(idx.fetch("chrZ", 0, 1))
+
+
+def _random_bam(path, rng, n_rec, refs):
+    """A coordinate-sorted BAM whose records fall into every BAI bin level (spans from 1 base to several Mbase)."""
+    recs = []
+    for i in range(n_rec):
+        tid = int(rng.integers(0, len(refs)))
+        L = refs[tid][1]
+        span = int(rng.choice([1, 30, 900, 20000, 300000, 3000000]))
+        span = max(1, min(span, L - 1))
+        pos = int(rng.integers(0, L - span))
+        kind = rng.random()
+        if kind < 0.1:
+            cigar = []                                            # placed but without a CIGAR: counts as length 1
+        elif kind < 0.5:
+            cigar = [(4, 7), (0, span)]
+        else:
+            a = max(1, span // 3)
+            cigar = [(0, a), (2, span - a) if span - a > 0 else (1, 3), (1, 5)] if span > 1 else [(0, 1)]
+        recs.append(dict(name=f"q{i}_{'x' * int(rng.integers(0, 40))}", ref_id=tid, pos=pos, cigar=cigar, seq_len=0,
+                         flag=int(rng.choice([0, 16, 256, 2048, 2064]))))
+    recs.sort(key=lambda r: (r["ref_id"], r["pos"]))
+    bamio.write_bam(path, refs, recs)
+    return recs
+
+
+def test_native_bam_fetch_matches_the_pure_python_reader(built, tmp_path):
+    """telr_bam_fetch (BGZF random access through the .bai written by telr_bam_index_build) against bamio.BamIndex, which
+    inflates the whole file and scans it: same names in the same order for random windows; and an indexed query touches
+    a handful of BGZF blocks, not the file."""
+    rng = np.random.default_rng(42)
+    refs = [("chr2L", 23_000_000), ("chrX", 400_000_000), ("tiny", 40)]
+    p = str(tmp_path / "r.bam")
+    _random_bam(p, rng, 6000, refs)
+    gather.index_bam(p)
+    ref = bamio.BamIndex(p)
+    nat = gather.BamFile(p)
+    assert nat.refs == refs
+    total_blocks = os.path.getsize(p) // 20000
+    for _ in range(300):
+        chrom, L = refs[int(rng.integers(0, 3))]
+        w = int(rng.choice([1, 2000, 2000, 100000, 5_000_000]))
+        s = int(rng.integers(0, max(1, L - 1)))
+        want = list(ref.fetch(chrom, s, s + w))
+        b0 = nat.blocks_inflated
+        got = nat.fetch(chrom, s, s + w)
+        assert got == want, (chrom, s, w, len(got), len(want))
+        if w <= 2000:
+            assert nat.blocks_inflated - b0 <= 12
+    assert nat.fetch("chrX", 0, 400_000_000) == list(ref.fetch("chrX", 0, 400_000_000))
+    assert nat.fetch("tiny", 50, 60) == [] and nat.fetch("chr2L", 10, 10) == []
+    with pytest.raises(ValueError):
+        nat.fetch("chrZ", 0, 1)
+    nat.close()
+    os.remove(p + ".bai")
+    with pytest.raises(gather.IoError):
+        gather.BamFile(p)
+
+
+@pytest.mark.parametrize("fmt", ["fasta", "fastq", "fasta.gz"])
+def test_native_gather_packs_the_same_batch_as_the_python_path(built, tmp_path, fmt):
+    """telr_gather_run against the previous pure-Python gather (BamIndex.fetch + dict of reads + pack_sequences)."""
+    import gzip
+    rng = np.random.default_rng(7)
+    n_reads, n_loci = 300, 12
+    alpha = np.frombuffer(b"ACGTNacgtnRY", np.uint8)
+    reads = {f"read{i}/ccs": bytes(alpha[rng.choice(len(alpha), int(rng.integers(1, 3000)), p=[.23, .23, .23, .23, .01, .01, .01, .01, .01, .01, .01, .01])]) for i in range(n_reads)}
+    names = list(reads)
+    recs = []
+    for i, nm in enumerate(names):
+        for _ in range(int(rng.integers(1, 3))):                  # supplementary / secondary records repeat the name
+            recs.append(dict(name=nm, ref_id=0, pos=int(rng.integers(0, 60000)), cigar=[(0, int(rng.integers(50, 4000)))], seq_len=0, flag=int(rng.choice([0, 256, 2048]))))
+    recs.sort(key=lambda r: r["pos"])
+    bam = str(tmp_path / "g.bam")
+    bamio.write_bam(bam, [("chr1", 100000)], recs)
+    gather.index_bam(bam)
+    order = rng.permutation(n_reads)
+    raw = str(tmp_path / ("raw." + fmt))
+    if fmt == "fastq":
+        body = b"".join(b"@" + names[i].encode() + b" desc\n" + reads[names[i]] + b"\n+\n" + b"I" * len(reads[names[i]]) + b"\n" for i in order)
+    else:
+        body = b"".join(b">" + names[i].encode() + b" desc\n" + b"\n".join(reads[names[i]][k:k + 70] for k in range(0, len(reads[names[i]]), 70)) + b"\n" for i in order)
+    with (gzip.open(raw, "wb") if fmt.endswith(".gz") else open(raw, "wb")) as fh:
+        fh.write(body)
+    begs = [int(x) for x in rng.integers(0, 58000, n_loci)]
+    ends = [b + 2000 for b in begs]
+    contigs = [bytes(alpha[rng.integers(0, 5, int(rng.integers(100, 900)))]) if l % 4 != 3 else None for l in range(n_loci)]
+    rdir = tmp_path / "reads"; rdir.mkdir()
+    g = gather.gather(bam, raw, ["chr1"] * n_loci, begs, ends, contigs, reads_dir=str(rdir), locus_names=[f"L{l}" for l in range(n_loci)], threads=3)
+    idx = bamio.BamIndex(bam)
+    per_locus = [sorted(set(idx.fetch("chr1", b, e))) for b, e in zip(begs, ends)]
+    assert g.n_names.tolist() == [len(x) for x in per_locus]
+    live = [l for l in range(n_loci) if contigs[l]]
+    assert g.live_index.tolist() == live
+    seqs, hashes, lrb = [], [], [0]
+    for l in live:
+        seqs.append(contigs[l])
+        for nm in per_locus[l]:
+            seqs.append(reads[nm]); hashes.append(name_hash(nm))
+        lrb.append(len(hashes))
+    seq2, nmask, offs, lens = pack_sequences(seqs)
+    assert g.n_bases == len(seq2) * 16 and (g.seq2 == seq2).all() and (g.nmask == nmask).all()
+    is_ctg = np.zeros(len(seqs), bool); k = 0
+    for j in range(len(live)):
+        is_ctg[k] = True; k += 1 + lrb[j + 1] - lrb[j]
+    assert (g.read_off == offs[~is_ctg]).all() and (g.read_len == lens[~is_ctg]).all() and (g.read_hash == np.array(hashes, np.uint32)).all()
+    assert (g.contig_off == offs[is_ctg]).all() and (g.contig_len == lens[is_ctg]).all() and (g.locus_read_begin == np.array(lrb)).all()
+    for l in range(n_loci):                                        # read files exist for every locus, contig or not
+        fa = (rdir / f"L{l}.reads.fa").read_bytes()
+        assert fa == b"".join(b">" + nm.encode() + b"\n" + reads[nm] + b"\n" for nm in per_locus[l])
+    assert g.timing["unique_reads"] == len(set(sum(per_locus, [])))
+    g.free()
+    # a read named in the BAM but absent from the raw reads: KeyError like SeqIO.index(...).get_raw; unknown contig: ValueError like pysam
+    open(raw, "wb").write(b">someone_else\nACGT\n")
+    with pytest.raises(KeyError):
+        gather.gather(bam, raw, ["chr1"], [0], [60000], [b"ACGT"])
+    with pytest.raises(ValueError):
+        gather.gather(bam, raw, ["chrNope"], [0], [10], [b"ACGT"])
 
 
 def _make_stage3_artifacts(tmp_path, b: Batch, drop_contig=None, drop_annot=None):
