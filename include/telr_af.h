@@ -76,6 +76,14 @@ typedef struct telr_aln {
     int32_t mlen, blen;
     int32_t n_cigar;
     int64_t cigar_off; /* into telr_af_result.cigar                           */
+    int32_t mapq;      /* SAM MAPQ (mm_set_mapq)                              */
+    int32_t dp_score;  /* AS:i                                                */
+    int32_t cnt;       /* cm:i  minimizers on the chain                       */
+    int32_t score;     /* s1:i  chaining score                                */
+    int32_t subsc;     /* s2:i  chaining score of the best secondary          */
+    int32_t n_ambi;    /* nn:i  ambiguous bases in the alignment              */
+    int32_t inv;       /* tp:A:I  inversion piece                             */
+    int32_t n_sub;     /* suboptimal hits counted by mm_set_parent            */
 } telr_aln;
 
 typedef struct telr_af_result {
@@ -147,6 +155,12 @@ typedef struct telr_dp_out {
 int telr_af_dp(telr_af_ctx *ctx, int32_t preset, int32_t n_tasks, const telr_dp_task *tasks,
                const uint8_t *qseq, int64_t qbytes, const uint8_t *tseq, int64_t tbytes,
                telr_dp_out *out, uint32_t *cigar, int64_t cigar_cap);
+
+/* Mapping options on top of the preset, as on the minimap2 command line (0 restores the preset's value):
+ *   "bw"       -r NUM   chaining / alignment bandwidth (the polishing alignment of TELR_assembly.py:199-212 runs `-r2k`)
+ *   "bw_long"  -r ,NUM  long-join bandwidth
+ * Returns TELR_EINVAL for an unknown name or a negative value. */
+int telr_af_set_option(telr_af_ctx *ctx, const char *name, int32_t value);
 
 const char *telr_af_strerror(int code);
 int telr_af_last_cuda(const telr_af_ctx *ctx);      /* last cudaError_t seen by this ctx */

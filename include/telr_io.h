@@ -87,7 +87,7 @@ typedef struct telr_sam_rec {         /* one SAM line of `minimap2 -a` */
     int32_t flag, tid, pos, mapq;     /* pos 0-based; tid -1 + flag 4 = unmapped */
     const uint32_t *cigar; int32_t n_cigar;   /* BAM encoding len<<4|op (M I D N S H P = X) */
     const char *seq; int32_t l_seq;   /* ASCII, already in the orientation SAM prints; NULL/0 = '*' */
-    int32_t nm, ms, as_, s1, n_tags_mask;     /* optional integer tags NM ms AS s1: bit k of n_tags_mask enables tag k in that order */
+    const uint8_t *aux; int32_t l_aux;        /* optional fields, BAM-encoded (tag[2] type value ...), appended verbatim */
 } telr_sam_rec;
 /* Writes `path` (BGZF BAM, records sorted by (tid, pos), unmapped last, stable) and `path`.bai. */
 int telr_bam_write_sorted(const char *path, int32_t n_ref, const char *const *ref_name, const int32_t *ref_len,

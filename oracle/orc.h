@@ -38,6 +38,7 @@ typedef struct orc_opt {
     int32_t best_n;
     float q_occ_frac, mid_occ_frac;
     int32_t min_mid_occ, max_mid_occ;
+    int32_t max_max_occ, occ_dist;
     int32_t seed;
     int64_t max_sw_mat;
     int32_t rank_min_len;
@@ -45,6 +46,7 @@ typedef struct orc_opt {
 } orc_opt_t;
 
 void orc_opt_preset(orc_opt_t *o, int preset);
+void orc_set_bw(int bw, int bw_long);   /* minimap2 -r NUM[,NUM] on top of the preset for orc_af_run (0 = preset value) */
 
 /* Reach counters of the stated deviations from upstream: how often an input reaches a spot where this
  * restatement knowingly differs from minimap2 2.22.  0 = query minimizers dropped by the plain `n > mid_occ` filter (upstream:
@@ -87,6 +89,7 @@ typedef struct orc_aln {
     int32_t dp_max, mlen, blen;
     int32_t n_cigar;
     int64_t cigar_off;
+    int32_t mapq, dp_score, cnt, score, subsc, n_ambi, inv, n_sub;   /* SAM MAPQ and the AS / cm / s1 / s2 / nn / tp tags */
 } orc_aln_t;
 
 /* batch identical in layout to telr_af_batch (include/telr_af.h) */

@@ -20,6 +20,11 @@
 #endif
 #include "orc.h"
 
+/* command-line style overrides on top of the preset (minimap2 -r NUM[,NUM]); 0 = preset value */
+int orc_override_bw = 0, orc_override_bw_long = 0;
+void orc_set_bw(int bw, int bw_long) { orc_override_bw = bw; orc_override_bw_long = bw_long; }
+
+
 void *orc_idx_new(const orc_opt_t *opt, const uint8_t *contig, int32_t clen);
 void orc_idx_del(void *mi);
 int64_t orc_idx_size(void *mi);
@@ -126,6 +131,8 @@ int orc_af_run(const orc_batch_t *b, orc_result_t *res, int n_threads, int first
     int64_t dp_cells = 0, n_tasks = 0, n_mz = 0, n_anch = 0, n_blocks = 0;
     int err = 0;
     orc_opt_preset(&opt, b->preset);
+    if (orc_override_bw > 0) opt.bw = orc_override_bw;
+    if (orc_override_bw_long > 0) opt.bw_long = orc_override_bw_long;
     if (n_run <= 0) n_run = b->n_loci - first_locus;
     last = first_locus + n_run;
     if (last > b->n_loci) last = b->n_loci;

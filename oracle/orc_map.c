@@ -12,11 +12,10 @@
  *             mm_set_sam_pri, mm_split_reg, mm_squeeze_a, mm_update_dp_max
  *   align.c   mm_align_skeleton, mm_align1, mm_fix_bad_ends, mm_filter_bad_seeds(_alt),
  *             mm_adjust_minier, mm_test_zdrop, mm_fix_cigar, mm_update_extra, mm_align1_inv
- * Not restated (do not influence coordinates/CIGAR/secondary status): mm_est_err, mm_set_mapq.
- * Stated deviations: (1) mm_seed_select's high-occurrence rescue is replaced by a plain n>mid_occ
- * filter (only reachable for contigs with >=5000 distinct minimizers, ~27 kb); (2) krmq ties in the
- * RMQ priority are resolved to the largest (y,i) key instead of by AVL shape; (3) clean DP band
- * (orc_ksw.c).
+ *   seed.c    mm_seed_select;  hit.c mm_set_mapq, mm_set_inv_mapq
+ * Not restated (does not influence coordinates/CIGAR/secondary status/MAPQ): mm_est_err (dv:f tag only).
+ * Stated deviations: (2) krmq ties in the RMQ priority are resolved to the largest (y,i) key instead of by
+ * AVL shape; (3) clean DP band (orc_ksw.c); logf in mm_set_mapq is the correctly rounded float logarithm.
  */
 #include <stdlib.h>
 #include <string.h>
@@ -168,42 +167,114 @@ static int64_t seed_mz_flt(int64_t n, uint64_t *mx, uint64_t *my, int32_t q_occ_
     return j;
 }
 
-/* [UP] mm_seed_collect_all + mm_collect_matches + collect_seed_hits */
-static orc128_t *collect_seed_hits(const idx_t *mi, int qlen, int64_t n_mz, const uint64_t *mx, const uint64_t *my,
-                                   int64_t *n_a_)
+/* [UP] seed.c mm_seed_select: inside every streak of consecutive high-occurrence seeds keep the (streak length / dist)
+ * seeds with the fewest occurrences (a max-heap of n<<32|index, ksort.h ks_heapmake / ks_heapdown), drop the rest */
+#define MAX_MAX_HIGH_OCC 128
+typedef struct { uint32_t q_pos, q_span; int32_t n, flt, is_tandem; const orc128_t *cr; } seed_t;
+static void heapdown_u64(size_t i, size_t n, uint64_t *l)
 {
-    int64_t i, n_a = 0, cap = 0;
-    orc128_t *a;
-    for (i = 0; i < n_mz; ++i) {
-        int t;
-        idx_get(mi, mx[i] >> 8, &t);
-        if (t > mi->mid_occ) { DEV_COUNT(0); continue; }      /* flt (deviation (1): no mm_seed_select rescue) */
-        cap += t;
+    size_t k = i;
+    uint64_t tmp = l[i];
+    while ((k = (k << 1) + 1) < n) {
+        if (k != n - 1 && l[k] < l[k + 1]) ++k;
+        if (l[k] < tmp) break;
+        l[i] = l[k]; i = k;
     }
-    a = (orc128_t *)malloc((size_t)(cap + 1) * 16);
-    for (i = 0; i < n_mz; ++i) {
-        int t, k, is_tandem = 0;
-        const orc128_t *cr = idx_get(mi, mx[i] >> 8, &t);
-        uint32_t q_pos = (uint32_t)my[i], q_span = (uint32_t)(mx[i] & 0xff);
-        if (t == 0 || t > mi->mid_occ) continue;
-        if (i > 0 && mx[i] >> 8 == mx[i - 1] >> 8) is_tandem = 1;
-        if (i < n_mz - 1 && mx[i] >> 8 == mx[i + 1] >> 8) is_tandem = 1;
-        for (k = 0; k < t; ++k) {
-            uint64_t r = cr[k].y;
-            int32_t rpos = (uint32_t)r >> 1;
-            orc128_t *p = &a[n_a++];
-            if ((r & 1) == (q_pos & 1)) {
-                p->x = (r & 0xffffffff00000000ULL) | (uint64_t)rpos;
-                p->y = (uint64_t)q_span << 32 | q_pos >> 1;
-            } else {
-                p->x = 1ULL << 63 | (r & 0xffffffff00000000ULL) | (uint64_t)rpos;
-                p->y = (uint64_t)q_span << 32 | (uint32_t)(qlen - ((int32_t)(q_pos >> 1) + 1 - (int32_t)q_span) - 1);
+    l[i] = tmp;
+}
+static void heapmake_u64(size_t n, uint64_t *l)
+{
+    size_t i;
+    for (i = (n >> 1) - 1; i != (size_t)(-1); --i) heapdown_u64(i, n, l);
+}
+static void seed_select(int32_t n, seed_t *a, int len, int max_occ, int max_max_occ, int dist)
+{
+    int32_t i, last0, m;
+    uint64_t b[MAX_MAX_HIGH_OCC];
+    if (n == 0 || n == 1) return;
+    for (i = m = 0; i < n; ++i)
+        if (a[i].n > max_occ) ++m;
+    if (m == 0) return;
+    for (i = 0, last0 = -1; i <= n; ++i) {
+        if (i == n || a[i].n <= max_occ) {
+            if (i - last0 > 1) {
+                int32_t ps = last0 < 0 ? 0 : (int32_t)(a[last0].q_pos >> 1);
+                int32_t pe = i == n ? len : (int32_t)(a[i].q_pos >> 1);
+                int32_t j, k, st = last0 + 1, en = i;
+                int32_t max_high_occ = (int32_t)((double)(pe - ps) / dist + .499);
+                if (max_high_occ > 0) {
+                    if (max_high_occ > MAX_MAX_HIGH_OCC) max_high_occ = MAX_MAX_HIGH_OCC;
+                    for (j = st, k = 0; j < en && k < max_high_occ; ++j, ++k) b[k] = (uint64_t)a[j].n << 32 | (uint32_t)j;
+                    heapmake_u64((size_t)k, b);
+                    for (; j < en; ++j)
+                        if (a[j].n < (int32_t)(b[0] >> 32)) {
+                            b[0] = (uint64_t)a[j].n << 32 | (uint32_t)j;
+                            heapdown_u64(0, (size_t)k, b);
+                        }
+                    for (j = 0; j < k; ++j) a[(uint32_t)b[j]].flt = 1;
+                }
+                for (j = st; j < en; ++j) a[j].flt ^= 1;
+                for (j = st; j < en; ++j)
+                    if (a[j].n > max_max_occ) a[j].flt = 1;
             }
-            if (is_tandem) p->y |= SEED_TANDEM;
+            last0 = i;
         }
     }
+}
+
+/* [UP] mm_seed_collect_all + mm_collect_matches + collect_seed_hits; *rep_len_ = query bases under filtered seeds */
+static orc128_t *collect_seed_hits(const orc_opt_t *opt, const idx_t *mi, int qlen, int64_t n_mz, const uint64_t *mx, const uint64_t *my,
+                                   int64_t *n_a_, int32_t *rep_len_)
+{
+    int64_t i, n_a = 0, cap = 0;
+    int32_t n_m = 0, rep_st = 0, rep_en = 0, rep_len = 0;
+    orc128_t *a;
+    seed_t *m = (seed_t *)malloc((size_t)(n_mz + 1) * sizeof(seed_t));
+    for (i = 0; i < n_mz; ++i) {
+        int t;
+        const orc128_t *cr = idx_get(mi, mx[i] >> 8, &t);
+        seed_t *q;
+        if (t == 0) continue;
+        q = &m[n_m++];
+        q->q_pos = (uint32_t)my[i], q->q_span = (uint32_t)(mx[i] & 0xff), q->cr = cr, q->n = t, q->flt = 0, q->is_tandem = 0;
+        if (i > 0 && mx[i] >> 8 == mx[i - 1] >> 8) q->is_tandem = 1;
+        if (i < n_mz - 1 && mx[i] >> 8 == mx[i + 1] >> 8) q->is_tandem = 1;
+        if (t > mi->mid_occ) DEV_COUNT(0);      /* counts the high-occurrence seeds (mm_seed_select decides their fate) */
+    }
+    if (opt->occ_dist > 0 && opt->max_max_occ > mi->mid_occ) seed_select(n_m, m, qlen, mi->mid_occ, opt->max_max_occ, opt->occ_dist);
+    else for (i = 0; i < n_m; ++i) if (m[i].n > mi->mid_occ) m[i].flt = 1;
+    for (i = 0; i < n_m; ++i) {
+        const seed_t *q = &m[i];
+        if (q->flt) {
+            int en = (int)(q->q_pos >> 1) + 1, st = en - (int)q->q_span;
+            if (st > rep_en) { rep_len += rep_en - rep_st; rep_st = st, rep_en = en; }
+            else rep_en = en;
+        } else cap += q->n;
+    }
+    rep_len += rep_en - rep_st;
+    a = (orc128_t *)malloc((size_t)(cap + 1) * 16);
+    for (i = 0; i < n_m; ++i) {
+        const seed_t *q = &m[i];
+        int k;
+        if (q->flt) continue;
+        for (k = 0; k < q->n; ++k) {
+            uint64_t r = q->cr[k].y;
+            int32_t rpos = (uint32_t)r >> 1;
+            orc128_t *p = &a[n_a++];
+            if ((r & 1) == (q->q_pos & 1)) {
+                p->x = (r & 0xffffffff00000000ULL) | (uint64_t)rpos;
+                p->y = (uint64_t)q->q_span << 32 | q->q_pos >> 1;
+            } else {
+                p->x = 1ULL << 63 | (r & 0xffffffff00000000ULL) | (uint64_t)rpos;
+                p->y = (uint64_t)q->q_span << 32 | (uint32_t)(qlen - ((int32_t)(q->q_pos >> 1) + 1 - (int32_t)q->q_span) - 1);
+            }
+            if (q->is_tandem) p->y |= SEED_TANDEM;
+        }
+    }
+    free(m);
     orc_radix_sort_128x(a, a + n_a);
     *n_a_ = n_a;
+    *rep_len_ = rep_len;
     return a;
 }
 
@@ -697,6 +768,67 @@ static void select_sub(float pri_ratio, int min_diff, int best_n, int check_stra
         }
         if (k != n) sync_regs(k, r);
         *n_ = k;
+    }
+}
+
+/* [UP] hit.c mm_set_inv_mapq + mm_set_mapq (long reads: is_sr = 0).  logf is taken as the correctly rounded float
+ * logarithm, (float)log((double)x), so that the CUDA path can reproduce it bit for bit. */
+static inline float logf_cr(float x) { return (float)log((double)x); }
+static void set_mapq(int n_regs, reg_t *regs, int min_chain_sc, int match_sc, int rep_len, int32_t *mapq)
+{
+    static const float q_coef = 40.0f;
+    int64_t sum_sc = 0;
+    float uniq_ratio;
+    int i;
+    if (n_regs == 0) return;
+    for (i = 0; i < n_regs; ++i)
+        if (regs[i].parent == regs[i].id) sum_sc += regs[i].score;
+    uniq_ratio = (float)sum_sc / (sum_sc + rep_len);
+    for (i = 0; i < n_regs; ++i) {
+        reg_t *r = &regs[i];
+        if (r->inv) mapq[i] = 0;
+        else if (r->parent == r->id) {
+            int mq, subsc;
+            float pen_s1 = (r->score > 100 ? 1.0f : 0.01f * r->score) * uniq_ratio;
+            float pen_cm = r->cnt > 10 ? 1.0f : 0.1f * r->cnt;
+            pen_cm = pen_s1 < pen_cm ? pen_s1 : pen_cm;
+            subsc = r->subsc > min_chain_sc ? r->subsc : min_chain_sc;
+            if (r->has_p && r->dp_max2 > 0 && r->dp_max > 0) {
+                float identity = (float)r->mlen / r->blen;
+                float x = (float)r->dp_max2 * subsc / r->dp_max / r->score0;
+                int mq_alt;
+                mq = (int)(identity * pen_cm * q_coef * (1.0f - x * x) * logf_cr((float)r->dp_max / match_sc));
+                mq_alt = (int)(6.02f * identity * identity * (r->dp_max - r->dp_max2) / match_sc + .499f);
+                mq = mq < mq_alt ? mq : mq_alt;
+            } else {
+                float x = (float)subsc / r->score0;
+                if (r->has_p) {
+                    float identity = (float)r->mlen / r->blen;
+                    mq = (int)(identity * pen_cm * q_coef * (1.0f - x) * logf_cr((float)r->dp_max / match_sc));
+                } else mq = (int)(pen_cm * q_coef * (1.0f - x) * logf_cr((float)r->score));
+            }
+            mq -= (int)(4.343f * logf_cr((float)(r->n_sub + 1)) + .499f);
+            mq = mq > 0 ? mq : 0;
+            mapq[i] = mq < 60 ? mq : 60;
+            if (r->has_p && r->dp_max > r->dp_max2 && mapq[i] == 0) mapq[i] = 1;
+        } else mapq[i] = 0;
+    }
+    /* mm_set_inv_mapq: an inversion piece takes the smaller MAPQ of its two neighbours on the target */
+    if (n_regs >= 3) {
+        for (i = 0; i < n_regs; ++i) if (regs[i].inv) break;
+        if (i < n_regs) {
+            orc128_t *aux = (orc128_t *)malloc((size_t)n_regs * 16);
+            int n_aux = 0;
+            for (i = 0; i < n_regs; ++i)
+                if (regs[i].parent == i || regs[i].parent < 0) aux[n_aux].y = (uint64_t)i, aux[n_aux++].x = (uint64_t)regs[i].rid << 32 | (uint32_t)regs[i].rs;
+            orc_radix_sort_128x(aux, aux + n_aux);
+            for (i = 1; i < n_aux - 1; ++i)
+                if (regs[aux[i].y].inv) {
+                    int32_t l = mapq[aux[i - 1].y], rr = mapq[aux[i + 1].y];
+                    mapq[aux[i].y] = l < rr ? l : rr;
+                }
+            free(aux);
+        }
     }
 }
 
@@ -1476,8 +1608,10 @@ static int map_with_index(const orc_opt_t *opt, const idx_t *mi, const uint8_t *
     orc128_t *a;
     uint32_t hash;
     int n_regs0 = 0, i, n_out = 0;
+    int32_t rep_len = 0;
     float chn_pen_gap, chn_pen_skip;
     reg_t *regs0;
+    int32_t *mapq = 0;
     arena_t A = {0};
     actx_t c;
     uint8_t *qrc;
@@ -1497,7 +1631,7 @@ static int map_with_index(const orc_opt_t *opt, const idx_t *mi, const uint8_t *
         dbg->mz_x = (uint64_t *)malloc((size_t)(n_mz + 1) * 8); dbg->mz_y = (uint64_t *)malloc((size_t)(n_mz + 1) * 8);
         memcpy(dbg->mz_x, mx, (size_t)n_mz * 8); memcpy(dbg->mz_y, my, (size_t)n_mz * 8);
     }
-    a = collect_seed_hits(mi, qlen, n_mz, mx, my, &n_a);
+    a = collect_seed_hits(opt, mi, qlen, n_mz, mx, my, &n_a, &rep_len);
     free(mx); free(my);
     if (n_a_out) *n_a_out += n_a;
     if (dbg) {
@@ -1553,6 +1687,8 @@ static int map_with_index(const orc_opt_t *opt, const idx_t *mi, const uint8_t *
         set_parent(opt->mask_level, opt->mask_len, n_regs0, regs0, opt->a * 2 + opt->b);
         select_sub(opt->pri_ratio, opt->k * 2, opt->best_n, 0, (int)(opt->max_gap * 0.8), &n_regs0, regs0);
         set_sam_pri(n_regs0, regs0);
+        mapq = (int32_t *)calloc((size_t)n_regs0 + 1, 4);
+        set_mapq(n_regs0, regs0, opt->min_chain_score, opt->a, rep_len, mapq);
         if (dp_cells) *dp_cells += c.cells;
         if (n_dp_tasks) *n_dp_tasks += c.n_tasks;
         free(c.ez.cigar);
@@ -1568,10 +1704,13 @@ static int map_with_index(const orc_opt_t *opt, const idx_t *mi, const uint8_t *
             o->flag = (r->rev ? 0x10 : 0) | (r->parent != r->id ? 0x100 : !r->sam_pri ? 0x800 : 0);
             o->dp_max = r->dp_max, o->mlen = r->mlen, o->blen = r->blen;
             o->n_cigar = r->n_cigar, o->cigar_off = *n_cigar;
+            o->mapq = mapq[i], o->dp_score = r->dp_score, o->cnt = r->cnt, o->score = r->score, o->subsc = r->subsc;
+            o->n_ambi = r->n_ambi, o->inv = r->inv, o->n_sub = r->n_sub;
             if (r->n_cigar) memcpy(cigar + *n_cigar, r->cigar, (size_t)r->n_cigar * 4);
             *n_cigar += r->n_cigar;
         }
     }
+    free(mapq);
     free(regs0);
     free(a);
     afree_all(&A);

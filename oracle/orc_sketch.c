@@ -23,6 +23,7 @@ void orc_opt_preset(orc_opt_t *o, int preset)
     o->rmq_rescue_ratio = 0.1f; o->chain_gap_scale = 0.8f; o->chain_skip_scale = 0.0f;
     o->mask_level = 0.5f; o->mask_len = INT32_MAX; o->pri_ratio = 0.8f; o->best_n = 5;
     o->q_occ_frac = 0.01f; o->mid_occ_frac = 2e-4f; o->min_mid_occ = 10; o->max_mid_occ = 1000000;
+    o->max_max_occ = 4095; o->occ_dist = 500;
     o->seed = 11; o->max_sw_mat = 100000000; o->rank_min_len = 500; o->rank_frac = 0.9f;
     o->max_clip_ratio = 1.0f;
     if (preset == 1) {            /* map-pb */

@@ -75,7 +75,7 @@ def main():
                 cig_keep.append(cg); name_keep.append(rn)
                 rec = recs[r]
                 rec.qname, rec.flag, rec.tid, rec.pos, rec.mapq = rn, 0, l // per_chr, starts[l] - 500 + (r % 400), 60
-                rec.cigar, rec.n_cigar, rec.seq, rec.l_seq, rec.n_tags_mask = cg.ctypes.data, 1, None, 0, 0
+                rec.cigar, rec.n_cigar, rec.seq, rec.l_seq, rec.aux, rec.l_aux = cg.ctypes.data, 1, None, 0, None, 0
             for _ in range(int(args.extra_reads * (b.locus_read_begin[l + 1] - b.locus_read_begin[l]))):
                 ln = int(rng.integers(2000, 20000))
                 fr.write(b">x%d_%d\n" % (l, _) + acgt[rng.integers(0, 4, ln)].tobytes() + b"\n")

@@ -28,12 +28,12 @@ class CBatch(C.Structure):
 class CAln(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
                 ("read", "strand", "rs", "re", "qs", "qe", "rev", "flag", "dp_max", "mlen", "blen", "n_cigar")] + \
-               [("cigar_off", C.c_int64)]
+               [("cigar_off", C.c_int64)] + [(n, C.c_int32) for n in ("mapq", "dp_score", "cnt", "score", "subsc", "n_ambi", "inv", "n_sub")]
 
 
 ALN_DTYPE = np.dtype([(n, "<i4") for n in
                       ("read", "strand", "rs", "re", "qs", "qe", "rev", "flag", "dp_max", "mlen", "blen", "n_cigar")]
-                     + [("cigar_off", "<i8")])
+                     + [("cigar_off", "<i8")] + [(n, "<i4") for n in ("mapq", "dp_score", "cnt", "score", "subsc", "n_ambi", "inv", "n_sub")])
 assert ALN_DTYPE.itemsize == C.sizeof(CAln)
 
 

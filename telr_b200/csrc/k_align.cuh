@@ -27,6 +27,7 @@ namespace telr {
 #define TELR_CENSUS_BUILD 0
 #endif
 #define AL_CENSUS(A) (TELR_CENSUS_BUILD && (A).census)
+constexpr int ALN_REC_INTS = 24;        // int32 words per alignment record written by k_al_finish
 constexpr int AL_THREADS = 128;
 constexpr int AL_WARPS = AL_THREADS / 32;
 #ifndef TELR_AL_BLOCKS
@@ -69,6 +70,7 @@ struct AlignArgs {
     const int64_t *prob_aoff, *prob_roff;
     Anchor *anchors; Reg *regs;
     uint8_t *prob_scratch; const int64_t *prob_soff;           // chaining scratch, reused (HitScratch, long-gap list)
+    const int32_t *prob_replen;
     const int32_t *work_list;
     AlWork *work; AlnCtx *actx; DpTask *tasks; DpRes *res;
     uint32_t *cigs;
@@ -451,7 +453,7 @@ __global__ void __launch_bounds__(128) k_al_init(const __grid_constant__ AlignAr
         hit_scratch_carve(c.hs, b + chain_scratch_bytes((size_t)n_a + 1), (size_t)(2 * (n_a / 3) + 8));
         c.K = cs.ord; c.capK = n_a;
     }
-    c.err = 0; c.n_tasks = 0; c.defer_finish = 1;
+    c.err = 0; c.n_tasks = 0; c.defer_finish = 1; c.rep_len = A.prob_replen ? A.prob_replen[pidx] : 0;
     c.phase = PH_START;
     res_reset(A.res[w]);
     A.res[w].cigar = A.cigs + W.ez_off;
@@ -1054,12 +1056,13 @@ __global__ void __launch_bounds__(128) k_al_finish(const __grid_constant__ Align
         else {
             for (int i = 0; i < c.n_regs; ++i) {
                 const Reg &r = c.regs[i];
-                int32_t *oo = A.aln_out + (ao + i) * 16;
+                int32_t *oo = A.aln_out + (ao + i) * ALN_REC_INTS;
                 oo[0] = read + A.read_base; oo[1] = strand; oo[2] = r.rs; oo[3] = r.re; oo[4] = r.qs; oo[5] = r.qe; oo[6] = r.rev;
                 oo[7] = (r.rev ? 0x10 : 0) | (r.parent != r.id ? 0x100 : !r.sam_pri ? 0x800 : 0);
                 oo[8] = r.dp_max; oo[9] = r.mlen; oo[10] = r.blen; oo[11] = r.n_cigar;
                 oo[12] = (int32_t)(co & 0xffffffffLL); oo[13] = (int32_t)(co >> 32);
                 oo[14] = pidx + 2 * A.read_base; oo[15] = i;
+                oo[16] = r.mapq; oo[17] = r.dp_score; oo[18] = r.cnt; oo[19] = r.score; oo[20] = r.subsc; oo[21] = r.n_ambi; oo[22] = r.inv; oo[23] = r.n_sub;
                 const uint32_t *cg = c.cig + r.cig;
                 for (int k = 0; k < r.n_cigar; ++k) A.cig_out[co + k] = cg[k];
                 co += r.n_cigar;

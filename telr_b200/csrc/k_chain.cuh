@@ -55,6 +55,7 @@ struct ChainArgs {
     const int64_t *prob_roff;                      // [n_prob+1]   region capacity offsets
     Anchor *anchors; Reg *regs;
     int32_t *prob_nregs, *prob_nca;
+    int32_t *prob_replen;                          // [n_prob] query bases under filtered high-occurrence seeds (MAPQ)
     uint8_t *warp_scratch; size_t warp_scratch_stride; int32_t max_na;   // per-warp: kept-minimizer list of the fill pass
     int32_t *work_counter; int32_t *err;
     int32_t *dp_counter, *rmq_counter;      // dynamic problem queues of k_chain_dp / k_chain_rmq (problem sizes vary 7x)
@@ -418,26 +419,10 @@ __device__ void chain_item(const ChainArgs &A, IDX &I, IdxSmem &C, int item, int
         const int qlen = A.read_len[read];
         const bool do_flt = o.q_occ_frac > 0.0f && mid_occ > 0 && n > mid_occ;
         const float thr = (float)n * o.q_occ_frac;
-        if (A.mode == 0) {
-            int na = 0;
-            for (int i = lane; i < n; i += 32) {
-                int c = qc[i];
-                if (do_flt && c > mid_occ && (float)c > thr) continue;
-                int st, t = idx_lookup(I, qx[i] >> 8, &st);
-                if (t <= mid_occ) na += t;
-            }
-#pragma unroll
-            for (int d = 16; d; d >>= 1) na += __shfl_xor_sync(FULL, na, d);
-            if (lane == 0) { A.prob_na[pidx] = na; A.prob_read[pidx] = read; A.prob_ls[pidx] = item; }
-            continue;
-        }
-        // ---------------- fill mode ----------------
-        const int64_t ao = A.prob_aoff[pidx];
-        const int n_a = (int)(A.prob_aoff[pidx + 1] - ao);
-        Anchor *a = A.anchors + ao;
-        if (n_a == 0) continue;
+        // per-warp scratch: minimizers that survive the query-occurrence filter, their occurrences in the index, a work list
         uint8_t *wsb = A.warp_scratch + (size_t)(blockIdx.x * CH_WARPS + wid) * A.warp_scratch_stride;
-        int32_t *kept = (int32_t *)wsb;    // indices of minimizers that survive the query-occurrence filter
+        const size_t ws_cap = A.warp_scratch_stride / 12;
+        int32_t *kept = (int32_t *)wsb, *tarr = kept + ws_cap, *cidx = tarr + ws_cap;
         int nk = 0;
         for (int ib = 0; ib < n; ib += 32) {
             int i = ib + lane;
@@ -448,15 +433,44 @@ __device__ void chain_item(const ChainArgs &A, IDX &I, IdxSmem &C, int item, int
             nk += __popc(m);
         }
         __syncwarp();
+        bool hi = false;
+        for (int j = lane; j < nk; j += 32) {
+            int st, t = idx_lookup(I, qx[kept[j]] >> 8, &st);
+            tarr[j] = t;
+            hi |= t > mid_occ;
+        }
+        hi = __any_sync(FULL, hi);
+        int rep_len = 0;
+        if (hi) {       // rare: streaks of high-occurrence seeds are thinned out sequentially (mm_seed_select)
+            __syncwarp();
+            if (lane == 0) rep_len = seeds_filter(mid_occ, o.max_max_occ, o.occ_dist, nk, kept, qx, qy, tarr, cidx, qlen);
+            rep_len = __shfl_sync(FULL, rep_len, 0);
+            __syncwarp();
+        }
+        if (A.mode == 0) {
+            int na = 0;
+            for (int j = lane; j < nk; j += 32) na += tarr[j] > 0 ? tarr[j] : 0;
+#pragma unroll
+            for (int d = 16; d; d >>= 1) na += __shfl_xor_sync(FULL, na, d);
+            if (lane == 0) { A.prob_na[pidx] = na; A.prob_read[pidx] = read; A.prob_ls[pidx] = item; }
+            __syncwarp();
+            continue;
+        }
+        // ---------------- fill mode ----------------
+        if (lane == 0) A.prob_replen[pidx] = rep_len;
+        const int64_t ao = A.prob_aoff[pidx];
+        const int n_a = (int)(A.prob_aoff[pidx + 1] - ao);
+        Anchor *a = A.anchors + ao;
+        if (n_a == 0) { __syncwarp(); continue; }
         int run = 0;
         for (int jb = 0; jb < nk; jb += 32) {
             int j = jb + lane, t = 0, st = 0; uint64_t x = 0; uint32_t y = 0; bool tandem = false;
             if (j < nk) {
                 int i = kept[j];
                 x = qx[i]; y = qy[i];
-                t = idx_lookup(I, x >> 8, &st);
-                if (t > mid_occ) t = 0;
+                t = tarr[j] > 0 ? tarr[j] : 0;
                 if (t) {
+                    idx_lookup(I, x >> 8, &st);
                     if (j > 0 && (qx[kept[j - 1]] >> 8) == (x >> 8)) tandem = true;
                     if (j < nk - 1 && (qx[kept[j + 1]] >> 8) == (x >> 8)) tandem = true;
                 }

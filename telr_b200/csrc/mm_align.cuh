@@ -26,7 +26,7 @@ struct AlnCtx {
     uint32_t *cig; uint32_t cig_top, cig_cap;
     HitScratch hs;
     int32_t *K; int capK;
-    int err;
+    int err, rep_len;       // rep_len: query bases under filtered high-occurrence seeds (feeds MAPQ)
     int defer_finish;       // 1: leave reg_finish + the final region pass to aln_finish() (GPU rounds), 0: inline
     int64_t n_tasks;
     // ---- coroutine state ----
@@ -811,6 +811,7 @@ TELR_HDN void aln_finish(AlnCtx &c)
     regs_set_parent(o, c.n_regs, c.regs, c.hs);
     regs_select_sub(o, 0, &c.n_regs, c.regs, c.hs, c.cap_regs);
     regs_set_sam_pri(c.n_regs, c.regs);
+    regs_set_mapq(o, c.n_regs, c.regs, c.rep_len, c.hs);
     c.phase = PH_DONE;
 }
 

@@ -6,18 +6,6 @@
 
 namespace telr {
 
-#if defined(__CUDA_ARCH__)
-#define TELR_FMUL(a, b) __fmul_rn((a), (b))
-#define TELR_FADD(a, b) __fadd_rn((a), (b))
-#define TELR_DMUL(a, b) __dmul_rn((a), (b))
-#define TELR_DADD(a, b) __dadd_rn((a), (b))
-#else   // host builds use -ffp-contract=off
-#define TELR_FMUL(a, b) ((a) * (b))
-#define TELR_FADD(a, b) ((a) + (b))
-#define TELR_DMUL(a, b) ((a) * (b))
-#define TELR_DADD(a, b) ((a) + (b))
-#endif
-
 // fast log2 used by the chaining gap penalty; fp32 without fused multiply-add
 TELR_HD float fast_log2(float x)
 {
@@ -273,6 +261,70 @@ TELR_HD void rmq_step(const Opt &o, int n, int i, const Anchor *a, ChainScratch 
     f[i] = max_f, p[i] = max_j;
     v[i] = max_j >= 0 && v[max_j] > max_f ? v[max_j] : max_f;
     (void)n;
+}
+
+// ---- high-occurrence seeds of one read (minimap2 seed.c mm_seed_select + the rep_len bookkeeping of mm_collect_matches) ----
+// ks_heapdown / ks_heapmake of klib's ksort.h on uint64 (max-heap)
+TELR_HD void heapdown_u64(int i, int n, uint64_t *l)
+{
+    int k = i;
+    uint64_t tmp = l[i];
+    while ((k = (k << 1) + 1) < n) {
+        if (k != n - 1 && l[k] < l[k + 1]) ++k;
+        if (l[k] < tmp) break;
+        l[i] = l[k]; i = k;
+    }
+    l[i] = tmp;
+}
+// kept[0..nk): the read's minimizers after the query-side filter; tarr[j] = occurrences of kept[j] in the contig index.
+// Marks every seed upstream would filter by NEGATING tarr[j] and returns rep_len, the query bases under filtered seeds.
+// Inside a streak of consecutive high-occurrence seeds (among the seeds that hit the index) the (streak span / occ_dist)
+// seeds with the fewest occurrences survive; seeds above max_max_occ never do.  cidx: scratch, nk words.  Sequential.
+TELR_HDN int seeds_filter(int max_occ, int max_max_occ, int occ_dist, int nk, const int32_t *kept, const uint64_t *qx, const uint32_t *qy,
+                          int32_t *tarr, int32_t *cidx, int qlen)
+{
+    int n = 0;
+    for (int j = 0; j < nk; ++j) if (tarr[j] > 0) cidx[n++] = j;
+#define SF_T(i) tarr[cidx[i]]
+#define SF_QPOS(i) ((int32_t)(qy[kept[cidx[i]]] >> 1))
+    if (occ_dist > 0 && max_max_occ > max_occ) {
+        if (n > 1) {
+            uint64_t b[128];
+            int last0 = -1;
+            for (int i = 0; i <= n; ++i) {
+                if (i == n || SF_T(i) <= max_occ) {
+                    if (i - last0 > 1) {
+                        const int ps = last0 < 0 ? 0 : SF_QPOS(last0), pe = i == n ? qlen : SF_QPOS(i);
+                        const int st = last0 + 1, en = i;
+                        int j, k, max_high_occ = (int)((double)(pe - ps) / occ_dist + .499);
+                        if (max_high_occ > 0) {
+                            if (max_high_occ > 128) max_high_occ = 128;
+                            for (j = st, k = 0; j < en && k < max_high_occ; ++j, ++k) b[k] = (uint64_t)(uint32_t)SF_T(j) << 32 | (uint32_t)j;
+                            for (int h = (k >> 1) - 1; h >= 0; --h) heapdown_u64(h, k, b);
+                            for (; j < en; ++j)
+                                if (SF_T(j) < (int32_t)(b[0] >> 32)) { b[0] = (uint64_t)(uint32_t)SF_T(j) << 32 | (uint32_t)j; heapdown_u64(0, k, b); }
+                            for (j = 0; j < k; ++j) SF_T((uint32_t)b[j]) = -SF_T((uint32_t)b[j]);          // flt = 1 on the chosen ...
+                        }
+                        for (j = st; j < en; ++j) SF_T(j) = -SF_T(j);                                        // ... then flt ^= 1 over the streak
+                        for (j = st; j < en; ++j) { const int t = SF_T(j) < 0 ? -SF_T(j) : SF_T(j); if (t > max_max_occ) SF_T(j) = -t; }
+                    }
+                    last0 = i;
+                }
+            }
+        }
+    } else {
+        for (int i = 0; i < n; ++i) if (SF_T(i) > max_occ) SF_T(i) = -SF_T(i);
+    }
+    int rep_st = 0, rep_en = 0, rep_len = 0;
+    for (int i = 0; i < n; ++i)
+        if (SF_T(i) < 0) {
+            const int en = SF_QPOS(i) + 1, st = en - (int)(qx[kept[cidx[i]]] & 0xff);
+            if (st > rep_en) { rep_len += rep_en - rep_st; rep_st = st; rep_en = en; }
+            else rep_en = en;
+        }
+#undef SF_T
+#undef SF_QPOS
+    return rep_len + (rep_en - rep_st);
 }
 
 struct RmqWin { int st, st_inner, i0, max_dist, max_dist_inner; };

@@ -2,6 +2,7 @@
 // generation from chains, primary/secondary assignment, sub-optimal selection, filtering, sorting.
 // Sequential; runs on one lane between the warp-parallel stages (or on the host in tests/emu).
 #pragma once
+#include <math.h>
 #include "mm_sort.cuh"
 
 namespace telr {
@@ -234,6 +235,66 @@ TELR_HDN void regs_sort(int *n_regs, Reg *r, HitScratch &s)
     for (int i = n_aux - 1; i >= 0; --i) s.tmp[n_aux - 1 - i] = r[aux[i].y];
     for (int i = 0; i < n_aux; ++i) r[i] = s.tmp[i];
     *n_regs = n_aux;
+}
+
+// minimap2 hit.c mm_set_mapq (long reads) + mm_set_inv_mapq.  logf = correctly rounded float logarithm through fp64,
+// the same on the host and on the device.
+TELR_HD float logf_cr(float x) { return (float)log((double)x); }
+TELR_HDN void regs_set_mapq(const Opt &o, int n_regs, Reg *regs, int rep_len, HitScratch &s)
+{
+    const float q_coef = 40.0f;
+    const int min_chain_sc = o.min_chain_score, match_sc = o.a;
+    long long sum_sc = 0;
+    if (n_regs == 0) return;
+    for (int i = 0; i < n_regs; ++i)
+        if (regs[i].parent == regs[i].id) sum_sc += regs[i].score;
+    const float uniq_ratio = (float)sum_sc / (float)(sum_sc + rep_len);
+    for (int i = 0; i < n_regs; ++i) {
+        Reg &r = regs[i];
+        if (r.inv) r.mapq = 0;
+        else if (r.parent == r.id) {
+            int mq;
+            float pen_s1 = TELR_FMUL(r.score > 100 ? 1.0f : TELR_FMUL(0.01f, (float)r.score), uniq_ratio);
+            float pen_cm = r.cnt > 10 ? 1.0f : TELR_FMUL(0.1f, (float)r.cnt);
+            pen_cm = pen_s1 < pen_cm ? pen_s1 : pen_cm;
+            const int subsc = r.subsc > min_chain_sc ? r.subsc : min_chain_sc;
+            if (r.has_p && r.dp_max2 > 0 && r.dp_max > 0) {
+                const float identity = (float)r.mlen / (float)r.blen;
+                const float x = TELR_FMUL((float)r.dp_max2, (float)subsc) / (float)r.dp_max / (float)r.score0;
+                const float one_m = TELR_FADD(1.0f, -TELR_FMUL(x, x));
+                mq = (int)TELR_FMUL(TELR_FMUL(TELR_FMUL(TELR_FMUL(identity, pen_cm), q_coef), one_m), logf_cr((float)r.dp_max / (float)match_sc));
+                const int mq_alt = (int)TELR_FADD(TELR_FMUL(TELR_FMUL(TELR_FMUL(6.02f, identity), identity), (float)(r.dp_max - r.dp_max2)) / (float)match_sc, .499f);
+                mq = mq < mq_alt ? mq : mq_alt;
+            } else {
+                const float x = (float)subsc / (float)r.score0;
+                const float one_m = TELR_FADD(1.0f, -x);
+                if (r.has_p) {
+                    const float identity = (float)r.mlen / (float)r.blen;
+                    mq = (int)TELR_FMUL(TELR_FMUL(TELR_FMUL(TELR_FMUL(identity, pen_cm), q_coef), one_m), logf_cr((float)r.dp_max / (float)match_sc));
+                } else mq = (int)TELR_FMUL(TELR_FMUL(TELR_FMUL(pen_cm, q_coef), one_m), logf_cr((float)r.score));
+            }
+            mq -= (int)TELR_FADD(TELR_FMUL(4.343f, logf_cr((float)(r.n_sub + 1))), .499f);
+            mq = mq > 0 ? mq : 0;
+            r.mapq = mq < 60 ? mq : 60;
+            if (r.has_p && r.dp_max > r.dp_max2 && r.mapq == 0) r.mapq = 1;
+        } else r.mapq = 0;
+    }
+    if (n_regs >= 3) {          // an inversion piece takes the smaller MAPQ of its neighbours on the target
+        int i;
+        for (i = 0; i < n_regs; ++i) if (regs[i].inv) break;
+        if (i < n_regs) {
+            Anchor *aux = s.z;
+            int n_aux = 0;
+            for (i = 0; i < n_regs; ++i)
+                if (regs[i].parent == i || regs[i].parent < 0) aux[n_aux].y = (uint64_t)i, aux[n_aux++].x = (uint64_t)(uint32_t)regs[i].rs;
+            rs_sort_emul(aux, n_aux, KeyX(), s.sortws);
+            for (i = 1; i < n_aux - 1; ++i)
+                if (regs[aux[i].y].inv) {
+                    const int l = regs[aux[i - 1].y].mapq, rr = regs[aux[i + 1].y].mapq;
+                    regs[aux[i].y].mapq = l < rr ? l : rr;
+                }
+        }
+    }
 }
 
 // squeeze anchors not referenced by any region; returns number of anchors kept

@@ -18,6 +18,20 @@
 #define TELR_HDN
 #endif
 
+// fp32 / fp64 arithmetic without fused multiply-add, identical on the device and in host builds (-ffp-contract=off)
+#if defined(__CUDA_ARCH__)
+#define TELR_FMUL(a, b) __fmul_rn((a), (b))
+#define TELR_FADD(a, b) __fadd_rn((a), (b))
+#define TELR_DMUL(a, b) __dmul_rn((a), (b))
+#define TELR_DADD(a, b) __dadd_rn((a), (b))
+#else   // host builds use -ffp-contract=off
+#define TELR_FMUL(a, b) ((a) * (b))
+#define TELR_FADD(a, b) ((a) + (b))
+#define TELR_DMUL(a, b) ((a) * (b))
+#define TELR_DADD(a, b) ((a) + (b))
+#endif
+
+
 namespace telr {
 
 struct Anchor { uint64_t x, y; };
@@ -50,6 +64,7 @@ struct Opt {
     int best_n;
     float q_occ_frac, mid_occ_frac;
     int min_mid_occ, max_mid_occ;
+    int max_max_occ, occ_dist;     // mm_seed_select: cap on occurrences, one rescued seed per occ_dist query bases
     uint32_t seed_term;      // Wang hash of opt->seed (map.c mm_map_frag)
     long long max_sw_mat;
     int rank_min_len;
@@ -64,6 +79,7 @@ struct Reg {
     int32_t dp_score, dp_max, dp_max2, n_ambi, n_cigar;
     uint32_t cig;            // offset of this region's CIGAR in the problem's cigar arena
     int32_t fin_q, fin_t;    // where the joined CIGAR starts on query/target (deferred reg_finish)
+    int32_t mapq;
 };
 
 // result of one DP call (ksw_extz_t)

@@ -60,7 +60,7 @@ struct telr_af_ctx {
     DevBuf b_cov, b_af, b_depth;
     DevBuf b_lrb, b_cboff, b_ctg, b_descs, b_counts, b_mzoff, b_mzx, b_mzy, b_self, b_tabk, b_tabc, b_hpc, b_hpp, b_hpr;
     DevBuf b_pna, b_pread, b_pls, b_paoff, b_prcap, b_proff, b_pnregs, b_pnca, b_anch, b_regs, b_chws, b_alws, b_work;
-    DevBuf b_psb, b_psoff, b_pscr, b_pnu, b_pm;
+    DevBuf b_psb, b_psoff, b_pscr, b_pnu, b_pm, b_prep;
     DevBuf b_hpoff, b_hpn;                // compressed step stream: slice per sequence, steps per sequence
     DevBuf b_order, b_wflag, b_woff;      // LPT order of the chunk's problems, work-list filter
     DevBuf b_tfirst, b_tcnt, b_toff, b_tmpx, b_tmpy;     // tile sketch: first tile per sequence, per-tile counts/offsets, per-tile slots
@@ -71,6 +71,7 @@ struct telr_af_ctx {
     // loop bodies as designed, but end to end it is within +-1.5 % of k_al_fused on map-ont and 18 % slower on map-pb / map-hifi, so the
     // fused kernel stays the default.
     int al_queue = 0, ext_per8 = 2, wide_per8 = 2;
+    int opt_bw = 0, opt_bw_long = 0;     // telr_af_set_option overrides (0 = preset value)
     DevBuf b_qring, b_qstate;
     int al_blocks = AL_BLOCKS_PER_SM;    // resident k_al_fused CTAs per SM this context asks for (fewer leaves room for a second context's kernels)
     DevBuf b_rbytes, b_rboff, b_alwork, b_alctx, b_altask, b_alres, b_alsz, b_aloff, b_cigs, b_pool, b_tlist, b_rc, b_opt, b_idxbig;
@@ -92,6 +93,7 @@ static void opt_preset(Opt &o, int preset)
     float gap_scale = 0.8f, skip_scale = 0.0f;
     o.mask_level = 0.5f; o.mask_len = INT32_MAX; o.pri_ratio = 0.8f; o.best_n = 5;
     o.q_occ_frac = 0.01f; o.mid_occ_frac = 2e-4f; o.min_mid_occ = 10; o.max_mid_occ = 1000000;
+    o.max_max_occ = 4095; o.occ_dist = 500;
     o.seed_term = wang_hash32(11u); o.max_sw_mat = 100000000LL; o.rank_min_len = 500; o.rank_frac = 0.9f; o.max_clip_ratio = 1.0f;
     if (preset == TELR_PRESET_MAP_PB) { o.hpc = 1; o.k = 19; }
     else if (preset == TELR_PRESET_MAP_HIFI) {
@@ -410,6 +412,11 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
     ca.idx_big = ctx->b_idxbig.as<IdxBig>();
     ca.locus_bad = ctx->b_lbad.as<uint8_t>();
     const size_t ch_smem = sizeof(IdxSmem);
+    // per-warp seeding scratch: three int32 lists of up to one entry per read base (kept minimizers, occurrences, work list)
+    const size_t ch_stride = (((size_t)max_qlen + 64) * 12 + 255) & ~(size_t)255;
+    ENS(ctx->b_chws, ch_stride * (size_t)ch_grid * CH_WARPS);
+    ENS(ctx->b_prep, (size_t)(n_prob + 1) * 4);
+    ca.warp_scratch = ctx->b_chws.as<uint8_t>(); ca.warp_scratch_stride = ch_stride; ca.prob_replen = ctx->b_prep.as<int32_t>();
     CK(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch_smem));
     { ++ctx->launches; k_chain<<<ch_grid, CH_THREADS, ch_smem, st>>>(ca); }
     { ++ctx->launches; k_excl_scan<int32_t><<<1, 1024, 0, st>>>(ctx->b_pna.as<int32_t>(), ctx->b_paoff.as<int64_t>(), n_prob, ctr + C_MAXNA); }
@@ -432,12 +439,10 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
                 na[n_prob / 2], na[(size_t)n_prob * 9 / 10], na[(size_t)n_prob * 99 / 100], na[(size_t)n_prob * 999 / 1000], (double)s2);
     }
     ENS(ctx->b_anch, (tot_na + 1) * sizeof(Anchor)); ENS(ctx->b_regs, (tot_rcap + 1) * sizeof(Reg)); ENS(ctx->b_pscr, tot_scr + 256);
-    const size_t ch_stride = (((size_t)max_qlen + 64) * 4 + 255) & ~(size_t)255;
-    ENS(ctx->b_chws, ch_stride * (size_t)ch_grid * CH_WARPS);
     CK(cudaMemsetAsync(ctr + C_WORK_CHAIN, 0, 8, st));
     ca.mode = 1; ca.prob_aoff = ctx->b_paoff.as<int64_t>(); ca.prob_roff = ctx->b_proff.as<int64_t>();
     ca.anchors = ctx->b_anch.as<Anchor>(); ca.regs = ctx->b_regs.as<Reg>();
-    ca.warp_scratch = ctx->b_chws.as<uint8_t>(); ca.warp_scratch_stride = ch_stride; ca.max_na = (int)max_na;
+    ca.max_na = (int)max_na;
     ca.prob_scratch = ctx->b_pscr.as<uint8_t>(); ca.prob_soff = ctx->b_psoff.as<int64_t>();
     ca.prob_nu = ctx->b_pnu.as<int32_t>(); ca.prob_m = ctx->b_pm.as<int32_t>(); ca.n_prob = n_prob;
     { ++ctx->launches; k_chain<<<ch_grid, CH_THREADS, ch_smem, st>>>(ca); }
@@ -475,7 +480,7 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
     aa.prob_read = ctx->b_pread.as<int32_t>(); aa.prob_ls = ctx->b_pls.as<int32_t>(); aa.prob_nca = ctx->b_pnca.as<int32_t>();
     aa.prob_nregs = ctx->b_pnregs.as<int32_t>(); aa.prob_aoff = ctx->b_paoff.as<int64_t>(); aa.prob_roff = ctx->b_proff.as<int64_t>();
     aa.anchors = ctx->b_anch.as<Anchor>(); aa.regs = ctx->b_regs.as<Reg>();
-    aa.prob_scratch = ctx->b_pscr.as<uint8_t>(); aa.prob_soff = ctx->b_psoff.as<int64_t>();
+    aa.prob_scratch = ctx->b_pscr.as<uint8_t>(); aa.prob_soff = ctx->b_psoff.as<int64_t>(); aa.prob_replen = ctx->b_prep.as<int32_t>();
     aa.work_list = ctx->b_work.as<int32_t>();
     std::vector<int64_t> rbo(n_reads + 1);     // outlives its upload: the function synchronises again before it returns
     {   // nt4 bytes of every read of the chunk (forward + reverse complement)
@@ -669,6 +674,8 @@ static int run_device(telr_af_ctx *ctx, const telr_af_batch *db, const HostMeta 
     Opt o;
     if (db->preset < 0 || db->preset > 2) return TELR_EINVAL;
     opt_preset(o, db->preset);
+    if (ctx->opt_bw > 0) o.bw = ctx->opt_bw;
+    if (ctx->opt_bw_long > 0) o.bw_long = ctx->opt_bw_long;
     const int n_loci = db->n_loci;
     std::vector<int64_t> depth_off(n_loci + 1, 0);
     for (int l = 0; l < n_loci; ++l) depth_off[l + 1] = depth_off[l] + 2 * (int64_t)hm.contig_len[l];
@@ -717,6 +724,15 @@ const char *telr_af_strerror(int code)
 int telr_af_last_cuda(const telr_af_ctx *ctx) { return ctx ? ctx->last_cuda : 0; }
 long long telr_af_launch_count(const telr_af_ctx *ctx) { return ctx ? ctx->launches : 0; }
 void *telr_af_stream(const telr_af_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int telr_af_set_option(telr_af_ctx *ctx, const char *name, int32_t value)
+{
+    if (!ctx || !name || value < 0) return TELR_EINVAL;
+    if (!strcmp(name, "bw")) ctx->opt_bw = value;
+    else if (!strcmp(name, "bw_long")) ctx->opt_bw_long = value;
+    else return TELR_EINVAL;
+    return TELR_OK;
+}
 
 int telr_af_create(telr_af_ctx **out, int device, size_t workspace_bytes)
 {
@@ -773,7 +789,7 @@ int telr_af_destroy(telr_af_ctx *ctx)
                      &ctx->b_alws, &ctx->b_work, &ctx->b_blk, &ctx->b_pblkoff, &ctx->b_pblkcnt, &ctx->b_ctr, &ctx->b_alnout, &ctx->b_cigout, &ctx->b_doff, &ctx->b_grow, &ctx->b_lbad,
                      &ctx->b_big, &ctx->b_biglock, &ctx->b_rbytes, &ctx->b_rboff, &ctx->b_alwork, &ctx->b_alctx, &ctx->b_altask, &ctx->b_alres, &ctx->b_alsz, &ctx->b_aloff,
                      &ctx->b_cigs, &ctx->b_pool, &ctx->b_tlist, &ctx->b_rc, &ctx->b_opt, &ctx->b_idxbig, &ctx->b_psb, &ctx->b_psoff, &ctx->b_pscr, &ctx->b_pnu, &ctx->b_pm,
-                     &ctx->b_tfirst, &ctx->b_tcnt, &ctx->b_toff, &ctx->b_tmpx, &ctx->b_tmpy, &ctx->b_order, &ctx->b_wflag, &ctx->b_woff, &ctx->b_hpoff, &ctx->b_hpn, &ctx->b_qring, &ctx->b_qstate};
+                     &ctx->b_tfirst, &ctx->b_tcnt, &ctx->b_toff, &ctx->b_tmpx, &ctx->b_tmpy, &ctx->b_order, &ctx->b_wflag, &ctx->b_woff, &ctx->b_hpoff, &ctx->b_hpn, &ctx->b_qring, &ctx->b_qstate, &ctx->b_prep};
     for (auto *b : all) b->release();
     for (auto &b : ctx->b_in) b.release();
     for (auto &e : ctx->ev) cudaEventDestroy(e);
@@ -820,7 +836,7 @@ int telr_af_run(telr_af_ctx *ctx, const telr_af_batch *hb, telr_af_result *hr)
     if (hr->depth) { ENS(ctx->b_depth, (size_t)depth_n * 4 + 64); dres.depth = ctx->b_depth.as<int32_t>(); }
     int32_t *d_aln = nullptr; uint32_t *d_cig = nullptr;
     if (hr->aln && hr->cigar) {
-        ENS(ctx->b_alnout, (size_t)hr->aln_cap * 64 + 64); ENS(ctx->b_cigout, (size_t)hr->cigar_cap * 4 + 64);
+        ENS(ctx->b_alnout, (size_t)hr->aln_cap * ALN_REC_INTS * 4 + 64); ENS(ctx->b_cigout, (size_t)hr->cigar_cap * 4 + 64);
         d_aln = ctx->b_alnout.as<int32_t>(); d_cig = ctx->b_cigout.as<uint32_t>();
     }
     rc = run_device(ctx, &db, hm, &dres, hr, d_aln, hr->aln_cap, d_cig, hr->cigar_cap, &cuts, &up);
@@ -832,8 +848,8 @@ int telr_af_run(telr_af_ctx *ctx, const telr_af_batch *hb, telr_af_result *hr)
     if (hr->depth) CK(cudaMemcpyAsync(hr->depth, dres.depth, (size_t)depth_n * 4, cudaMemcpyDeviceToHost, st));
     std::vector<int32_t> raw;
     if (d_aln) {
-        raw.resize((size_t)hr->n_aln * 16 + 16);
-        if (hr->n_aln) CK(cudaMemcpyAsync(raw.data(), d_aln, (size_t)hr->n_aln * 64, cudaMemcpyDeviceToHost, st));
+        raw.resize((size_t)hr->n_aln * ALN_REC_INTS + 16);
+        if (hr->n_aln) CK(cudaMemcpyAsync(raw.data(), d_aln, (size_t)hr->n_aln * ALN_REC_INTS * 4, cudaMemcpyDeviceToHost, st));
         if (hr->n_cigar) CK(cudaMemcpyAsync(hr->cigar, d_cig, (size_t)hr->n_cigar * 4, cudaMemcpyDeviceToHost, st));
     }
     CK(cudaStreamSynchronize(st));
@@ -842,16 +858,17 @@ int telr_af_run(telr_af_ctx *ctx, const telr_af_batch *hb, telr_af_result *hr)
         std::vector<int64_t> ord(hr->n_aln);
         for (int64_t i = 0; i < hr->n_aln; ++i) ord[i] = i;
         std::sort(ord.begin(), ord.end(), [&](int64_t a, int64_t b) {
-            const int32_t *x = &raw[a * 16], *y = &raw[b * 16];       // problem index orders by (locus, strand, read)
+            const int32_t *x = &raw[a * ALN_REC_INTS], *y = &raw[b * ALN_REC_INTS];       // problem index orders by (locus, strand, read)
             if (x[14] != y[14]) return x[14] < y[14];
             return x[15] < y[15];
         });
         for (int64_t i = 0; i < hr->n_aln; ++i) {
-            const int32_t *x = &raw[ord[i] * 16];
+            const int32_t *x = &raw[ord[i] * ALN_REC_INTS];
             telr_aln &a = hr->aln[i];
             a.read = x[0]; a.strand = x[1]; a.rs = x[2]; a.re = x[3]; a.qs = x[4]; a.qe = x[5]; a.rev = x[6]; a.flag = x[7];
             a.dp_max = x[8]; a.mlen = x[9]; a.blen = x[10]; a.n_cigar = x[11];
             a.cigar_off = (int64_t)(uint32_t)x[12] | (int64_t)x[13] << 32;
+            a.mapq = x[16]; a.dp_score = x[17]; a.cnt = x[18]; a.score = x[19]; a.subsc = x[20]; a.n_ambi = x[21]; a.inv = x[22]; a.n_sub = x[23];
         }
     }
     return TELR_OK;

@@ -795,16 +795,6 @@ struct BgzfWriter {
     }
 };
 
-void put_tag_i(std::vector<uint8_t> &v, const char *tag, int32_t x)
-{
-    v.push_back((uint8_t)tag[0]); v.push_back((uint8_t)tag[1]);
-    if (x >= 0 && x < 256) { v.push_back('C'); v.push_back((uint8_t)x); }
-    else if (x >= -128 && x < 0) { v.push_back('c'); v.push_back((uint8_t)(int8_t)x); }
-    else if (x >= 0 && x < 65536) { v.push_back('S'); uint16_t y = (uint16_t)x; v.insert(v.end(), (uint8_t *)&y, (uint8_t *)&y + 2); }
-    else if (x >= -32768 && x < 0) { v.push_back('s'); int16_t y = (int16_t)x; v.insert(v.end(), (uint8_t *)&y, (uint8_t *)&y + 2); }
-    else { v.push_back('i'); v.insert(v.end(), (uint8_t *)&x, (uint8_t *)&x + 4); }
-}
-
 }  // namespace
 
 extern "C" int telr_bam_write_sorted(const char *path, int32_t n_ref, const char *const *ref_name, const int32_t *ref_len,
@@ -832,7 +822,6 @@ extern "C" int telr_bam_write_sorted(const char *path, int32_t n_ref, const char
         v = (int32_t)strlen(ref_name[i]) + 1;
         w.write(&v, 4); w.write(ref_name[i], (size_t)v); w.write(&ref_len[i], 4);
     }
-    static const char *tags[4] = {"NM", "ms", "AS", "s1"};
     uint8_t code[256];
     memset(code, 15, sizeof(code));
     { const char *s = "=ACMGRSVTWYHKDBN"; for (int i = 0; i < 16; ++i) { code[(int)s[i]] = (uint8_t)i; if (s[i] >= 'A') code[(int)s[i] + 32] = (uint8_t)i; } }
@@ -859,8 +848,7 @@ extern "C" int telr_bam_write_sorted(const char *path, int32_t n_ref, const char
             body.push_back((uint8_t)(a << 4 | b));
         }
         body.insert(body.end(), (size_t)r.l_seq, (uint8_t)0xff);        // FASTA input: no base qualities ('*')
-        const int32_t tv[4] = {r.nm, r.ms, r.as_, r.s1};
-        for (int k = 0; k < 4; ++k) if (r.n_tags_mask >> k & 1) put_tag_i(body, tags[k], tv[k]);
+        if (r.aux && r.l_aux > 0) body.insert(body.end(), r.aux, r.aux + r.l_aux);
         v = (int32_t)body.size();
         w.write(&v, 4); w.write(body.data(), body.size());
     }

@@ -46,7 +46,7 @@ class GatherOut(C.Structure):
 class SamRec(C.Structure):
     _fields_ = [("qname", C.c_char_p), ("flag", C.c_int32), ("tid", C.c_int32), ("pos", C.c_int32), ("mapq", C.c_int32),
                 ("cigar", C.c_void_p), ("n_cigar", C.c_int32), ("seq", C.c_char_p), ("l_seq", C.c_int32),
-                ("nm", C.c_int32), ("ms", C.c_int32), ("as_", C.c_int32), ("s1", C.c_int32), ("n_tags_mask", C.c_int32)]
+                ("aux", C.c_char_p), ("l_aux", C.c_int32)]
 
 
 def lib():

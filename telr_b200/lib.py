@@ -44,7 +44,7 @@ assert DPTASK_DTYPE.itemsize == C.sizeof(DpTask) and DPOUT_DTYPE.itemsize == C.s
 
 EXPORTS = ["telr_af_create", "telr_af_destroy", "telr_af_run", "telr_af_run_device", "telr_af_sketch", "telr_af_depth_af",
            "telr_af_dp", "telr_af_strerror", "telr_af_last_cuda", "telr_af_version", "telr_af_launch_count", "telr_af_stream",
-           "telr_pack_seq", "telr_name_hash", "telr_af_plan_chunks"]
+           "telr_pack_seq", "telr_name_hash", "telr_af_plan_chunks", "telr_af_set_option"]
 
 
 def lib():
@@ -74,6 +74,7 @@ def lib():
         L.telr_af_stream.restype = C.c_void_p
         L.telr_af_stream.argtypes = [C.c_void_p]
         L.telr_name_hash.argtypes = [C.c_char_p]
+        L.telr_af_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int32]
         L.telr_af_plan_chunks.restype = C.c_int
         L.telr_af_plan_chunks.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32]
         for fn in ("telr_af_create", "telr_af_destroy", "telr_af_run", "telr_af_run_device", "telr_af_sketch",
@@ -170,6 +171,12 @@ class Context:
         if rc != 0:
             raise TelrError(rc, "telr_af_run")
         return r
+
+    def set_option(self, name: str, value: int):
+        """Mapping option on top of the preset, e.g. set_option("bw", 2000) for `minimap2 -r2k`; 0 restores the preset value."""
+        rc = lib().telr_af_set_option(self._h, name.encode(), int(value))
+        if rc != 0:
+            raise TelrError(rc, f"telr_af_set_option({name})")
 
     def run_device(self, cb: CBatch, cres: CResult):
         rc = lib().telr_af_run_device(self._h, C.byref(cb), C.byref(cres))

@@ -22,7 +22,7 @@ import time
 import numpy as np
 
 from . import gather, lib
-from .batch import Batch, PRESETS
+from .batch import Batch, PRESETS, name_hash
 
 _COMP = bytes.maketrans(b"ACGTacgtNnUuRYKMSWBDHVrykmswbdhv", b"TGCAtgcaNnAaYRMKSWVHDByrmkswvhdb")
 
@@ -148,6 +148,54 @@ def run_batch(batch: Batch, devices=None, **kw):
     return cov, af, None
 
 
+def _run_with_bams(batch: Batch, locus_names, out_dir, raw_reads, slice_bases=200_000_000):
+    """The device path with alignment records kept, written as the reference's per-locus BAMs (TELR_te.py:502-515).  Loci are
+    processed in slices so that the record buffers stay small; read names are recovered from their X31 hashes."""
+    from . import realign
+    names_by_hash = {}
+    for nm, _ in read_fasta_names(raw_reads):
+        names_by_hash.setdefault(name_hash(nm), nm)
+    cov = np.zeros((batch.n_loci, 8), np.int32)
+    af = np.zeros(batch.n_loci, np.float64)
+    csum = np.concatenate([[0], np.cumsum(batch.read_len.astype(np.int64))])
+    ctx = lib.Context(0)
+    try:
+        l0 = 0
+        while l0 < batch.n_loci:
+            l1 = l0 + 1
+            while l1 < batch.n_loci and csum[batch.locus_read_begin[l1 + 1]] - csum[batch.locus_read_begin[l0]] <= slice_bases:
+                l1 += 1
+            sub = batch.subset(range(l0, l1))
+            r = ctx.run(sub, want_aln=True)
+            cov[l0:l1], af[l0:l1] = r.cov2x, r.af
+            rn = [names_by_hash.get(int(h), "read_%08x" % int(h)) for h in sub.read_hash]
+            realign.write_realign_bams(sub, r, rn, [os.path.join(out_dir, locus_names[l]) for l in range(l0, l1)])
+            l0 = l1
+    finally:
+        ctx.close()
+    return cov, af
+
+
+def read_fasta_names(path):
+    """(id, None) of every record of a FASTA/FASTQ file (plain or gzip) without keeping sequences."""
+    import gzip
+    op = gzip.open if open(path, "rb").read(2) == b"\x1f\x8b" else open
+    with op(path, "rb") as fh:
+        first = fh.read(1)
+        fh.seek(0)
+        if first == b"@":
+            while True:
+                h = fh.readline()
+                if not h:
+                    break
+                fh.readline(); fh.readline(); fh.readline()
+                yield h[1:].split()[0].decode(), None
+        else:
+            for line in fh:
+                if line.startswith(b">"):
+                    yield (line[1:].split() or [b""])[0].decode(), None
+
+
 def locus_costs(batch: Batch) -> np.ndarray:
     """Cost estimate of every locus for the partitioner: read bases + contig length."""
     lrb = batch.locus_read_begin
@@ -237,9 +285,13 @@ def get_af(out, sample_name, bam, raw_reads, contig_te_annotation, contig_dir, v
     batch = Batch(PRESETS[presets], g.seq2, g.nmask, g.read_off, g.read_len, g.read_hash, lrb, g.contig_off, g.contig_len, te_s, te_e,
                   int(flank_intervel_size), int(flank_offset), int(te_interval_size or 0), int(te_offset), meta={"owner": g})      # the arrays are views of g's buffers
     empty = [j for j in range(len(live)) if lrb[j + 1] == lrb[j]]
+    keep_bam = os.environ.get("TELR_B200_KEEP_BAM", "0") == "1"      # the `-k` intermediates <locus>[.revcomp].realign.sort.bam(.bai)
     if batch.n_loci:
         try:
-            cov2x, af, _ = run_batch(batch)
+            if keep_bam:
+                cov2x, af = _run_with_bams(batch, [names_l[i] for i in live], telr_reads_dir, raw_reads)
+            else:
+                cov2x, af, _ = run_batch(batch)
         except Exception as e:     # noqa: BLE001   (TELR_te.py:649-652)
             print(e)
             print("Local realignment failed, exiting...")
@@ -277,10 +329,14 @@ def get_af(out, sample_name, bam, raw_reads, contig_te_annotation, contig_dir, v
                 d["te_5p_cov" + sfx], d["te_3p_cov" + sfx], d["flank_5p_cov" + sfx], d["flank_3p_cov" + sfx] = cov
                 if strand:
                     freq = combine_af(te_flank_ratio(d["te_5p_cov"], d["flank_5p_cov"]), te_flank_ratio(d["te_5p_cov_rc"], d["flank_5p_cov_rc"]))
-                    g = af[j]                       # device value before clamp/round; must agree with the Python formula
-                    ok = math.isnan(g) if freq is None else (not math.isnan(g) and abs(round(1 if g > 1 else g, 3) - freq) < 1e-9)
+                    # the returned value is the reference's own formula on the coverage integers; the device value (fp64, before
+                    # clamp/round) is only cross-checked against it, to the tolerance the path promises (1e-9 relative)
+                    g = af[j]
+                    t5, t3 = te_flank_ratio(d["te_5p_cov"], d["flank_5p_cov"]), te_flank_ratio(d["te_5p_cov_rc"], d["flank_5p_cov_rc"])
+                    raw = ((t5 + t3) / 2 if abs(t5 - t3) <= 0.3 else None) if (t5 and t3) else (t5 or t3 or None)
+                    ok = math.isnan(g) if raw is None else (not math.isnan(g) and abs(g - raw) <= 1e-9 * abs(raw))
                     if not ok:
-                        raise RuntimeError(f"{name}: device AF {g!r} disagrees with the reference formula {freq!r}")
+                        raise RuntimeError(f"{name}: device AF {g!r} disagrees with the reference formula {raw!r}")
                     d["freq"] = freq
     logging.info("Allele frequency estimation finished in " + format_time(time.time() - start_time))
     return te_freq

@@ -24,7 +24,7 @@ static void opt_from_orc(Opt &o, const orc_opt_t &p)
     o.rmq_rescue_size = p.rmq_rescue_size; o.rmq_rescue_ratio = p.rmq_rescue_ratio;
     o.chn_pen_gap = (float)(p.chain_gap_scale * 0.01 * p.k); o.chn_pen_skip = (float)(p.chain_skip_scale * 0.01 * p.k);
     o.mask_level = p.mask_level; o.mask_len = p.mask_len; o.pri_ratio = p.pri_ratio; o.best_n = p.best_n;
-    o.q_occ_frac = p.q_occ_frac; o.mid_occ_frac = p.mid_occ_frac; o.min_mid_occ = p.min_mid_occ; o.max_mid_occ = p.max_mid_occ;
+    o.q_occ_frac = p.q_occ_frac; o.mid_occ_frac = p.mid_occ_frac; o.min_mid_occ = p.min_mid_occ; o.max_mid_occ = p.max_mid_occ; o.max_max_occ = p.max_max_occ; o.occ_dist = p.occ_dist;
     o.seed_term = wang_hash32((uint32_t)p.seed); o.max_sw_mat = p.max_sw_mat; o.rank_min_len = p.rank_min_len;
     o.rank_frac = p.rank_frac; o.max_clip_ratio = p.max_clip_ratio;
 }

@@ -22,7 +22,7 @@ class OrcOpt(C.Structure):
         ("rmq_rescue_ratio", C.c_float), ("chain_gap_scale", C.c_float), ("chain_skip_scale", C.c_float),
         ("mask_level", C.c_float), ("mask_len", C.c_int32), ("pri_ratio", C.c_float), ("best_n", C.c_int32),
         ("q_occ_frac", C.c_float), ("mid_occ_frac", C.c_float), ("min_mid_occ", C.c_int32),
-        ("max_mid_occ", C.c_int32), ("seed", C.c_int32), ("max_sw_mat", C.c_int64), ("rank_min_len", C.c_int32),
+        ("max_mid_occ", C.c_int32), ("max_max_occ", C.c_int32), ("occ_dist", C.c_int32), ("seed", C.c_int32), ("max_sw_mat", C.c_int64), ("rank_min_len", C.c_int32),
         ("rank_frac", C.c_float), ("max_clip_ratio", C.c_float)]
 
 
@@ -71,6 +71,7 @@ def lib():
                                   C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(OrcDbg)]
         L.orc_dbg_free.argtypes = [C.POINTER(OrcDbg)]
         L.orc_radix_sort_128x.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_set_bw.argtypes = [C.c_int, C.c_int]
         L.orc_name_hash.restype = C.c_uint32
         L.orc_name_hash.argtypes = [C.c_char_p]
         _LIB = L
@@ -172,3 +173,8 @@ def map_one(o: OrcOpt, contig: np.ndarray, read: np.ndarray, name_hash: int = 0,
                         if dbg.n_regs0 else np.zeros((0, 10), np.int32))
         lib().orc_dbg_free(C.byref(dbg))
     return out
+
+
+def set_bw(bw: int = 0, bw_long: int = 0):
+    """minimap2 -r NUM[,NUM] on top of the preset for af_run (0 = preset value)."""
+    lib().orc_set_bw(int(bw), int(bw_long))

@@ -348,6 +348,60 @@ def test_degenerate_reads_and_contigs(ctx):
     assert r.c.dp_cells == ro.c.dp_cells
 
 
+def _batch_from_sequences(preset, loci):
+    """loci: [(contig nt4 array, [read nt4 arrays], te_start, te_end)] -> Batch"""
+    from telr_b200.batch import Batch, pack_sequences, name_hash
+    ACGT = np.frombuffer(b"ACGTN", np.uint8)
+    seqs, lrb, n_reads = [], [0], 0
+    for c, reads, _, _ in loci:
+        seqs += [bytes(ACGT[r]) for r in reads]
+        n_reads += len(reads)
+        lrb.append(n_reads)
+    seqs += [bytes(ACGT[c]) for c, _, _, _ in loci]
+    seq2, nmask, offs, lens = pack_sequences(seqs)
+    return Batch(preset, seq2, nmask, offs[:n_reads].copy(), lens[:n_reads].copy(), np.array([name_hash("rr%d" % i) for i in range(n_reads)], np.uint32),
+                 np.array(lrb, np.int32), offs[n_reads:].copy(), lens[n_reads:].copy(), np.array([l[2] for l in loci], np.int32), np.array([l[3] for l in loci], np.int32))
+
+
+def _repeat_motif_batch(preset, seed=300):
+    """Contigs (36-45 kb) that carry one k-mer with a very small hash ~55 times, 700-800 bp apart: that single key exceeds
+    mid_occ on the index side (in a single-contig index mid_occ sits at the 0.9998 quantile of the key counts, so only the top
+    one or two keys ever can), while a read sees it too rarely for the query-side filter: mm_seed_select and the rep_len term
+    of the MAPQ run.  The five synthetic configurations never reach this path (tests/test_oracle_props.py counters)."""
+    rng = np.random.default_rng(seed + preset)
+    o = orc.opt(preset)
+    cands = rng.integers(0, 4, (4000, o.k)).astype(np.uint8)
+    hashes = [int(orc.sketch(c, o.w, o.k, 0)[0][0] >> 8) if len(orc.sketch(c, o.w, o.k, 0)[0]) else 1 << 62 for c in cands]
+    motif = cands[int(np.argmin(hashes))]
+    loci = []
+    for n_copies, gap in (((55, 700), (60, 760)) if preset == 0 else ((75, 800), (80, 820))):
+        parts = [rng.integers(0, 4, 1200).astype(np.uint8)]
+        for _ in range(n_copies):
+            parts += [motif, rng.integers(0, 4, gap + int(rng.integers(0, 40))).astype(np.uint8)]
+        contig = np.concatenate(parts)
+        reads = []
+        for _ in range(8):
+            ln = int(rng.integers(5000, 9000)); a = int(rng.integers(0, len(contig) - ln))
+            rd = _mut(rng, contig[a:a + ln], 0.05 if preset == 0 else 0.002)
+            reads.append(rd if rng.random() < .5 else (3 - rd[::-1]).astype(np.uint8))
+        loci.append((contig, reads, 5000, len(contig) - 5000))
+    return _batch_from_sequences(preset, loci)
+
+
+@pytest.mark.parametrize("preset", [0, 2])
+def test_high_occurrence_seeds_are_selected_like_upstream(ctx, preset):
+    import ctypes as C
+    b = _repeat_motif_batch(preset)
+    out = (C.c_int64 * 8)()
+    orc.lib().orc_dev_counters(out, 1)
+    ro = orc.af_run(b, threads=0)
+    orc.lib().orc_dev_counters(out, 1)
+    assert out[0] > 50, list(out)                        # high-occurrence seeds were met on the index side
+    r = ctx.run(b, want_depth=True, want_aln=True)
+    util.assert_same_results(r, ro)
+    assert r.c.dp_cells == ro.c.dp_cells and r.c.n_anchors == ro.c.n_anchors
+
+
 def test_long_read_config_matches_oracle(ctx):
     b = synth.generate("ont_30k_30x", 0, 2, depth=5)
     r = ctx.run(b, want_depth=True, want_aln=True)
@@ -530,3 +584,94 @@ def test_contig_longer_than_the_shared_memory_depth_row(ctx):
     ro = orc.af_run(b, threads=0)
     util.assert_same_results(r, ro)
     assert r.c.dp_cells == ro.c.dp_cells
+
+
+def _rec_key(r):
+    return (r["qname"], r["flag"], r["tid"], r["pos"], r["mapq"], tuple(int(x) for x in r["cigar"]), bytes(r["seq"]) if not isinstance(r["seq"], str) else r["seq"], r["aux"])
+
+
+def test_get_af_keeps_the_realign_bams(built, tmp_path, monkeypatch):
+    """Row f2: with TELR_B200_KEEP_BAM=1 the drop-in leaves <locus>.realign.sort.bam / <locus>.revcomp.realign.sort.bam (+ .bai) in
+    telr_reads/ like realignment() (TELR_te.py:502-515); their records equal the SAM records built from the oracle's regions
+    (FLAG 0x10/0x100/0x800, POS, MAPQ, CIGAR with clips, SEQ, tags) and `samtools depth` over them gives the coverage integers."""
+    from telr_b200 import realign
+    from tests.test_host import _depth_from_records
+    b = synth.generate("ont_3k_50x", 0, 3, depth=10)
+    kw = _make_stage3_artifacts(tmp_path, b)
+    monkeypatch.setenv("TELR_B200_KEEP_BAM", "1")
+    te_freq = stage4.get_af(**kw)
+    assert len(te_freq) == 3
+    ro = orc.af_run(b, threads=0)
+    names = [f"L{l:06d}_R{r - b.locus_read_begin[l]:04d}" for l in range(3) for r in range(b.locus_read_begin[l], b.locus_read_begin[l + 1])]
+    off = np.concatenate([[0], np.cumsum(2 * b.contig_len.astype(np.int64))])
+    for l in range(3):
+        L = int(b.contig_len[l])
+        for strand, sfx in ((0, ""), (1, ".revcomp")):
+            p = os.path.join(kw["out"], "telr_reads", f"chr1_{10000 * (l + 1)}_{10000 * (l + 1) + 1}{sfx}.realign.sort.bam")
+            assert os.path.isfile(p) and os.path.isfile(p + ".bai")
+            _, refs, recs = realign.read_bam(p)
+            assert refs == [("ctg1", L)]
+            want = realign.strand_records(b, ro, l, strand, names)
+            order = sorted(range(len(want)), key=lambda i: (want[i]["tid"] & 0xffffffff, want[i]["pos"]))      # samtools sort (stable)
+            assert len(recs) == len(want)
+            for g, i in zip(recs, order):
+                w = want[i]
+                assert (g["qname"], g["flag"], g["tid"], g["pos"], g["mapq"]) == (w["qname"], w["flag"], w["tid"], w["pos"], w["mapq"])
+                assert (g["cigar"] == w["cigar"]).all() and g["seq"] == w["seq"].decode()
+            assert (_depth_from_records(recs, L) == ro.depth[off[l] + strand * L: off[l] + (strand + 1) * L]).all()
+
+
+def test_polishing_alignment_r2k_matches_oracle(ctx, tmp_path):
+    """Row f1: `minimap2 -ax map-ont -r2k contig reads | samtools sort` (TELR_assembly.py:199-212) = the same kernels with bw 2000."""
+    from telr_b200 import realign
+    b0 = synth.generate("ont_3k_50x", 11, 1, depth=14)
+    acgt = np.frombuffer(b"ACGTN", np.uint8)
+    contig = acgt[b0.unpack(int(b0.contig_off[0]), int(b0.contig_len[0]))].tobytes()
+    reads = [(f"r{r}", acgt[b0.unpack(int(b0.read_off[r]), int(b0.read_len[r]))].tobytes()) for r in range(b0.n_reads)]
+    bam = str(tmp_path / "polish.bam")
+    n = realign.align_to_bam("ctg1", contig, reads, "map-ont", bam, bw=2000, ctx=ctx)
+    _, refs, recs = realign.read_bam(bam)
+    assert refs == [("ctg1", len(contig))] and len(recs) == n and os.path.isfile(bam + ".bai")
+    b, names = realign._batch_of("map-ont", [("ctg1", contig)], [reads])
+    orc.set_bw(2000, 0)
+    try:
+        ro = orc.af_run(b, threads=0)
+    finally:
+        orc.set_bw(0, 0)
+    want = realign.strand_records(b, ro, 0, 0, names)
+    order = sorted(range(len(want)), key=lambda i: (want[i]["tid"] & 0xffffffff, want[i]["pos"]))
+    assert len(recs) == len(want)
+    for g, i in zip(recs, order):
+        w = want[i]
+        assert (g["qname"], g["flag"], g["pos"], g["mapq"]) == (w["qname"], w["flag"], w["pos"], w["mapq"]) and (g["cigar"] == w["cigar"]).all()
+    # the option is per call: the next run on the same context uses the preset bandwidth again
+    r_def = ctx.run(b, want_aln=True)
+    ro_def = orc.af_run(b, threads=0)
+    util.assert_same_results(r_def, ro_def)
+
+
+def test_annotation_alignments_paf_match_oracle(ctx):
+    """Row f4: `minimap2 -cx <preset> --secondary=no contig query` (VCF insertion sequence vs its contig, TELR_te.py:68-78) and
+    `minimap2 -cx <preset> contig te_library` (TELR_te.py:119-132): PAF lines with cg:Z:, all contigs in one batch."""
+    from telr_b200 import realign
+    rng = np.random.default_rng(17)
+    b0 = synth.generate("ont_3k_50x", 20, 4, depth=4)
+    acgt = np.frombuffer(b"ACGTN", np.uint8)
+    contigs, queries = [], []
+    lib_te = [(f"TE{k}", acgt[rng.integers(0, 4, int(rng.integers(800, 3000)))].tobytes()) for k in range(3)]
+    for l in range(4):
+        c = b0.unpack(int(b0.contig_off[l]), int(b0.contig_len[l]))
+        contigs.append((f"chr1_{l}_ctg", acgt[c].tobytes()))
+        ts, te = int(b0.te_start[l]), int(b0.te_end[l])
+        ins = _mut(rng, c[ts:te], 0.03)                                   # the insertion sequence Sniffles reported for this locus
+        qs = [(f"ins{l}", acgt[ins].tobytes()), (f"ins{l}_rc", acgt[(3 - ins[::-1])].tobytes())] + lib_te + [(f"fam{l}", acgt[_mut(rng, c[ts:te], 0.1)].tobytes())]
+        queries.append(qs)
+    for secondary in (False, True):
+        got = realign.align_to_paf(contigs, queries, "map-ont", secondary=secondary, ctx=ctx)
+        b, names = realign._batch_of("map-ont", contigs, queries)
+        ro = orc.af_run(b, threads=0)
+        want = realign.paf_lines(b, ro, names, [c[0] for c in contigs], secondary=secondary)
+        assert got == want and len(got) >= 8
+        f = got[0].split("\t")
+        assert len(f) >= 12 and f[4] in "+-" and f[-1].startswith("cg:Z:") and int(f[3]) - int(f[2]) > 500
+    assert all("tp:A:S" not in ln for ln in realign.align_to_paf(contigs, queries, "map-ont", secondary=False, ctx=ctx))

@@ -8,7 +8,7 @@ import re
 import numpy as np
 import pytest
 
-from telr_b200 import bamio, gather, lib, stage4, synth
+from telr_b200 import bamio, gather, lib, realign, stage4, synth
 from telr_b200.batch import Batch, PRESETS, name_hash, pack_sequences
 from tests import orc, util
 
@@ -341,3 +341,68 @@ def test_two_rank_sharding_gloo(built):
     b = synth.generate("ont_3k_50x", 0, 6, depth=6)
     ref = orc.af_run(b, threads=0, want_depth=False, want_aln=False)
     assert (cov == ref.cov2x).all()
+
+
+def _depth_from_records(recs, L):
+    """`samtools depth -aa` over BAM records: every record that is not SECONDARY or UNMAPPED, M/=/X bases only."""
+    d = np.zeros(L + 1, np.int64)
+    for r in recs:
+        if r["flag"] & 0x104:
+            continue
+        pos = r["pos"]
+        for w in r["cigar"].tolist():
+            op, ln = w & 15, w >> 4
+            if op in (0, 7, 8):
+                d[pos] += 1; d[pos + ln] -= 1; pos += ln
+            elif op in (2, 3):
+                pos += ln
+    return np.cumsum(d)[:L]
+
+
+def test_realign_bam_records_reproduce_the_depth(built, tmp_path):
+    """Row f2 on the host: SAM records built from alignment records (here the oracle's), written as sorted BAM + BAI by the
+    native writer, read back: coordinate order, FLAG/CIGAR/SEQ consistency of `minimap2 -a` output, and `samtools depth`
+    recomputed from the BAM equals the depth the path reports for that contig strand."""
+    b = synth.generate("ont_3k_50x", 7, 3, depth=12)
+    ro = orc.af_run(b, threads=0)
+    names = [f"read{r}" for r in range(b.n_reads)]
+    paths = realign.write_realign_bams(b, ro, names, [str(tmp_path / f"L{l}") for l in range(b.n_loci)])
+    assert len(paths) == 6 and all(os.path.isfile(p) and os.path.isfile(p + ".bai") for p in paths)
+    off = np.concatenate([[0], np.cumsum(2 * b.contig_len.astype(np.int64))])
+    for l in range(b.n_loci):
+        L = int(b.contig_len[l])
+        for strand in (0, 1):
+            text, refs, recs = realign.read_bam(paths[2 * l + strand])
+            assert refs == [("ctg1", L)] and text.startswith("@HD\tVN:1.6\tSO:coordinate")
+            mapped = [r for r in recs if not r["flag"] & 4]
+            assert [r["pos"] for r in mapped] == sorted(r["pos"] for r in mapped) and all(r["flag"] & 4 for r in recs[len(mapped):])
+            want = ro.depth[off[l] + strand * L: off[l] + (strand + 1) * L]
+            assert (_depth_from_records(recs, L) == want).all()
+            n_reads_l = int(b.locus_read_begin[l + 1] - b.locus_read_begin[l])
+            assert len({r["qname"] for r in recs}) == n_reads_l                       # every read has at least one line
+            for r in mapped:
+                op, ln = r["cigar"] & 15, r["cigar"] >> 4
+                qlen_cig = int(ln[(op == 0) | (op == 1) | (op == 4)].sum())
+                rd = int(r["qname"][4:])
+                full = int(ln[(op == 0) | (op == 1) | (op == 4) | (op == 5)].sum())
+                assert full == int(b.read_len[rd])                                     # clips + aligned query = read length
+                if r["flag"] & 0x100:
+                    assert r["seq"] == "" and (op != 4).all()                          # secondary: SEQ '*', hard clips
+                else:
+                    assert len(r["seq"]) == qlen_cig
+                    assert ((op != 5).all() if not r["flag"] & 0x800 else (op != 4).all())
+                assert {"NM", "ms", "AS", "nn", "tp", "cm", "s1", "de"} <= set(r["tags"]) and 0 <= r["mapq"] <= 60
+                assert r["tags"]["tp"] == ("S" if r["flag"] & 0x100 else r["tags"]["tp"]) and ("s2" in r["tags"]) == (not r["flag"] & 0x100)
+            # primary SEQ is the read (reverse-complemented for reverse hits)
+            prim = next(r for r in mapped if not r["flag"] & 0x900)
+            rd = int(prim["qname"][4:])
+            codes = b.unpack(int(b.read_off[rd]), int(b.read_len[rd]))
+            fw = "".join("ACGTN"[c] for c in codes)
+            rc = "".join("TGCAN"[c] for c in codes[::-1])
+            assert prim["seq"] == (rc if prim["flag"] & 0x10 else fw)
+            # the index serves window queries on the written file
+            f = gather.BamFile(paths[2 * l + strand])
+            mid = L // 2
+            want_names = sorted({r["qname"] for r in mapped if r["pos"] < mid + 50 and r["pos"] + int((r["cigar"] >> 4)[np.isin(r["cigar"] & 15, (0, 2, 3, 7, 8))].sum()) > mid})
+            assert sorted(set(f.fetch("ctg1", mid, mid + 50))) == want_names
+            f.close()

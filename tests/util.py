@@ -29,7 +29,8 @@ def load_config1():
                  d["contig_off"], d["contig_len"], d["te_start"], d["te_end"])
 
 
-ALN_FIELDS = ("read", "strand", "rs", "re", "qs", "qe", "rev", "flag", "dp_max", "mlen", "blen", "n_cigar")
+ALN_FIELDS = ("read", "strand", "rs", "re", "qs", "qe", "rev", "flag", "dp_max", "mlen", "blen", "n_cigar",
+              "mapq", "dp_score", "cnt", "score", "subsc", "n_ambi", "inv", "n_sub")
 
 
 def assert_same_results(r, ro, check_aln=True):
