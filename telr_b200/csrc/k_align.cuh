@@ -18,11 +18,6 @@ namespace telr {
 
 // The cycle census (TELR_CENSUS=1) costs 1.5 KB of code inside the hottest loop of an instruction-cache-bound kernel, so it is
 // compiled in only with -DTELR_CENSUS_BUILD=1 (profiles/census.sh builds that variant).
-// Batched gap fills (warp_fill_stream, k_fill.cuh) are bit-exact but slower inside this kernel (profiles/README.md): compiled in
-// only with -DTELR_FILL_STREAM=1, then enabled per context with TELR_FILL_BATCH=<fills per batch>.
-#ifndef TELR_FILL_STREAM
-#define TELR_FILL_STREAM 0
-#endif
 #ifndef TELR_CENSUS_BUILD
 #define TELR_CENSUS_BUILD 0
 #endif
@@ -74,7 +69,7 @@ struct AlignArgs {
     const int32_t *work_list;
     AlWork *work; AlnCtx *actx; DpTask *tasks; DpRes *res;
     uint32_t *cigs;
-    uint8_t *warp_scratch; size_t warp_scratch_stride; int32_t max_tlen, max_qlen, use_fast, use_vec, census, fill_batch; int64_t dir_cap;    // per resident warp: spilled DP state + traceback bytes
+    uint8_t *warp_scratch; size_t warp_scratch_stride; int32_t max_tlen, max_qlen, use_fast, use_vec, census; int64_t dir_cap;    // per resident warp: spilled DP state + traceback bytes
     uint8_t *big; int64_t big_cap; int32_t n_big; int32_t *big_lock;                          // shared large traceback buffers
     unsigned long long *rc;      // [2] work queue head
     int32_t *err;
@@ -356,9 +351,6 @@ __device__ void extd2_traceback(const DpTask &T, DpRes &R, const uint8_t *p, uin
 __device__ __forceinline__ int warp_extd2(const Opt &o, const DpTask &T, DpRes &R, DpScratch &S, unsigned long long *cells_acc, int32_t *err)
 {
     if (S.vsm && vec_ok(o, T.qlen, T.tlen, T.w) && vec_dir_bytes(T.qlen, T.tlen, T.w) <= S.dir_cap) {
-#if TELR_LANE_EXT
-        if (T.tlen <= 32 && !(T.flag & KSW_APPROX_MAX)) { if (warp_extd2_lane(o, T, R, S.dir, cells_acc)) return 1; } else
-#endif
         if (warp_extd2_vec(o, T, R, *S.vsm, S.stab, S.dir, cells_acc)) return 1;
     }
     warp_extd2_impl<false>(o, T, R, S, cells_acc, err);      // ambiguous bases or a band wider than the window: state arrays in global memory
@@ -459,69 +451,10 @@ __global__ void __launch_bounds__(128) k_al_init(const __grid_constant__ AlignAr
     A.res[w].cigar = A.cigs + W.ez_off;
 }
 
-#if TELR_FILL_STREAM
-// Batched gap fills: `task` (a fast-path fill just emitted by the coroutine) plus the fills that will follow it if none of
-// them z-drops run as one systolic stream (warp_fill_stream); their direction bytes share the warp's traceback buffer.
-// Returns the number of fills computed (0: the task has to take the single-fill path).  Speculative results that the
-// coroutine does not ask for afterwards are simply dropped.
-__device__ int fill_batch_run(const Opt &o, const FillLut &L, const AlnCtx &c, const DpTask &task, FillJob *jobs, int max_jobs, uint8_t *dir, int64_t dir_cap, uint32_t *bnd,
-                              uint32_t *bnd_smem, int bnd_smem_pairs, uint8_t *b2j)
-{
-    const int lane = threadIdx.x & 31;
-    const unsigned FULL = 0xffffffffu;
-    __shared__ int nj_s[AL_WARPS];
-    int &nj = nj_s[threadIdx.x >> 5];
-    if (lane == 0) {
-        PeekFill pk[FB_MAX];
-        pk[0].q = task.q; pk[0].t = task.t; pk[0].qlen = task.qlen; pk[0].tlen = task.tlen;
-        int n = 1 + (max_jobs > 1 ? aln_peek_fills(c, pk + 1, max_jobs - 1) : 0);
-        int64_t off = 0; int blk = 0, k = 0;
-        const int np0 = (task.qlen + 1) >> 1;
-        for (; k < n; ++k) {
-            const int64_t need = ((int64_t)pk[k].qlen * fill_stride(pk[k].tlen) + 15) & ~(int64_t)15;
-            if (off + need > dir_cap) break;
-            const int np = (pk[k].qlen + 1) >> 1;
-            if (blk + ((pk[k].tlen + 7) >> 3) > FB_MAX_BLOCKS) break;
-            if (k > 0 && (np > np0 + (np0 >> 1) || np < np0 - (np0 >> 1))) break;      // a round lasts as long as the tallest fill: keep heights within 50 %
-            jobs[k].q = pk[k].q; jobs[k].t = pk[k].t; jobs[k].qlen = pk[k].qlen; jobs[k].tlen = pk[k].tlen;
-            jobs[k].dir = dir + off; jobs[k].blk0 = blk; jobs[k].score = 0;
-            off += need; blk += (pk[k].tlen + 7) >> 3;
-        }
-        nj = k;
-    }
-    __syncwarp();
-    int n = nj;
-    // ambiguous bases take the general path: the batch ends before the first fill that has one
-    for (int k = 0; k < n; ++k) {
-        bool amb = false;
-        for (int i = lane; i < jobs[k].qlen; i += 32) amb |= jobs[k].q[i] > 3;
-        for (int i = lane; i < jobs[k].tlen; i += 32) amb |= jobs[k].t[i] > 3;
-        if (__any_sync(FULL, amb)) { n = k; break; }
-    }
-    if (o.a > 127 || o.b > 127) n = 0;
-    if (n > 0) {
-        int np_max = 32;
-        for (int k = 0; k < n; ++k) np_max = max(np_max, (jobs[k].qlen + 1) >> 1);
-        const int total = jobs[n - 1].blk0 + ((jobs[n - 1].tlen + 7) >> 3);
-        for (int g = lane; g < total; g += 32) {          // block -> fill
-            int f2 = 0;
-            for (int f = 1; f < n; ++f) if (jobs[f].blk0 <= g) f2 = f;
-            b2j[g] = (uint8_t)f2;
-        }
-        __syncwarp();
-        warp_fill_stream(o, L, jobs, n, np_max <= bnd_smem_pairs ? bnd_smem : bnd, b2j);     // the hand-over column lives in the idle DP window when it fits
-    }
-    return n;
-}
-#endif
 
 // coroutine + DP + traceback for one problem per warp (persistent warps, dynamic queue, no global barriers).
 // The coroutine state lives in shared memory while the warp owns the problem and is written back for k_al_finish.
-#if TELR_FILL_STREAM
-struct AlWarpSmem { AlnCtx c; DpTask task; DpRes res; int more, role; FillJob jobs[FB_MAX]; int n_jobs, job_next; uint8_t b2j[FB_MAX_BLOCKS]; };
-#else
 struct AlWarpSmem { AlnCtx c; DpTask task; DpRes res; int more, role; };
-#endif
 
 __global__ void __launch_bounds__(AL_THREADS, AL_BLOCKS_PER_SM) k_al_fused(const __grid_constant__ AlignArgs A)
 {
@@ -545,10 +478,6 @@ __global__ void __launch_bounds__(AL_THREADS, AL_BLOCKS_PER_SM) k_al_fused(const
     uint8_t *own_dir = base;
     S.s_state = nullptr; S.s_H = nullptr; S.vsm = A.use_vec ? &DS[wid] : nullptr; S.stab = stab;
     vec_fill_stab(stab, o);
-#if TELR_FILL_STREAM
-    __shared__ FillLut flut;
-    fill_lut_init(flut, o);
-#endif
     for (;;) {
         int wi = 0;
         if (lane == 0) wi = (int)atomicAdd(&A.rc[2], 1ULL);
@@ -560,9 +489,6 @@ __global__ void __launch_bounds__(AL_THREADS, AL_BLOCKS_PER_SM) k_al_fused(const
             for (int i = lane; i < (int)(sizeof(AlnCtx) / 4); i += 32) dst[i] = src[i];
         }
         if (lane == 0) { res_reset(W.res); W.res.cigar = A.cigs + A.work[wi].ez_off; }
-#if TELR_FILL_STREAM
-        if (lane == 0) { W.n_jobs = 0; W.job_next = 0; }
-#endif
         S.ezcig = A.cigs + A.work[wi].ez_off; S.ezcap = A.work[wi].ez_cap;
         __syncwarp();
         for (;;) {
@@ -575,46 +501,6 @@ __global__ void __launch_bounds__(AL_THREADS, AL_BLOCKS_PER_SM) k_al_fused(const
             __syncwarp();
             if (!W.more) break;
             if (AL_CENSUS(A)) t0 = clock64();
-#if TELR_FILL_STREAM
-            bool served = false;
-            if (W.task.kind == 0 && A.fill_batch && A.use_fast && fill_fast_ok(W.task)) {
-                // the pending batch holds this very fill?  otherwise start a new batch with it
-                int hit = -1;
-                if (W.job_next < W.n_jobs) {
-                    const FillJob &J = W.jobs[W.job_next];
-                    if (J.q == W.task.q && J.t == W.task.t && J.qlen == W.task.qlen && J.tlen == W.task.tlen) hit = W.job_next;
-                }
-                if (hit < 0) {
-                    long long tb0 = 0;
-                    if (AL_CENSUS(A)) tb0 = clock64();
-                    const int n = fill_batch_run(o, flut, W.c, W.task, W.jobs, A.fill_batch, own_dir, A.dir_cap, S.bnd, reinterpret_cast<uint32_t *>(DS[wid].st), (int)(sizeof(DS[wid].st) / 12), W.b2j);
-                    if (lane == 0) { W.n_jobs = n; W.job_next = 0; }
-                    if (AL_CENSUS(A) && lane == 0) {
-                        atomicAdd(&A.rc[90], (unsigned long long)n); atomicAdd(&A.rc[91], 1ULL); atomicAdd(&A.rc[93], (unsigned long long)(clock64() - tb0));
-                        unsigned long long cells = 0; for (int k = 0; k < n; ++k) cells += (unsigned long long)W.jobs[k].qlen * W.jobs[k].tlen;
-                        atomicAdd(&A.rc[94], cells);
-                    }
-                    __syncwarp();
-                    hit = n > 0 ? 0 : -1;
-                }
-                if (hit >= 0) {
-                    const FillJob &J = W.jobs[hit];
-                    if (lane == 0) {
-                        res_reset(W.res); W.res.score = J.score;
-                        atomicAdd(A.stat_cells, (unsigned long long)J.qlen * (unsigned long long)J.tlen);
-                    }
-                    __syncwarp();
-                    fill_traceback(W.task, W.res, J.dir, S.ezcig, S.ezcap, A.err, *reinterpret_cast<TbSmem *>(DS[wid].H));
-                    if (lane == 0) W.job_next = hit + 1;
-                    if (AL_CENSUS(A) && lane == 0) atomicAdd(&A.rc[92], 1ULL);
-                    __syncwarp();
-                    served = true;
-                }
-            }
-            if (!served && lane == 0) W.n_jobs = 0;        // anything else invalidates what was computed ahead
-            if (served) {
-            } else
-#endif
             if (W.task.kind == 0) {
                 const bool fast = A.use_fast && fill_fast_ok(W.task);
                 const int64_t need = fast ? (int64_t)W.task.qlen * fill_stride(W.task.tlen) : vec_dir_bytes(W.task.qlen, W.task.tlen, W.task.w);
@@ -722,47 +608,10 @@ __device__ __forceinline__ int aq_pop(const AlignArgs &A, int role)
     return v - 1;
 }
 
-#if TELR_FILL_STREAM
-#define AQ_FLUT_PARAM , const FillLut &flut
-#define AQ_FLUT_ARG , flut
-#else
-#define AQ_FLUT_PARAM
-#define AQ_FLUT_ARG
-#endif
-__device__ __forceinline__ void aq_exec(const AlignArgs &A, const Opt &o, AlWarpSmem &W, DpScratch &S, uint8_t *own_dir, VecSmem &vs AQ_FLUT_PARAM)
+__device__ __forceinline__ void aq_exec(const AlignArgs &A, const Opt &o, AlWarpSmem &W, DpScratch &S, uint8_t *own_dir, VecSmem &vs)
 {
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
-#if TELR_FILL_STREAM
-    if (W.task.kind == 0 && A.fill_batch && A.use_fast && fill_fast_ok(W.task)) {
-        // the pending batch holds this very fill?  otherwise start a new batch with it
-        int hit = -1;
-        if (W.job_next < W.n_jobs) {
-            const FillJob &J = W.jobs[W.job_next];
-            if (J.q == W.task.q && J.t == W.task.t && J.qlen == W.task.qlen && J.tlen == W.task.tlen) hit = W.job_next;
-        }
-        if (hit < 0) {
-            const int n = fill_batch_run(o, flut, W.c, W.task, W.jobs, A.fill_batch, own_dir, A.dir_cap, S.bnd, reinterpret_cast<uint32_t *>(vs.st), (int)(sizeof(vs.st) / 12), W.b2j);
-            if (lane == 0) { W.n_jobs = n; W.job_next = 0; }
-            __syncwarp();
-            hit = n > 0 ? 0 : -1;
-        }
-        if (hit >= 0) {
-            const FillJob &J = W.jobs[hit];
-            if (lane == 0) {
-                res_reset(W.res); W.res.score = J.score;
-                atomicAdd(A.stat_cells, (unsigned long long)J.qlen * (unsigned long long)J.tlen);
-            }
-            __syncwarp();
-            fill_traceback(W.task, W.res, J.dir, S.ezcig, S.ezcap, A.err, *reinterpret_cast<TbSmem *>(vs.H));
-            if (lane == 0) W.job_next = hit + 1;
-            __syncwarp();
-            return;
-        }
-    }
-    if (lane == 0) W.n_jobs = 0;        // anything else invalidates what was computed ahead
-    __syncwarp();
-#endif
     if (W.task.kind == 0) {
         const bool fast = A.use_fast && fill_fast_ok(W.task);
         const int64_t need = fast ? (int64_t)W.task.qlen * fill_stride(W.task.tlen) : vec_dir_bytes(W.task.qlen, W.task.tlen, W.task.w);
@@ -819,10 +668,6 @@ __global__ void __launch_bounds__(AL_THREADS, AL_BLOCKS_PER_SM) k_al_queue(const
     uint8_t *own_dir = base;
     S.s_state = nullptr; S.s_H = nullptr; S.vsm = A.use_vec ? &DS[wid] : nullptr; S.stab = stab;
     vec_fill_stab(stab, o);
-#if TELR_FILL_STREAM
-    __shared__ FillLut flut;
-    fill_lut_init(flut, o);
-#endif
     unsigned smid;
     asm("mov.u32 %0, %%smid;" : "=r"(smid));
     // The role belongs to the SM (all its warps run one loop); it starts from a fixed interleave and MOVES when the SM's ring
@@ -874,14 +719,11 @@ __global__ void __launch_bounds__(AL_THREADS, AL_BLOCKS_PER_SM) k_al_queue(const
             }
         }
         if (lane == 0) { res_reset(W.res); W.res.cigar = A.cigs + A.work[wi].ez_off; }
-#if TELR_FILL_STREAM
-        if (lane == 0) { W.n_jobs = 0; W.job_next = 0; }
-#endif
         S.ezcig = A.cigs + A.work[wi].ez_off; S.ezcap = A.work[wi].ez_cap;
         __syncwarp();
         int have_task = !fresh;
         for (;;) {
-            if (have_task) aq_exec(A, o, W, S, own_dir, DS[wid] AQ_FLUT_ARG);
+            if (have_task) aq_exec(A, o, W, S, own_dir, DS[wid]);
             if (lane == 0) {
                 W.more = aln_next(W.c, W.res, W.task) ? 1 : 0;
                 if (W.more) W.more = 1 + aq_role_of(A, W.task);

@@ -13,9 +13,6 @@
 // Requests that contain an ambiguous base, or whose band does not fit the window, return false and take the scalar path.
 #pragma once
 #include "k_fill.cuh"
-#ifndef TELR_LANE_EXT
-#define TELR_LANE_EXT 0
-#endif
 
 namespace telr {
 
@@ -271,129 +268,6 @@ __device__ bool warp_extd2_vec(const Opt &o, const DpTask &T, DpRes &R, VecSmem 
     return true;
 }
 
-#if TELR_LANE_EXT
-// One-column-per-lane form of warp_extd2_vec for targets of at most 32 bases in exact-max mode.  All state is one 32-bit
-// register per array and lane; the left neighbour arrives by shuffle; same seeds, tie order and direction bytes as
-// warp_extd2_vec (bit-exact in the GPU suite).  NOT compiled into the product: alone it is 1.6x faster on the overhang
-// extensions that make up 57 % of the general-DP tasks, but inside k_al_fused its loop body pushes the hot code past the
-// instruction cache and the kernel gets 11 % slower (profiles/README.md).  It is kept for the round-2 design in which
-// extension tasks run on their own SMs.
-__device__ bool warp_extd2_lane(const Opt &o, const DpTask &T, DpRes &R, uint8_t *p, unsigned long long *cells_acc)
-{
-    const int lane = threadIdx.x & 31;
-    const unsigned FULL = 0xffffffffu;
-    const int qlen = T.qlen, tlen = T.tlen, flag = T.flag;
-    const bool RIGHT = flag & KSW_RIGHT;
-    int q = o.q, e = o.e, q2 = o.q2, e2 = o.e2;
-    if (q2 + e2 < q + e) { int t = q; q = q2; q2 = t; t = e; e = e2; e2 = t; }
-    const int qe = q + e, qe2 = q2 + e2;
-    const int w = T.w < 0 ? (tlen > qlen ? tlen : qlen) : T.w;
-    const int vstride = vec_stride(qlen, tlen, T.w);
-    int LT = e != e2 ? (q2 - q) / (e - e2) - 1 : 0;
-    if (q2 + e2 + LT * e2 > q + e + LT * e) ++LT;
-    const int LD = LT * (e - e2) - (q2 - q) - e2;
-    const int QC1 = q - 1 + (RIGHT ? 1 : 0), QC2 = q2 - 1 + (RIGHT ? 1 : 0);
-    const int tc = lane < tlen ? dp_base(T.t, T.tstep, 0, lane) : 0;
-    if (__any_sync(FULL, tc > 3)) return false;
-    int u = 0, v = 0, x = 0, y = 0, x2 = 0, y2 = 0, H = 0;
-    int qbuf = 0, qc = 0;
-    int pst = -1, pen = -1;
-    int32_t ez_max = 0, ez_max_t = -1, ez_max_q = -1, ez_mqe = KSW_NEG_INF, ez_mqe_t = -1, ez_mte = KSW_NEG_INF, ez_mte_q = -1;
-    int32_t ez_score = KSW_NEG_INF, zdropped = 0;
-    unsigned long long cells = 0;
-    const int nr = qlen + tlen - 1;
-    for (int r = 0; r < nr; ++r) {
-        int st = 0, en = tlen - 1;
-        if (st < r - qlen + 1) st = r - qlen + 1;
-        if (en > r) en = r;
-        if (st < (r - w + 1) >> 1) st = (r - w + 1) >> 1;
-        if (en > (r + w) >> 1) en = (r + w) >> 1;
-        if (st > en) { zdropped = 1; break; }
-        cells += (unsigned long long)(en - st + 1);
-        if ((r & 31) == 0) {            // next 32 query bases, one per lane
-            const int i = r + lane;
-            qbuf = i < qlen ? dp_base(T.q, T.qstep, T.qcomp, i) : 0;
-            if (__any_sync(FULL, qbuf > 3)) return false;
-        }
-        {   // the query slides one lane per row: lane t holds q[r - t]
-            const int qn = __shfl_sync(FULL, qbuf, r & 31);
-            qc = __shfl_up_sync(FULL, qc, 1);
-            if (lane == 0) qc = qn;
-        }
-        const int bnd = r == 0 ? -q - e : r < LT ? -e : r == LT ? LD : -e2;
-        if (en > pen && lane == en) { u = v = x = y = -qe; x2 = y2 = -qe2; }
-        if (en == r && lane == r) u = bnd;
-        if ((st == 0 || !(st - 1 >= pst && st - 1 <= pen)) && st > 0 && lane == st - 1) { x = -qe; x2 = -qe2; v = -qe; }
-        int32_t Hp = 0;
-        if (r > 0) Hp = __shfl_sync(FULL, H, en > 0 ? en - 1 : 0);
-        int Lv = __shfl_up_sync(FULL, v, 1), Lx = __shfl_up_sync(FULL, x, 1), Lx2 = __shfl_up_sync(FULL, x2, 1);
-        if (st == 0 && lane == 0) { Lv = bnd; Lx = -qe; Lx2 = -qe2; }
-        const bool act = lane >= st && lane <= en;
-        const int en1 = st + ((en - st) >> 2 << 2);
-        const unsigned n_upd = (unsigned)(en - st), n_trk = (unsigned)(en1 - st);
-        int32_t kmax = INT32_MIN;
-        if (act) {
-            const int S = qc == tc ? o.a : -o.b;
-            const int A = Lx + Lv, A2 = Lx2 + Lv, B = y + u, B2 = y2 + u;
-            const int Z = max(max(max(S, A), max(B, A2)), B2);
-            const int DA = A - Z, DB = B - Z, DA2 = A2 - Z, DB2 = B2 - Z;
-            const int fO = (RIGHT ? B2 : S) - Z;
-            const int nv = Z - u;
-            u = Z - Lv; v = nv;
-            x = max(DA - e, -qe); y = max(DB - e, -qe); x2 = max(DA2 - e2, -qe2); y2 = max(DB2 - e2, -qe2);
-            const uint32_t dw = ((uint32_t)fO >> 31) | ((uint32_t)DA >> 31) << 1 | ((uint32_t)DB >> 31) << 2 | ((uint32_t)DA2 >> 31) << 3 |
-                                ((uint32_t)(DA + QC1) >> 31) << 4 | ((uint32_t)(DB + QC1) >> 31) << 5 | ((uint32_t)(DA2 + QC2) >> 31) << 6 | ((uint32_t)(DB2 + QC2) >> 31) << 7;
-            p[(int64_t)r * vstride + (lane - (st & ~3))] = (uint8_t)dw;
-            if (r > 0) {
-                const unsigned rel = (unsigned)(lane - st);
-                if (rel < n_upd) {
-                    H += nv;
-                    const int rank = rel < n_trk ? 2046 - (int)(rel & 3u) * 256 - (int)(rel >> 2) : 1022 - (int)(rel - n_trk);
-                    kmax = H * 2048 + rank;
-                }
-            }
-        }
-        int32_t max_H, max_t, Hen, Hst;
-        if (r > 0) {
-            Hen = Hp + __shfl_sync(FULL, en > 0 ? u : v, en);
-            {
-                const int32_t key = Hen * 2048 + 2047;
-                if (key > kmax) kmax = key;
-            }
-            const int32_t kall = __reduce_max_sync(FULL, kmax);
-            max_H = kall >> 11;
-            const int rk = 2047 - (kall & 2047);
-            if (rk == 0) max_t = en;
-            else { const int cls = (rk - 1) >> 8, idx = (rk - 1) & 255; max_t = cls < 4 ? st + 4 * idx + cls : en1 + idx; }
-            const int32_t hst = __shfl_sync(FULL, H, st);
-            Hst = st == en ? Hen : hst;
-        } else {
-            Hen = Hst = __shfl_sync(FULL, v, 0) - qe;
-            max_H = Hen, max_t = 0;
-        }
-        if (lane == en) H = Hen;
-        if (en == tlen - 1 && Hen > ez_mte) ez_mte = Hen, ez_mte_q = r - en;
-        if (r - st == qlen - 1 && Hst > ez_mqe) ez_mqe = Hst, ez_mqe_t = st;
-        bool stop = false;
-        if (max_H > ez_max) ez_max = max_H, ez_max_t = max_t, ez_max_q = r - max_t;
-        else if (max_t >= ez_max_t && r - max_t >= ez_max_q) {
-            int tl = max_t - ez_max_t, ql = (r - max_t) - ez_max_q, l = tl > ql ? tl - ql : ql - tl;
-            if (T.zdrop >= 0 && ez_max - max_H > T.zdrop + l * e2) zdropped = 1, stop = true;
-        }
-        if (stop) break;
-        if (r == nr - 1 && en == tlen - 1) ez_score = Hen;
-        pst = st, pen = en;
-    }
-    if (lane == 0) {
-        atomicAdd(cells_acc, cells);
-        res_reset(R);
-        R.max = ez_max; R.max_t = ez_max_t; R.max_q = ez_max_q; R.mqe = ez_mqe; R.mqe_t = ez_mqe_t;
-        R.mte = ez_mte; R.mte_q = ez_mte_q; R.score = ez_score; R.zdropped = zdropped;
-    }
-    __syncwarp();
-    return true;
-}
-#endif
 
 // ksw_backtrack over the sign-bit direction bytes of warp_extd2_vec; sequential, one thread
 __device__ void extd2_traceback_vec(const DpTask &T, DpRes &R, const uint8_t *p, uint32_t *ezcig, int ezcap, int32_t *err)

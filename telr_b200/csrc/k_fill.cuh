@@ -238,192 +238,6 @@ __device__ bool warp_fill_fast(const Opt &o, const DpTask &T, DpRes &R, uint8_t 
     return true;
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Batched form of the forward pass: the column blocks (8 columns each) of up to FB_MAX consecutive gap fills of one read
-// are dealt round-robin to the 32 lanes and run as ONE continuous systolic stream.  Lane l works on block 32k + l in
-// round k, NP row pairs per round (the tallest fill of the batch; shorter fills idle at the end of their rounds), one step
-// behind lane l-1, and starts its next block the step after it finishes the current one: there is no drain between
-// fills, and a 257..384-column fill simply owns 33..48 consecutive blocks instead of a second, nearly empty pass.
-// The first block of a fill takes the boundary column as its left input; a block on lane 0 takes what lane 31 wrote for
-// the same fill one round earlier (bnd[]); every other block is fed by shuffle.  Cells, direction bytes and scores are
-// those of warp_fill_fwd.
-constexpr int FB_MAX = 8;
-constexpr int FB_MAX_BLOCKS = 512;      // blocks per batch (block -> fill table): fills of up to 512 target columns batch 8 deep
-struct FillJob {
-    const uint8_t *q, *t;
-    uint8_t *dir;
-    int32_t qlen, tlen, blk0, score;       // blk0: index of the fill's first block in the stream; score: out
-};
-// boundary values of ksw_extd2's first row / first column, tabulated once per CTA (they only vary up to r = LT + 1)
-constexpr int FB_LUT = 64;
-struct FillLut { uint32_t top[FB_LUT], left[FB_LUT / 2]; int lt; };      // top[r] = pk2(0, f(r)); left[m] = pk2(f(2m), f(2m+1))
-__device__ __forceinline__ void fill_lut_init(FillLut &L, const Opt &o)
-{
-    int q = o.q, e = o.e, q2 = o.q2, e2 = o.e2;
-    if (q2 + e2 < q + e) { int t = q; q = q2; q2 = t; t = e; e = e2; e2 = t; }
-    const int qe = q + e;
-    int LT = e != e2 ? (q2 - q) / (e - e2) - 1 : 0;
-    if (q2 + e2 + LT * e2 > q + e + LT * e) ++LT;
-    const int LD = LT * (e - e2) - (q2 - q) - e2;
-#define BNDF(r) ((r) == 0 ? -qe : (r) < LT ? -e : (r) == LT ? LD : -e2)
-    for (int r = threadIdx.x; r < FB_LUT; r += blockDim.x) L.top[r] = pk2(0, BNDF(r));
-    for (int m = threadIdx.x; m < FB_LUT / 2; m += blockDim.x) L.left[m] = pk2(BNDF(2 * m), BNDF(2 * m + 1));
-#undef BNDF
-    if (threadIdx.x == 0) L.lt = LT;
-    __syncthreads();
-}
-
-__device__ void warp_fill_stream(const Opt &o, const FillLut &L, FillJob *jobs, int n_jobs, uint32_t *bnd, const uint8_t *b2j)
-{
-    constexpr int FC = 8;
-    const int lane = threadIdx.x & 31;
-    const unsigned FULL = 0xffffffffu;
-    int q = o.q, e = o.e, q2 = o.q2, e2 = o.e2;
-    if (q2 + e2 < q + e) { int t = q; q = q2; q2 = t; t = e; e = e2; e2 = t; }
-    const int qe = q + e, qe2 = q2 + e2;
-    const int LT = L.lt;
-    const uint32_t NE1 = pk1(-e), NQE1 = pk1(-qe), NE2 = pk1(-e2), NQE2 = pk1(-qe2);
-    const uint32_t QM1 = pk1(q - 1), Q2M1 = pk1(q2 - 1);
-    const uint32_t UY0 = pk2(0, -qe), UY20 = pk2(0, -qe2), UU0 = pk2(0, -e2);
-    const uint32_t TS_MIS = 0x01010101u * ((uint32_t)(-o.b) & 0xffu), TS_FLIP = ((uint32_t)o.a ^ (uint32_t)(-o.b)) & 0xffu;
-    // stream geometry
-    int total_blocks = 0, NP = 32;
-    for (int f = 0; f < n_jobs; ++f) {
-        const int np = (jobs[f].qlen + 1) >> 1;
-        total_blocks += (jobs[f].tlen + FC - 1) / FC;
-        NP = np > NP ? np : NP;
-    }
-    const int rounds = (total_blocks + 31) >> 5;
-    if (lane < n_jobs) jobs[lane].score = 0;
-    __syncwarp();
-    // per-lane block state
-    const uint8_t *Q = nullptr; uint8_t *dcol = nullptr;
-    int jf = 0, qlen = 0, tlen = 0, npairs = 0, stride = 0, t0 = 0;
-    bool live = false, first = false, feeds = false;
-    uint32_t TS[FC], Uu[FC], Uy[FC], Uy2[FC];
-#pragma unroll
-    for (int k = 0; k < FC; ++k) TS[k] = Uu[k] = Uy[k] = Uy2[k] = 0;
-    uint32_t inV = 0, inX = 0, inX2 = 0, Ufirst = 0, outV = 0, outX = 0, outX2 = 0;
-    int m = -lane, round = -1;                  // row pair within the round; the lane's first round starts when m reaches 0
-    const int n_steps = rounds * NP + 32;       // lane 31 closes its last block one step after its last row pair
-    for (int s = 0; s < n_steps; ++s, ++m) {
-        if (m == NP) m = 0;
-        if (m == 0) {
-            // ---- finish the block that just ended: u of the fill's last query row (score = boundary + sum of u) ----
-            if (live) {
-                int usum = 0;
-                const int nv = tlen - t0;       // valid columns of the block (>= 1)
-                if (qlen & 1) {
-#pragma unroll
-                    for (int k = 0; k < FC; ++k) usum += k < nv ? (k == 0 ? lo16(Ufirst) : lo16(Uu[k - 1])) : 0;
-                } else {
-#pragma unroll
-                    for (int k = 0; k < FC; ++k) usum += k < nv ? hi16(Uu[k]) : 0;
-                }
-                atomicAdd(&jobs[jf].score, usum);
-            }
-            // ---- next block of this lane ----
-            ++round;
-            const int g = (round << 5) + lane;
-            live = round < rounds && g < total_blocks;
-            if (live) {
-                jf = b2j[g];
-                const FillJob J = jobs[jf];
-                const int b = g - J.blk0;
-                Q = J.q; qlen = J.qlen; tlen = J.tlen; npairs = (qlen + 1) >> 1; stride = fill_stride(tlen);
-                t0 = b * FC; first = b == 0; dcol = J.dir + t0;
-                feeds = t0 + FC < tlen;           // a right neighbour of the same fill exists
-                const uint8_t *tp = J.t + t0;
-                const int nv = tlen - t0;
-#pragma unroll
-                for (int k = 0; k < FC; ++k) {
-                    const int tc = k < nv ? tp[k] : 0;
-                    TS[k] = TS_MIS ^ (TS_FLIP << (8 * tc));
-                    Uy[k] = UY0; Uy2[k] = UY20;
-                    Uu[k] = UU0;
-                }
-                if (t0 <= LT) {                   // the top boundary varies only over the first LT + 1 columns
-#pragma unroll
-                    for (int k = 0; k < FC; ++k) Uu[k] = L.top[t0 + k];
-                }
-            }
-        }
-        // ---- left input of this step: boundary column, lane 31's column of the previous round, or the shuffle ----
-        {
-            const uint32_t sV = __shfl_sync(FULL, outV, (lane + 31) & 31), sX = __shfl_sync(FULL, outX, (lane + 31) & 31), sX2 = __shfl_sync(FULL, outX2, (lane + 31) & 31);
-            inV = sV; inX = sX; inX2 = sX2;
-        }
-        const bool active = live && m >= 0 && m < npairs;
-        if (active) {
-            if (first) { inV = 2 * m > LT ? NE2 : L.left[m]; inX = NQE1; inX2 = NQE2; }
-            else if (lane == 0) { inV = bnd[3 * m]; inX = bnd[3 * m + 1]; inX2 = bnd[3 * m + 2]; }
-            const int j = 2 * m;
-            const uint32_t q0 = Q[j], q1 = j + 1 < qlen ? Q[j + 1] : 0;
-            const uint32_t inQ = q0 | (q0 | 8u) << 4 | (q1 + 4u) << 8 | (q1 + 12u) << 12;
-            uint32_t Lv = inV, Lx = inX, Lx2 = inX2, pu = 0, py = 0, py2 = 0, kV = 0, kX = 0, kX2 = 0;
-            uint32_t W[FC / 2 + 1];
-            uint32_t eDS = 0, eDA = 0, eDB = 0, eDA2 = 0, eCX = 0, eCY = 0, eCX2 = 0, eCY2 = 0;
-#pragma unroll
-            for (int k = 0; k <= FC; ++k) {
-                const int kk = k < FC ? k : FC - 1, kh = k > 0 ? k - 1 : 0;
-                const uint32_t up_u = __byte_perm(Uu[kk], pu, 0x5432), up_y = __byte_perm(Uy[kk], py, 0x5432), up_y2 = __byte_perm(Uy2[kk], py2, 0x5432);
-                if (k == 1) {
-                    Lv = __byte_perm(Lv, inV, 0x7610); Lx = __byte_perm(Lx, inX, 0x7610); Lx2 = __byte_perm(Lx2, inX2, 0x7610);
-                }
-                const uint32_t S = prmt(TS[kk], TS[kh], inQ);
-                const uint32_t A = __vadd2(Lx, Lv), A2 = __vadd2(Lx2, Lv), B = __vadd2(up_y, up_u), B2 = __vadd2(up_y2, up_u);
-                uint32_t Z = __vimax3_s16x2(S, A, B);
-                Z = __vimax3_s16x2(Z, A2, B2);
-                const uint32_t DS = __vsub2(S, Z), DA = __vsub2(A, Z), DB = __vsub2(B, Z), DA2 = __vsub2(A2, Z), DB2 = __vsub2(B2, Z);
-                const uint32_t nu = __vsub2(Z, Lv), nv = __vsub2(Z, up_u);
-                const uint32_t nx = __viaddmax_s16x2(DA, NE1, NQE1), ny = __viaddmax_s16x2(DB, NE1, NQE1);
-                const uint32_t nx2 = __viaddmax_s16x2(DA2, NE2, NQE2), ny2 = __viaddmax_s16x2(DB2, NE2, NQE2);
-                const uint32_t cx = __vadd2(DA, QM1), cy = __vadd2(DB, QM1), cx2 = __vadd2(DA2, Q2M1), cy2 = __vadd2(DB2, Q2M1);
-                if (k == FC) {
-                    uint32_t acc = prmt(DS, DA, 0xFDB9) & 0x02020101u;
-                    acc |= prmt(DB, DA2, 0xFDB9) & 0x08080404u;
-                    acc |= prmt(cx, cy, 0xFDB9) & 0x20201010u;
-                    acc |= prmt(cx2, cy2, 0xFDB9) & 0x80804040u;
-                    W[FC / 2] = acc | (acc >> 16);
-                } else if (!(k & 1)) {
-                    eDS = DS; eDA = DA; eDB = DB; eDA2 = DA2; eCX = cx; eCY = cy; eCX2 = cx2; eCY2 = cy2;
-                } else {
-                    uint32_t acc = prmt(eDS, DS, 0xFDB9) & 0x01010101u;
-                    acc |= prmt(eDA, DA, 0xFDB9) & 0x02020202u;
-                    acc |= prmt(eDB, DB, 0xFDB9) & 0x04040404u;
-                    acc |= prmt(eDA2, DA2, 0xFDB9) & 0x08080808u;
-                    acc |= prmt(eCX, cx, 0xFDB9) & 0x10101010u;
-                    acc |= prmt(eCY, cy, 0xFDB9) & 0x20202020u;
-                    acc |= prmt(eCX2, cx2, 0xFDB9) & 0x40404040u;
-                    acc |= prmt(eCY2, cy2, 0xFDB9) & 0x80808080u;
-                    W[k >> 1] = acc;
-                }
-                if (k >= 1) { Uu[k - 1] = nu; Uy[k - 1] = ny; Uy2[k - 1] = ny2; }
-                if (k == 0) Ufirst = nu;
-                if (k == FC - 1) { kV = nv; kX = nx; kX2 = nx2; }
-                pu = nu; py = ny; py2 = ny2; Lv = nv; Lx = nx; Lx2 = nx2;
-            }
-            outV = __byte_perm(kV, Lv, 0x7610); outX = __byte_perm(kX, Lx, 0x7610); outX2 = __byte_perm(kX2, Lx2, 0x7610);
-            {
-                uint8_t *r0 = dcol + (int64_t)j * stride, *r1 = r0 + stride;
-                const uint32_t w00 = __byte_perm(W[0], W[1], 0x6420), w01 = __byte_perm(W[2], W[3], 0x6420);
-                const uint32_t w10 = __byte_perm(__byte_perm(W[0], W[1], 0x0753), W[2], 0x5210), w11 = __byte_perm(__byte_perm(W[2], W[3], 0x0753), W[4], 0x5210);
-                *reinterpret_cast<uint2 *>(r0) = make_uint2(w00, w01);
-                if (j + 1 < qlen) *reinterpret_cast<uint2 *>(r1) = make_uint2(w10, w11);
-            }
-            if (lane == 31 && feeds) { bnd[3 * m] = outV; bnd[3 * m + 1] = outX; bnd[3 * m + 2] = outX2; }
-        }
-        __syncwarp();       // bnd[] written by lane 31 is read by lane 0 one round later
-    }
-    __syncwarp();
-    if (lane < n_jobs) {
-        const int ql = jobs[lane].qlen;
-        const int LD = LT * (e - e2) - (q2 - q) - e2;
-        jobs[lane].score += bnd_sum(ql, qe, e, e2, LT, LD);
-    }
-    __syncwarp();
-}
-
 // ksw_backtrack over the fast path's row-major direction bytes (global alignment, no band).
 // Warp-cooperative and run-at-a-time: the lanes stage a window of 56 rows x 64 columns that ends at the current cell
 // into shared memory (coalesced 8-byte loads, two rows per lane); then every step resolves a whole CIGAR run: lane k

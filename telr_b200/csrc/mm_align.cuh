@@ -205,36 +205,6 @@ TELR_HD void anchor_cut(const AlnCtx &c, const Anchor &an, int *r, int *q)
     }
 }
 
-// Look-ahead for the batched fill kernel: the gap fills that follow the one just emitted (phase PH_FILL1_DONE + 100) if every
-// fill in between is consumed without a z-drop — PH_FILL_NEXT replayed on copies of (i, rs, qs); nothing in c changes.
-// Stops at anything that is not a plain approximate-max global fill.
-struct PeekFill { const uint8_t *q, *t; int32_t qlen, tlen; };
-TELR_HD int aln_peek_fills(const AlnCtx &c, PeekFill *out, int max_n)
-{
-    const Opt &o = *c.o;
-    const Anchor *a = c.a;
-    int n = 0, i = c.i + 1, rs = c.re, qs = c.qe;
-    while (n < max_n && i < c.cnt1) {
-        const Anchor &an = a[c.as1 + i];
-        if ((an.y & (SEED_IGNORE | SEED_TANDEM)) && i != c.cnt1 - 1) { ++i; continue; }
-        int re, qe;
-        anchor_cut(c, an, &re, &qe);
-        if (i == c.cnt1 - 1 || (an.y & SEED_LONG_JOIN) || (qe - qs >= o.min_ksw_len && re - rs >= o.min_ksw_len)) {
-            const int ql = qe - qs, tl = re - rs;
-            int bw1 = c.bw_long;
-            if (an.y & SEED_LONG_JOIN) bw1 = ql > tl ? ql : tl;
-            if (o.max_sw_mat > 0 && (long long)tl * ql > o.max_sw_mat) break;
-            if (ql <= 0 || tl <= 0) break;
-            if (bw1 < (ql > tl ? ql : tl)) break;
-            out[n].q = &c.qseq[c.rev][qs]; out[n].t = &c.tseq[rs]; out[n].qlen = ql; out[n].tlen = tl;
-            ++n;
-            rs = re, qs = qe;
-        }
-        ++i;
-    }
-    return n;
-}
-
 // rescan a gap-fill CIGAR with single-affine costs: largest score drop along the path and where
 TELR_HDN void scan_zdrop(AlnCtx &c, const uint8_t *qseq, const uint8_t *tseq, int n_cigar, const uint32_t *cigar)
 {

@@ -65,7 +65,6 @@ struct telr_af_ctx {
     DevBuf b_order, b_wflag, b_woff;      // LPT order of the chunk's problems, work-list filter
     DevBuf b_tfirst, b_tcnt, b_toff, b_tmpx, b_tmpy;     // tile sketch: first tile per sequence, per-tile counts/offsets, per-tile slots
     int sketch_tiles = 1;
-    int fill_batch = 0;                  // -DTELR_FILL_STREAM=1 builds: gap fills of a read computed ahead as one systolic stream (TELR_FILL_BATCH)
     // TELR_AL_QUEUE=1 selects the role-specialised alignment kernel k_al_queue (ext_per8 / wide_per8: eighths of the SMs that start in the
     // extension role / the 12-column gap-fill role).  Measured (profiles/README.md, round 2): it removes the instruction-cache penalty of extra
     // loop bodies as designed, but end to end it is within +-1.5 % of k_al_fused on map-ont and 18 % slower on map-pb / map-hifi, so the
@@ -499,7 +498,7 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
     const int al_grid = std::max(1, std::min((n_work + AL_WARPS - 1) / AL_WARPS, sm * ctx->al_blocks));
     {
         size_t maxT = ((size_t)max_tlen + 64) & ~(size_t)15;
-        aa.max_tlen = max_tlen; aa.max_qlen = max_qlen; aa.dir_cap = ctx->dir_cap; aa.use_fast = ctx->use_fast; aa.use_vec = ctx->use_vec; aa.census = ctx->census; aa.fill_batch = ctx->fill_batch;
+        aa.max_tlen = max_tlen; aa.max_qlen = max_qlen; aa.dir_cap = ctx->dir_cap; aa.use_fast = ctx->use_fast; aa.use_vec = ctx->use_vec; aa.census = ctx->census;
         aa.warp_scratch_stride = (maxT * (6 + 4 + 24) + (((size_t)max_qlen + 64) & ~(size_t)15) * 6 + 512 + (size_t)ctx->dir_cap + 255) & ~(size_t)255;
         ENS(ctx->b_alws, aa.warp_scratch_stride * (size_t)al_grid * AL_WARPS);
         aa.warp_scratch = ctx->b_alws.as<uint8_t>();
@@ -565,7 +564,6 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
                 rc[4] / 1e6, rc[5] / 1e6, rc[8] / 1e6, rc[6] / 1e6, rc[9] / 1e6, rc[7] / 1e6, rc[10] / 1e6, rc[11] / 1e6);
         fprintf(stderr, "[census] tasks: fill %llu vec %llu scalar %llu ll %llu | q*t (M): fill %.1f vec %.1f scalar %.1f\n",
                 rc[12], rc[13], rc[14], rc[15], rc[16] / 1e6, rc[17] / 1e6, rc[18] / 1e6);
-        fprintf(stderr, "[census] fill batches %llu, fills computed %llu, served %llu, stream cycles(M) %.1f, q*t computed (M) %.1f\n", rc[91], rc[90], rc[92], rc[93] / 1e6, rc[94] / 1e6);
         static const char *fb[6] = {"<=256", "<=288", "<=320", "<=384", "<=512", ">512"};
         for (int b = 0; b < 6; ++b)
             fprintf(stderr, "[census] fill tlen %s: tasks %llu cycles(M) %.1f q*t(M) %.1f\n", fb[b], rc[64 + b], rc[70 + b] / 1e6, rc[76 + b] / 1e6);
@@ -756,8 +754,6 @@ int telr_af_create(telr_af_ctx **out, int device, size_t workspace_bytes)
     if (uf) ctx->use_fast = atoi(uf) ? 1 : 0;
     const char *uv = getenv("TELR_VEC_EXT");
     if (uv) ctx->use_vec = atoi(uv) ? 1 : 0;
-    const char *fbt = getenv("TELR_FILL_BATCH");
-    if (fbt && atoi(fbt) >= 0 && atoi(fbt) <= FB_MAX) ctx->fill_batch = atoi(fbt);
     const char *alb = getenv("TELR_AL_CTAS");
     if (alb && atoi(alb) >= 1 && atoi(alb) <= AL_BLOCKS_PER_SM) ctx->al_blocks = atoi(alb);
     const char *skt = getenv("TELR_SKETCH_TILES");

@@ -29,12 +29,6 @@ static void opt_from_orc(Opt &o, const orc_opt_t &p)
     o.rank_frac = p.rank_frac; o.max_clip_ratio = p.max_clip_ratio;
 }
 
-static long long g_peek_checked = 0, g_peek_mismatch = 0, g_peek_missed = 0;
-extern "C" void emu_peek_stats(long long *checked, long long *mismatch, long long *missed)
-{
-    *checked = g_peek_checked; *mismatch = g_peek_mismatch; *missed = g_peek_missed;
-}
-
 // run the product logic for one read x contig strand starting from SORTED anchors.
 // out regs: 13 ints each (rs,re,qs,qe,rev,flag,dp_max,mlen,blen,n_cigar,cig_off,score,cnt); returns n regs or <0
 extern "C" int emu_map_from_anchors(int preset, const uint8_t *contig, int clen, const uint8_t *read, int qlen,
@@ -98,19 +92,7 @@ extern "C" int emu_map_from_anchors(int preset, const uint8_t *contig, int clen,
     DpTask t;
     orc_ez_t ez; memset(&ez, 0, sizeof(ez));
     std::vector<uint8_t> qb, tb;
-    PeekFill pk[8]; int n_pk = 0; bool prev_fill = false, prev_zdropped = false;
     while (aln_next(c, res, t)) {
-        // look-ahead of the batched fill kernel (aln_peek_fills): after every approximate-max gap fill the coroutine emits,
-        // the fills predicted from the anchors alone must be the ones it emits next, unless a z-drop path intervenes
-        const bool is_fill = t.kind == 0 && t.flag == KSW_APPROX_MAX && t.qstep == 1 && t.tstep == 1 && !t.qcomp;
-        if (is_fill && prev_fill && !prev_zdropped) {
-            if (n_pk >= 1) {
-                ++g_peek_checked;
-                if (pk[0].q != t.q || pk[0].t != t.t || pk[0].qlen != t.qlen || pk[0].tlen != t.tlen) ++g_peek_mismatch;
-            } else ++g_peek_missed;
-        }
-        n_pk = is_fill ? aln_peek_fills(c, pk, 8) : 0;
-        prev_fill = is_fill;
         qb.resize(t.qlen); tb.resize(t.tlen);
         for (int i = 0; i < t.qlen; ++i) { uint8_t b = t.q[(ptrdiff_t)i * t.qstep]; qb[i] = t.qcomp ? (b >= 4 ? 4 : 3 - b) : b; }
         for (int i = 0; i < t.tlen; ++i) tb[i] = t.t[(ptrdiff_t)i * t.tstep];
@@ -120,7 +102,6 @@ extern "C" int emu_map_from_anchors(int preset, const uint8_t *contig, int clen,
             res.max = ez.max; res.max_q = ez.max_q; res.max_t = ez.max_t; res.mqe = ez.mqe; res.mqe_t = ez.mqe_t;
             res.mte = ez.mte; res.mte_q = ez.mte_q; res.score = ez.score; res.zdropped = ez.zdropped; res.reach_end = ez.reach_end;
             res.n_cigar = ez.n_cigar; res.cigar = ez.cigar;
-            prev_zdropped = ez.zdropped != 0;
         } else {
             int qe, te;
             res.ll_score = orc_ksw_ll(t.qlen, qb.data(), t.tlen, tb.data(), o.a, o.b, o.sc_ambi, o.q, o.e, &qe, &te);

@@ -161,11 +161,6 @@ def test_product_logic_emulated_on_host_matches_oracle(built, cfg, preset):
                     assert (cig[e[10]:e[10] + e[9]] == ref["cigar"][a["cigar_off"]:a["cigar_off"] + a["n_cigar"]]).all()
                 n_prob += 1
     assert n_prob > 20
-    # the look-ahead the batched fill kernel relies on (aln_peek_fills, checked inside the harness after every gap fill):
-    # what it predicts from the anchors is what the coroutine emits next
-    chk, bad, missed = C.c_longlong(0), C.c_longlong(0), C.c_longlong(0)
-    E.emu_peek_stats(C.byref(chk), C.byref(bad), C.byref(missed))
-    assert chk.value > 50 and bad.value == 0 and missed.value == 0, (chk.value, bad.value, missed.value)
 
 
 def test_oracle_alignment_invariants(built):
