@@ -306,6 +306,18 @@ __device__ void chain_rmq_warp(const Opt &o, int n, const Anchor *a, ChainScratc
     RmqWin w;
     rmq_win_init(w, o);
     int nw = 0;
+    // Outer range query.  Upstream asks a balanced tree for the best priority among the anchors in the window whose y lies in
+    // (yi - max_dist, yi); the first version here scanned the whole window for every anchor (O(n^2 / 32) per problem, 31 % of a
+    // map-hifi step).  Now the anchors are blocked by index, 32 per block, and every block keeps a summary of its ACTIVE anchors
+    // (inserted, not yet erased): the best anchor by the query's own total order (priority, then larger y, then larger index) and
+    // bounds on y.  A query takes the summary of a block whose y range lies inside the query range, skips a block whose range lies
+    // outside, and looks at the 32 anchors of the few blocks that straddle; the answer is the maximum of the same set under the
+    // same order, hence identical.  Bounds are only ever loosened by erasures (a loose bound costs a look, never a result).
+    const int nblk = (n + 31) >> 5;
+    int32_t *bsum = reinterpret_cast<int32_t *>(s.z);          // [nblk][4]: best anchor (-1 none), min y, max y of the active anchors
+    for (int b = lane; b < nblk; b += 32) { bsum[4 * b] = -1; bsum[4 * b + 1] = INT32_MAX; bsum[4 * b + 2] = INT32_MIN; }
+    __syncwarp();
+    int act_lo = 0, act_hi = 0;                                 // active anchors: [act_lo, act_hi)
     for (int i = 0; i < n; ++i) {
         // ---- window maintenance (same order of operations as the two trees upstream: insert, then erase) ----
         {
@@ -315,16 +327,70 @@ __device__ void chain_rmq_warp(const Opt &o, int n, const Anchor *a, ChainScratc
                 for (int j = old_i0; j < w.i0; ++j) w_insert(W, nw, a, j);
                 for (int j = old_sti; j < w.st_inner; ++j) w_erase(W, nw, a, j);
             }
+            const int new_lo = w.st < w.i0 ? w.st : w.i0, new_hi = w.i0;
+            if (lane == 0)
+                for (int j = act_hi; j < new_hi; ++j) {        // insertions: fold the anchor into its block's summary
+                    int32_t *bs = bsum + 4 * (j >> 5);
+                    const int32_t yj = (int32_t)a[j].y;
+                    const int cur = bs[0];
+                    if (cur < 0 || rmq_better(rmq_pri(a[j], f[j], o.chn_pen_gap), yj, j, rmq_pri(a[cur], f[cur], o.chn_pen_gap), (int32_t)a[cur].y, cur)) bs[0] = j;
+                    if (yj < bs[1]) bs[1] = yj;
+                    if (yj > bs[2]) bs[2] = yj;
+                }
+            __syncwarp();
+            if (new_lo > act_lo) {                              // erasures: rebuild the summaries of the blocks that lost anchors
+                for (int b = act_lo >> 5; b <= (new_lo - 1) >> 5 && b < nblk; ++b) {
+                    const int j = (b << 5) + lane;
+                    const bool act = j >= new_lo && j < new_hi;
+                    int bj = act ? j : -1; double bp = 0.0; int32_t by = act ? (int32_t)a[j].y : 0;
+                    if (act) bp = rmq_pri(a[j], f[j], o.chn_pen_gap);
+                    int32_t mn = act ? by : INT32_MAX, mx = act ? by : INT32_MIN;
+#pragma unroll
+                    for (int d = 16; d; d >>= 1) {
+                        int ob = __shfl_xor_sync(FULL, bj, d); double op = __shfl_xor_sync(FULL, bp, d); int32_t oy = __shfl_xor_sync(FULL, by, d);
+                        if (ob >= 0 && (bj < 0 || rmq_better(op, oy, ob, bp, by, bj))) bj = ob, bp = op, by = oy;
+                    }
+                    mn = __reduce_min_sync(FULL, mn); mx = __reduce_max_sync(FULL, mx);
+                    if (lane == 0) { bsum[4 * b] = bj; bsum[4 * b + 1] = mn; bsum[4 * b + 2] = mx; }
+                }
+                __syncwarp();
+            }
+            act_lo = new_lo; act_hi = new_hi;
         }
         const Anchor ai = a[i];
         const int32_t yi = (int32_t)ai.y;
-        // ---- outer RMQ ----
+        // ---- outer RMQ over the block summaries ----
         int best = -1; double bp = 0.0; int32_t by = 0;
-        for (int j = (w.st < w.i0 ? w.st : w.i0) + lane; j < w.i0; j += 32) {
-            const Anchor aj = a[j];
-            if (!rmq_in_range(aj, j, yi, w.max_dist)) continue;
-            double pri = rmq_pri(aj, f[j], o.chn_pen_gap);
-            if (best < 0 || rmq_better(pri, (int32_t)aj.y, j, bp, by, best)) best = j, bp = pri, by = (int32_t)aj.y;
+        if (act_hi > act_lo) {
+            const int32_t ylo = yi - w.max_dist;
+            const int b0 = act_lo >> 5, b1 = (act_hi - 1) >> 5;
+            for (int bb = b0; bb <= b1; bb += 32) {
+                const int b = bb + lane;
+                bool look = false;
+                if (b <= b1) {
+                    const int cj = bsum[4 * b]; const int32_t mn = bsum[4 * b + 1], mx = bsum[4 * b + 2];
+                    if (cj >= 0 && !(mn > yi || mx <= ylo)) {
+                        if (mx < yi && mn > ylo) {              // the whole block qualifies: its summary answers for it
+                            const double pri = rmq_pri(a[cj], f[cj], o.chn_pen_gap);
+                            const int32_t cy = (int32_t)a[cj].y;
+                            if (best < 0 || rmq_better(pri, cy, cj, bp, by, best)) best = cj, bp = pri, by = cy;
+                        } else look = true;
+                    }
+                }
+                unsigned lm = __ballot_sync(FULL, look);
+                while (lm) {                                    // blocks that straddle the query range: their 32 anchors
+                    const int lb = bb + __ffs(lm) - 1;
+                    lm &= lm - 1;
+                    const int j = (lb << 5) + lane;
+                    if (j >= act_lo && j < act_hi) {
+                        const Anchor aj = a[j];
+                        if (rmq_in_range(aj, j, yi, w.max_dist)) {
+                            const double pri = rmq_pri(aj, f[j], o.chn_pen_gap);
+                            if (best < 0 || rmq_better(pri, (int32_t)aj.y, j, bp, by, best)) best = j, bp = pri, by = (int32_t)aj.y;
+                        }
+                    }
+                }
+            }
         }
 #pragma unroll
         for (int d = 16; d; d >>= 1) {
