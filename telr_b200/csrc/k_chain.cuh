@@ -617,16 +617,179 @@ template <int STRIDE> __device__ __forceinline__ int tp_problem(int n_prob)
     return p < n_prob ? p : -1;
 }
 
+// Warp-cooperative form of rs_sort_emul for anchors keyed by x (same permutation, element for element): up to 64 elements a stable
+// rank sort (what the insertion sort of klib leaves); above that the MSD radix passes with the level skip, the histogram and
+// the bucket offsets computed by the 32 lanes, the unstable cycle-leader pass on lane 0 exactly as upstream walks it (its
+// deposit order is what fixes the order of equal keys), and the insertion sorts of the small buckets one bucket per lane.
+struct SortSmem { int32_t bb[256], be[256]; };
+__device__ void rs_sort_warp(Anchor *a, int n, int32_t *scratch, SortSmem &H)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    if (n <= 64) {
+        if (n < 2) return;
+        uint4 *tmp = reinterpret_cast<uint4 *>(&H);
+        for (int e = lane; e < n; e += 32) tmp[e] = *reinterpret_cast<const uint4 *>(&a[e]);
+        __syncwarp();
+        for (int e = lane; e < n; e += 32) {
+            const uint4 me = tmp[e];
+            const uint64_t ke = (uint64_t)me.y << 32 | me.x;
+            int rank = 0;
+            for (int j = 0; j < n; ++j) {
+                const uint64_t kj = (uint64_t)tmp[j].y << 32 | tmp[j].x;
+                rank += kj < ke || (kj == ke && j < e);
+            }
+            *reinterpret_cast<uint4 *>(&a[rank]) = me;
+        }
+        __syncwarp();
+        return;
+    }
+    int32_t *stk = scratch + 512;
+    if (lane == 0) { stk[0] = 0; stk[1] = n; stk[2] = 56; }
+    __syncwarp();
+    int sp = 1;
+    while (sp > 0) {
+        --sp;
+        const int beg = stk[3 * sp], end = stk[3 * sp + 1];
+        int s = stk[3 * sp + 2];
+        __syncwarp();
+        for (;;) {                      // levels on which every key has the same digit are no-ops upstream
+            const uint64_t k0 = a[beg].x >> s & 255;
+            bool diff = false;
+            for (int i = beg + 1 + lane; i < end; i += 32) diff |= (a[i].x >> s & 255) != k0;
+            if (__any_sync(FULL, diff) || s == 0) break;
+            s -= 8;
+        }
+        for (int k = lane; k < 256; k += 32) H.be[k] = 0;
+        __syncwarp();
+        for (int i = beg + lane; i < end; i += 32) atomicAdd(&H.be[(int)(a[i].x >> s & 255)], 1);
+        __syncwarp();
+        {
+            int c[8], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { c[j] = H.be[8 * lane + j]; sum += c[j]; }
+            int pre = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(FULL, pre, d); if (lane >= d) pre += y; }
+            int acc = beg + pre - sum;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { H.bb[8 * lane + j] = acc; acc += c[j]; H.be[8 * lane + j] = acc; }
+        }
+        __syncwarp();
+        if (lane == 0) {                // the cycle-leader permutation, in upstream's order
+            for (int k = 0; k < 256;) {
+                if (H.bb[k] != H.be[k]) {
+                    int l = (int)(a[H.bb[k]].x >> s & 255);
+                    if (l != k) {
+                        Anchor tmp = a[H.bb[k]], swp;
+                        do {
+                            swp = tmp; tmp = a[H.bb[l]]; a[H.bb[l]++] = swp;
+                            l = (int)(tmp.x >> s & 255);
+                        } while (l != k);
+                        a[H.bb[k]++] = tmp;
+                    } else ++H.bb[k];
+                } else ++k;
+            }
+        }
+        __syncwarp();
+        if (s) {
+            for (int k = lane; k < 256; k += 32) {          // small buckets: one per lane at a time
+                const int b0 = k ? H.be[k - 1] : beg, sz = H.be[k] - b0;
+                if (sz > 1 && sz <= 64) ins_sort(a + b0, sz, KeyX());
+            }
+            if (lane == 0)
+                for (int k = 0; k < 256; ++k) {
+                    const int b0 = k ? H.be[k - 1] : beg, sz = H.be[k] - b0;
+                    if (sz > 64) { stk[3 * sp] = b0; stk[3 * sp + 1] = H.be[k]; stk[3 * sp + 2] = s - 8; ++sp; }
+                }
+            sp = __shfl_sync(FULL, sp, 0);
+        }
+        __syncwarp();
+    }
+}
+
+// Warp forms of chain_backtrack / chain_compact (mm_chain.cuh): the filter, the sort, the clearing and the copies are spread
+// over the lanes; the walk that extracts the chains stays sequential on lane 0 (every step depends on the marks of the last).
+__device__ void chain_backtrack_warp(int n, ChainScratch &s, int min_cnt, int min_sc, int max_drop, int *n_u_, int *n_v_, SortSmem &H)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    const int32_t *f = s.f, *p = s.p;
+    int32_t *v = s.v, *t = s.t;
+    Anchor *z = s.z;
+    int n_z = 0;
+    *n_u_ = *n_v_ = 0;
+    for (int ib = 0; ib < n; ib += 32) {
+        const int i = ib + lane;
+        const bool keep = i < n && f[i] >= min_sc;
+        const unsigned m = __ballot_sync(FULL, keep);
+        if (keep) { Anchor e; e.x = (uint64_t)f[i]; e.y = (uint64_t)i; z[n_z + __popc(m & ((1u << lane) - 1))] = e; }
+        n_z += __popc(m);
+    }
+    __syncwarp();
+    if (n_z == 0) return;
+    rs_sort_warp(z, n_z, s.sortws, H);
+    for (int i = lane; i < n; i += 32) t[i] = 0;
+    __syncwarp();
+    int n_u = 0, n_v = 0;
+    if (lane == 0) {
+        for (int k = n_z - 1; k >= 0; --k) {
+            if (t[z[k].y] == 0) {
+                int n_v0 = n_v;
+                int32_t end_i = bk_end(max_drop, z, f, p, t, k), i;
+                for (i = (int32_t)z[k].y; i != end_i; i = p[i]) v[n_v++] = i, t[i] = 1;
+                int32_t sc = i < 0 ? (int32_t)z[k].x : (int32_t)z[k].x - f[i];
+                if (sc >= min_sc && n_v > n_v0 && n_v - n_v0 >= min_cnt) s.u[n_u++] = (uint64_t)sc << 32 | (uint32_t)(n_v - n_v0);
+                else n_v = n_v0;
+            }
+        }
+    }
+    __syncwarp();
+    *n_u_ = __shfl_sync(FULL, n_u, 0); *n_v_ = __shfl_sync(FULL, n_v, 0);
+}
+
+__device__ void chain_compact_warp(int n_u, ChainScratch &s, Anchor *a, SortSmem &H)
+{
+    const int lane = threadIdx.x & 31;
+    Anchor *b = s.b, *w = s.z;
+    uint64_t *u = s.u, *u2 = s.u2;
+    int k = 0;
+    for (int i = 0; i < n_u; ++i) {             // chains listed end -> start become start -> end
+        const int ni = (int32_t)u[i];
+        for (int j = lane; j < ni; j += 32) b[k + j] = a[s.v[k + (ni - j - 1)]];
+        k += ni;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        int kk = 0;
+        for (int i = 0; i < n_u; ++i) { w[i].x = b[kk].x; w[i].y = (uint64_t)kk << 32 | (uint32_t)i; kk += (int32_t)u[i]; }
+    }
+    __syncwarp();
+    rs_sort_warp(w, n_u, s.sortws, H);
+    k = 0;
+    for (int i = 0; i < n_u; ++i) {             // chains by target position
+        const int j = (int32_t)w[i].y, ni = (int32_t)u[j];
+        const Anchor *src = &b[w[i].y >> 32];
+        for (int c = lane; c < ni; c += 32) a[k + c] = src[c];
+        if (lane == 0) u2[i] = u[j];
+        k += ni;
+    }
+    __syncwarp();
+    for (int i = lane; i < n_u; i += 32) u[i] = u2[i];
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(128) k_chain_sort(const __grid_constant__ ChainArgs A)
 {
-    const int p = tp_problem<TP_CHAIN>(A.n_prob);
-    if (p < 0) return;
+    __shared__ SortSmem HS[4];
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (p >= A.n_prob) return;
     const int n_a = (int)(A.prob_aoff[p + 1] - A.prob_aoff[p]);
-    A.prob_nu[p] = 0; A.prob_m[p] = 0; A.prob_nregs[p] = 0; A.prob_nca[p] = 0;
+    if (lane == 0) { A.prob_nu[p] = 0; A.prob_m[p] = 0; A.prob_nregs[p] = 0; A.prob_nca[p] = 0; }
     if (n_a == 0) return;
     ChainScratch cs; HitScratch hs; int cap;
     prob_carve(A, p, n_a, cs, hs, &cap);
-    rs_sort_emul(A.anchors + A.prob_aoff[p], n_a, KeyX(), cs.sortws);
+    rs_sort_warp(A.anchors + A.prob_aoff[p], n_a, cs.sortws, HS[threadIdx.x >> 5]);
 }
 
 // chaining DP, one WARP per problem
@@ -648,28 +811,30 @@ __global__ void __launch_bounds__(256) k_chain_dp(const __grid_constant__ ChainA
 
 __global__ void __launch_bounds__(128) k_chain_bt(const __grid_constant__ ChainArgs A)
 {
-    const int p = tp_problem<TP_CHAIN>(A.n_prob);
-    if (p < 0) return;
+    __shared__ SortSmem HS[4];
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (p >= A.n_prob) return;
     const int n_a = (int)(A.prob_aoff[p + 1] - A.prob_aoff[p]);
     if (n_a == 0) return;
     const Opt &o = A.o;
+    SortSmem &H = HS[threadIdx.x >> 5];
     ChainScratch cs; HitScratch hs; int cap;
     prob_carve(A, p, n_a, cs, hs, &cap);
     Anchor *a = A.anchors + A.prob_aoff[p];
     const int qlen = A.read_len[A.prob_read[p]];
     int n_u = 0, n_v = 0, m = 0;
-    chain_backtrack(n_a, cs, o.min_cnt, o.min_chain_score, o.bw, &n_u, &n_v);
+    chain_backtrack_warp(n_a, cs, o.min_cnt, o.min_chain_score, o.bw, &n_u, &n_v, H);
     if (n_u > 0) {
-        chain_compact(n_u, n_v, cs, a);
+        chain_compact_warp(n_u, cs, a, H);
         if (o.bw_long > o.bw && n_u > 1) {
             int32_t st = (int32_t)a[0].y, en = (int32_t)a[(int32_t)cs.u[0] - 1].y;
             if (qlen - (en - st) > o.rmq_rescue_size || en - st > qlen * o.rmq_rescue_ratio) {
                 for (int i = 0; i < n_u; ++i) m += (int32_t)cs.u[i];
-                rs_sort_emul(a, m, KeyX(), cs.sortws);
+                rs_sort_warp(a, m, cs.sortws, H);
             }
         }
     }
-    A.prob_nu[p] = n_u; A.prob_m[p] = m;
+    if (lane == 0) { A.prob_nu[p] = n_u; A.prob_m[p] = m; }
 }
 
 // re-chaining DP, one WARP per flagged problem
@@ -692,11 +857,13 @@ __global__ void __launch_bounds__(256) k_chain_rmq(const __grid_constant__ Chain
 
 __global__ void __launch_bounds__(128) k_chain_regs(const __grid_constant__ ChainArgs A)
 {
-    const int p = tp_problem<TP_CHAIN>(A.n_prob);
-    if (p < 0) return;
+    __shared__ SortSmem HS[4];
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (p >= A.n_prob) return;
     const int n_a = (int)(A.prob_aoff[p + 1] - A.prob_aoff[p]);
     if (n_a == 0) return;
     const Opt &o = A.o;
+    SortSmem &H = HS[threadIdx.x >> 5];
     ChainScratch cs; HitScratch hs; int cap_regs;
     prob_carve(A, p, n_a, cs, hs, &cap_regs);
     Anchor *a = A.anchors + A.prob_aoff[p];
@@ -705,9 +872,10 @@ __global__ void __launch_bounds__(128) k_chain_regs(const __grid_constant__ Chai
     int n_u = A.prob_nu[p], n_v = 0;
     const int m = A.prob_m[p];
     if (m > 0) {
-        chain_backtrack(m, cs, o.min_cnt, o.min_chain_score, o.bw_long, &n_u, &n_v);
-        if (n_u > 0) chain_compact(n_u, n_v, cs, a);
+        chain_backtrack_warp(m, cs, o.min_cnt, o.min_chain_score, o.bw_long, &n_u, &n_v, H);
+        if (n_u > 0) chain_compact_warp(n_u, cs, a, H);
     }
+    if (lane != 0) return;          // region bookkeeping: sequential
     int n_regs = 0, nca = 0;
     if (n_u > 0) {
         if (n_u > cap_regs) { atomicOr(A.err, TELR_ERR_REGCAP); n_u = cap_regs; }
