@@ -114,6 +114,52 @@ class Batch:
         n = (self.nmask[idx >> 5] >> (idx & 31).astype(np.uint32)) & 1
         return np.where(n == 1, 4, c).astype(np.uint8)
 
+    def slice(self, l0: int, l1: int) -> "Batch":
+        """Loci [l0, l1) as VIEWS of this batch's packed sequences (no re-packing): valid when the batch is packed locus by locus
+        (every sequence of a locus lies between the first sequence of that locus and the first of the next), as the native
+        gather and the synthetic generator pack it.  The small per-read / per-locus arrays are rebased copies."""
+        l0, l1 = int(l0), int(l1)
+        r0, r1 = int(self.locus_read_begin[l0]), int(self.locus_read_begin[l1])
+        starts = []
+        if l1 > l0:
+            starts.append(int(self.contig_off[l0:l1].min()))
+        if r1 > r0:
+            starts.append(int(self.read_off[r0:r1].min()))
+        if not starts:
+            z = np.zeros(0, np.uint32)
+            return Batch(self.preset, z, z, np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros(0, np.uint32), np.zeros(1, np.int32),
+                         np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.int32),
+                         self.flank_len, self.flank_off, self.te_len, self.te_off, {"owner": self})
+        beg = min(starts)
+        ends = [int((self.contig_off[l0:l1] + (self.contig_len[l0:l1].astype(np.int64) + 63) // 64 * 64).max())]
+        if r1 > r0:
+            ends.append(int((self.read_off[r0:r1] + (self.read_len[r0:r1].astype(np.int64) + 63) // 64 * 64).max()))
+        end = max(ends)
+        assert beg % 64 == 0 and end % 64 == 0
+        return Batch(self.preset, self.seq2[beg // 16: end // 16], self.nmask[beg // 32: end // 32],
+                     self.read_off[r0:r1] - beg, self.read_len[r0:r1].copy(), self.read_hash[r0:r1].copy(),
+                     (self.locus_read_begin[l0:l1 + 1] - r0).astype(np.int32), self.contig_off[l0:l1] - beg, self.contig_len[l0:l1].copy(),
+                     self.te_start[l0:l1].copy(), self.te_end[l0:l1].copy(),
+                     self.flank_len, self.flank_off, self.te_len, self.te_off, {"owner": self})
+
+    def is_packed_by_locus(self) -> bool:
+        """True when loci occupy disjoint, ascending base ranges (what `slice` needs)."""
+        if self.n_loci == 0:
+            return True
+        lrb = self.locus_read_begin
+        first = self.contig_off.copy()
+        has = lrb[1:] > lrb[:-1]
+        idx = np.nonzero(has)[0]
+        if len(idx):
+            rmin = np.minimum.reduceat(self.read_off, lrb[:-1][has]) if self.n_reads else np.zeros(0, np.int64)
+            first[idx] = np.minimum(first[idx], rmin)
+            rmax = np.maximum.reduceat(self.read_off, lrb[:-1][has])
+            last = self.contig_off.copy()
+            last[idx] = np.maximum(last[idx], rmax)
+        else:
+            last = self.contig_off.copy()
+        return bool((first[1:] > last[:-1]).all())
+
     def subset(self, loci) -> "Batch":
         """A new batch holding only ``loci`` (in that order); sequences are re-packed contiguously."""
         loci = list(loci)

@@ -122,18 +122,22 @@ def run_batch(batch: Batch, devices=None, **kw):
             return r.cov2x, r.af, r
         finally:
             ctx.close()
-    shards = partition_loci(batch, len(devices))
+    # A batch packed locus by locus (the native gather's layout) is cut into contiguous ranges of loci of about equal cost, which
+    # are views of the same packed arrays; any other layout goes through the LPT partition and re-packs every shard.
+    contiguous = batch.is_packed_by_locus()
+    shards = partition_contiguous(locus_costs(batch), len(devices)) if contiguous else partition_loci(batch, len(devices))
     cov = np.zeros((batch.n_loci, 8), np.int32)
     af = np.zeros(batch.n_loci, np.float64)
     errs = []
 
     def work(dev, loci):
         try:
-            if not loci:
+            if not len(loci):
                 return
             ctx = lib.Context(dev)
             try:
-                r = ctx.run(batch.subset(loci))
+                sub = batch.slice(loci[0], loci[-1] + 1) if contiguous else batch.subset(loci)
+                r = ctx.run(sub)
                 cov[loci] = r.cov2x
                 af[loci] = r.af
             finally:
@@ -217,6 +221,16 @@ def partition_costs(cost, n: int):
     return [sorted(s) for s in shards]
 
 
+def partition_contiguous(cost, n: int):
+    """n contiguous ranges of items with about equal total cost (cuts at the multiples of total / n of the running sum)."""
+    cost = np.asarray(cost, np.int64)
+    csum = np.cumsum(cost)
+    total = int(csum[-1]) if len(csum) else 0
+    cuts = [0] + [int(np.searchsorted(csum, total * (k + 1) / n, side="left")) + 1 for k in range(n - 1)] + [len(cost)]
+    cuts = np.minimum.accumulate(np.minimum(np.array(cuts)[::-1], len(cost)))[::-1]
+    return [list(range(int(cuts[k]), int(max(cuts[k], cuts[k + 1])))) for k in range(n)]
+
+
 def partition_loci(batch: Batch, n: int):
     """Longest-processing-time-first assignment of loci to n shards by read bases + contig length."""
     return partition_costs(locus_costs(batch), n)
@@ -284,6 +298,8 @@ def get_af(out, sample_name, bam, raw_reads, contig_te_annotation, contig_dir, v
     te_e = np.array([coords.get(loci[i][0], (-1, -1))[1] for i in live], np.int32)
     batch = Batch(PRESETS[presets], g.seq2, g.nmask, g.read_off, g.read_len, g.read_hash, lrb, g.contig_off, g.contig_len, te_s, te_e,
                   int(flank_intervel_size), int(flank_offset), int(te_interval_size or 0), int(te_offset), meta={"owner": g})      # the arrays are views of g's buffers
+    if batch.n_loci and int(np.diff(lrb).max()) > 8000:
+        logging.warning("a locus has more than 8000 reads: samtools 1.9 depth would cap its pile-up (-d 8000); this path counts every read")
     empty = [j for j in range(len(live)) if lrb[j + 1] == lrb[j]]
     keep_bam = os.environ.get("TELR_B200_KEEP_BAM", "0") == "1"      # the `-k` intermediates <locus>[.revcomp].realign.sort.bam(.bai)
     if batch.n_loci:

@@ -310,6 +310,41 @@ def test_partition_is_balanced_and_complete(built):
         assert max(cost) <= 1.6 * (sum(cost) / n) + max(int(b.read_len.sum()) // 16, 1)
 
 
+def test_contiguous_shards_are_views_of_the_batch(built):
+    """run_batch over several devices cuts a batch that is packed locus by locus into contiguous ranges of about equal cost;
+    a range is a view of the packed arrays (Batch.slice) and holds exactly what the re-packing subset() holds."""
+    b = synth.generate("ont_3k_50x", 0, 17, depth=6)
+    assert b.is_packed_by_locus()
+    cost = stage4.locus_costs(b)
+    for n in (1, 2, 3, 8, 17, 20):
+        sh = stage4.partition_contiguous(cost, n)
+        assert len(sh) == n and sum(sh, []) == list(range(17))
+        loads = [int(cost[s].sum()) for s in sh if s]
+        if n <= 8:
+            assert max(loads) <= cost.sum() / n + cost.max()
+        for s_ in sh:
+            if not s_:
+                continue
+            v, w = b.slice(s_[0], s_[-1] + 1), b.subset(s_)
+            v.validate()
+            assert np.shares_memory(v.seq2, b.seq2)
+            assert (v.read_len == w.read_len).all() and (v.read_hash == w.read_hash).all() and (v.locus_read_begin == w.locus_read_begin).all()
+            assert (v.contig_len == w.contig_len).all() and (v.te_start == w.te_start).all()
+            for r in range(0, v.n_reads, 7):
+                assert (v.unpack(int(v.read_off[r]), int(v.read_len[r])) == w.unpack(int(w.read_off[r]), int(w.read_len[r]))).all()
+            for l in range(v.n_loci):
+                assert (v.unpack(int(v.contig_off[l]), int(v.contig_len[l])) == w.unpack(int(w.contig_off[l]), int(w.contig_len[l]))).all()
+            ro_v = orc.af_run(v, threads=0, want_depth=False, want_aln=False) if n == 3 else None
+            if ro_v is not None:
+                ro_w = orc.af_run(w, threads=0, want_depth=False, want_aln=False)
+                assert (ro_v.cov2x == ro_w.cov2x).all()
+    shuffled = b.subset([3, 1, 2])
+    assert shuffled.is_packed_by_locus()          # re-packed in the requested order
+    b2 = Batch(b.preset, b.seq2, b.nmask, b.read_off, b.read_len, b.read_hash, b.locus_read_begin, b.contig_off[::-1].copy(), b.contig_len[::-1].copy(),
+               b.te_start, b.te_end)
+    assert not b2.is_packed_by_locus()
+
+
 def _shard_worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
