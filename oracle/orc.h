@@ -78,6 +78,8 @@ typedef struct orc_ez {
 void orc_ksw_extd2(int qlen, const uint8_t *query, int tlen, const uint8_t *target,
                    int a, int b, int sc_ambi, int q, int e, int q2, int e2,
                    int w, int zdrop, int end_bonus, int flag, orc_ez_t *ez);
+/* bounded extension (work-saving, exact for every consumed output): on by default; 0 = compute every anti-diagonal like ksw2 */
+void orc_set_ext_bound(int on);
 /* [UP] ksw_ll_i16: local affine SW, score + end coordinates */
 int orc_ksw_ll(int qlen, const uint8_t *query, int tlen, const uint8_t *target,
                int a, int b, int sc_ambi, int gapo, int gape, int *qe, int *te);

@@ -17,6 +17,9 @@
 #include <assert.h>
 #include "orc.h"
 
+int orc_ext_bound = 1;     /* bounded extension rule on (see orc_ksw_extd2); tests switch it off to show that no output depends on it */
+void orc_set_ext_bound(int on) { orc_ext_bound = on; }
+
 #define KSW_NEG_INF (-0x40000000)
 
 static void ez_reset(orc_ez_t *ez)
@@ -138,6 +141,24 @@ void orc_ksw_extd2(int qlen, const uint8_t *query, int tlen, const uint8_t *targ
         int st = 0, en = tlen - 1;
         int32_t x1, x21, v1;
         uint8_t *pr;
+        /* Bounded extension (an exact work-saving rule of this project, not of ksw2; orc_ext_bound = 0 switches it off).  An
+         * extension only reports its maximum (max, max_t, max_q; align.c never reads zdropped of an extension, and with
+         * end_bonus <= 0 the query-end rule `mqe + end_bonus > max` cannot hold since mqe <= max).  A cell (i, j) of
+         * anti-diagonal r scores at most sc_a * min(i + 1, j + 1) - gap(|i - j|): that many matches at best, and the offset
+         * between the two coordinates has to be paid for by gaps, a single gap being the cheapest way.  Once a sequence is
+         * exhausted, |i - j| >= r - 2 (len - 1) grows with r, so as soon as the bound is not above the maximum found so far
+         * no later anti-diagonal can change the result: stop.  Typical case: a read overhanging the contig end by thousands
+         * of bases, where ksw2 keeps ~750 anti-diagonals of a few dozen cells alive until the band runs out. */
+        if (orc_ext_bound && (flag & ORC_KSW_EXTZ_ONLY) && !approx_max && end_bonus <= 0) {
+            int dmin = r - 2 * (tlen - 1) > r - 2 * (qlen - 1) ? r - 2 * (tlen - 1) : r - 2 * (qlen - 1);
+            if (dmin > 0) {
+                int mcap = tlen < qlen ? tlen : qlen;
+                int64_t g1 = (int64_t)q + (int64_t)e * dmin, g2 = (int64_t)q2 + (int64_t)e2 * dmin, ub;
+                if ((r >> 1) + 1 < mcap) mcap = (r >> 1) + 1;
+                ub = (int64_t)sc_a * mcap - (g1 < g2 ? g1 : g2);
+                if (ub <= ez->max) { ez->zdropped = 1; break; }
+            }
+        }
         if (st < r - qlen + 1) st = r - qlen + 1;
         if (en > r) en = r;
         if (st < (r - w + 1) >> 1) st = (r - w + 1) >> 1;

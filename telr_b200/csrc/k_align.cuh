@@ -86,6 +86,24 @@ constexpr int AQ_ROLES = 3;
 constexpr int AQ_MAX_SM = 1024;        // per-SM role words follow the counters in q_state
 enum { AQ_HEAD0 = 0, AQ_TAIL0 = 3, AQ_AVAIL0 = 6, AQ_DONE = 9, AQ_START = 10, AQ_STEAL = 11, AQ_SLOTS = 16 };
 
+// Bounded extension (exact work saving).  An extension only reports its maximum (max, max_t, max_q): the caller never reads
+// zdropped of an extension, and with end_bonus <= 0 the query-end rule `mqe + end_bonus > max` cannot hold (mqe <= max).  A cell
+// (i, j) of anti-diagonal r scores at most a * min(i + 1, j + 1) - gap(|i - j|) -- that many matches at best, and the offset
+// between the coordinates has to be paid for by gaps, one gap being the cheapest way.  Once one sequence is exhausted
+// |i - j| >= r - 2 (len - 1) grows with r; when the bound is not above the maximum found so far, no later anti-diagonal can
+// change the result.  Typical case: a read overhanging the contig end by thousands of bases, where ksw2 keeps ~750
+// anti-diagonals of a few dozen cells alive until the band runs out (11 % of the alignment kernel's time on config 2).
+// The oracle applies the same rule (orc_ksw_extd2), so cell counts stay equal; tests show that no output depends on it.
+__device__ __forceinline__ bool ext_bound_stop(int a, int q, int e, int q2, int e2, int qlen, int tlen, int r, int32_t ez_max)
+{
+    const int dt = r - 2 * (tlen - 1), dq = r - 2 * (qlen - 1), dmin = dt > dq ? dt : dq;
+    if (dmin <= 0) return false;
+    int mcap = tlen < qlen ? tlen : qlen;
+    if ((r >> 1) + 1 < mcap) mcap = (r >> 1) + 1;
+    const long long g1 = (long long)q + (long long)e * dmin, g2 = (long long)q2 + (long long)e2 * dmin;
+    return (long long)a * mcap - (g1 < g2 ? g1 : g2) <= (long long)ez_max;
+}
+
 __device__ __forceinline__ int dp_base(const uint8_t *p, int step, int comp, int i)
 {
     int b = p[(ptrdiff_t)i * step];
@@ -155,7 +173,9 @@ __device__ void warp_extd2_impl(const Opt &o, const DpTask &T, DpRes &R, DpScrat
     int32_t H0 = 0, last_H0_t = 0;
     unsigned long long cells = 0;
     const int nr = qlen + tlen - 1;
+    const bool bounded = (flag & KSW_EXTZ_ONLY) && !approx && T.end_bonus <= 0;
     for (int r = 0; r < nr; ++r) {
+        if (bounded && ext_bound_stop(o.a, q, e, q2, e2, qlen, tlen, r, ez_max)) { zdropped = 1; break; }
         int st = 0, en = tlen - 1;
         if (st < r - qlen + 1) st = r - qlen + 1;
         if (en > r) en = r;

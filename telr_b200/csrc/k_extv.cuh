@@ -84,7 +84,11 @@ __device__ bool warp_extd2_vec(const Opt &o, const DpTask &T, DpRes &R, VecSmem 
     unsigned long long cells = 0;
     const int nr = qlen + tlen - 1;
     bool bail = false;
+    const bool bounded = (flag & KSW_EXTZ_ONLY) && !approx && T.end_bonus <= 0;
+    const int mlen = tlen < qlen ? tlen : qlen, r_over = 2 * (mlen - 1);      // beyond r_over one sequence is exhausted
     for (int r = 0; r < nr; ++r) {
+        // bounded extension: no cell of this or a later anti-diagonal can beat the maximum found so far (ext_bound_stop)
+        if (bounded && r > r_over && ext_bound_stop(o.a, q, e, q2, e2, qlen, tlen, r, ez_max)) { zdropped = 1; break; }
         int st = 0, en = tlen - 1;
         if (st < r - qlen + 1) st = r - qlen + 1;
         if (en > r) en = r;

@@ -72,6 +72,7 @@ def lib():
         L.orc_dbg_free.argtypes = [C.POINTER(OrcDbg)]
         L.orc_radix_sort_128x.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_set_bw.argtypes = [C.c_int, C.c_int]
+        L.orc_set_ext_bound.argtypes = [C.c_int]
         L.orc_name_hash.restype = C.c_uint32
         L.orc_name_hash.argtypes = [C.c_char_p]
         _LIB = L
@@ -178,3 +179,8 @@ def map_one(o: OrcOpt, contig: np.ndarray, read: np.ndarray, name_hash: int = 0,
 def set_bw(bw: int = 0, bw_long: int = 0):
     """minimap2 -r NUM[,NUM] on top of the preset for af_run (0 = preset value)."""
     lib().orc_set_bw(int(bw), int(bw_long))
+
+
+def set_ext_bound(on: bool = True):
+    """Bounded extension rule of orc_ksw_extd2 (exact work saving); False = every anti-diagonal like ksw2."""
+    lib().orc_set_ext_bound(1 if on else 0)

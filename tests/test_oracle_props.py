@@ -263,3 +263,38 @@ def test_deviation_reach_counters(built):
     assert tot[5] > 1000 and tot[6] > 10000                    # the counted paths did run: banded DP calls, RMQ queries
     assert tot[0] == 0 and tot[2] == 0 and tot[3] == 0 and tot[4] == 0, tot.tolist()
     assert tot[1] <= 1e-5 * tot[6], tot.tolist()               # measured: 7 ties in 5.8 M queries over 530 loci (profiles/README.md)
+
+
+def test_bounded_extension_changes_no_output(built):
+    """The bounded-extension rule (stop an extension once no later anti-diagonal can beat the maximum found so far) saves rows,
+    never results: with the rule switched off -- every anti-diagonal computed, as ksw2 does -- the oracle gives the same alignment
+    records, CIGARs, depth and coverage integers; only the cell count differs."""
+    from telr_b200 import synth
+    from tests import util
+    saved = []
+    try:
+        for cfg, first, n in (("ont_3k_50x", 30, 6), ("clr_3k_40x", 5, 4), ("hifi_3k_40x", 5, 4)):
+            b = synth.generate(cfg, first, n)
+            orc.set_ext_bound(False)
+            r0 = orc.af_run(b, threads=0)
+            orc.set_ext_bound(True)
+            r1 = orc.af_run(b, threads=0)
+            util.assert_same_results(r1, r0)
+            assert r1.c.dp_cells < r0.c.dp_cells
+            saved.append(1 - int(r1.c.dp_cells) / int(r0.c.dp_cells))
+        # single calls: an overhanging query against a short target, with and without the rule
+        rng = np.random.default_rng(5)
+        o = orc.opt(0)
+        for tl in (8, 30, 120, 400):
+            t = rand_seq(rng, tl)
+            q = np.concatenate([t[: tl * 3 // 4], rand_seq(rng, 3000)])
+            for flag in (orc_flag("EXTZ"), orc_flag("EXTZ") | orc_flag("RIGHT") | orc_flag("REV")):
+                orc.set_ext_bound(False)
+                a = orc.ksw_extd2(q, t, o, 751, 400, -1, flag)
+                orc.set_ext_bound(True)
+                bnd = orc.ksw_extd2(q, t, o, 751, 400, -1, flag)
+                assert all(a[k] == bnd[k] for k in ("max", "max_q", "max_t", "reach_end")) and (a["cigar"] == bnd["cigar"]).all()
+                assert bnd["cells"] < a["cells"] * (0.6 if tl <= 120 else 1.0)
+    finally:
+        orc.set_ext_bound(True)
+    assert min(saved) > 0.005
