@@ -1,4 +1,5 @@
-"""Minimal BAM/BGZF reader and writer (pure Python) for the read gather of stage 4.
+"""Minimal BAM/BGZF reader and writer (pure Python).  TEST INFRASTRUCTURE: the independent implementation the native I/O library
+(telr_b200/csrc/telr_io.cpp) is checked against, and the writer of the test BAMs.  The product reads BAMs through telr_io only.
 
 The reference collects, per locus, the names of all BAM records overlapping the +-1 kb breakpoint window
 with ``pysam.AlignmentFile.fetch`` (TELR_assembly.py:385-408).  pysam/htslib are not available in this

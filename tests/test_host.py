@@ -8,7 +8,8 @@ import re
 import numpy as np
 import pytest
 
-from telr_b200 import bamio, gather, lib, realign, stage4, synth
+from telr_b200 import gather, lib, realign, stage4, synth
+from tests import bamio
 from telr_b200.batch import Batch, PRESETS, name_hash, pack_sequences
 from tests import orc, util
 
