@@ -12,6 +12,16 @@
 // four PRMTs in sign-replicate mode; one 8-byte store per row per lane writes them row-major.
 // Left-to-right values (v,x,x2) travel between lanes by shuffle, between 256-column passes through a small
 // per-warp boundary array.  No tensor cores: this is not a dense contraction.
+//
+// Number representation (round 2).  sm_100a has no packed 16x2 subtract (`__vsub2` = LOP3 + 2 x VIADD.16x2), and the recurrence
+// subtracts seven times per cell pair.  Every stored half-word therefore carries an offset that keeps it NON-NEGATIVE, so that a
+// plain 32-bit IADD3 (three inputs, free negation) acts on the two halves independently — no borrow ever crosses bit 16:
+//     u, v         + FB                      (FB = 60; the differences are bounded by the gap costs)
+//     s, z, a, b.. + 2 FB                    (the score table holds s + 2 FB as a positive int8)
+//     x, y         + (q + e - 1) + 0x8000,   x2, y2 + (q2 + e2 - 1) + 0x8000
+// With that offset a gap state equals 0x7fff exactly when it was reset to -(q + e) and has bit 15 set exactly when it continues:
+// the continuation flag is the stored value's top bit (no compare), and "t - z + 0x8000" has bit 15 set exactly when t is the
+// maximum.  33 -> 29 arithmetic/permute operations per cell pair, none of them a negation.
 #pragma once
 #include <cuda_runtime.h>
 #include "mm_align.cuh"
@@ -22,6 +32,7 @@ namespace telr {
 #define TELR_FILL_FC12 1
 #endif
 constexpr int FC_MAX = 12;            // columns per lane: 8 (256-column passes) or 12 (384-column passes)
+constexpr int FB = 60;                // offset of the stored differences (see "Number representation" above)
 
 // prmt.b32 in default mode: selector nibble bit 3 replicates the sign of the selected byte (__byte_perm drops that bit)
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
@@ -30,6 +41,17 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
     return d;
 }
+// a * m + c as an integer multiply-add: IMAD issues on the FMA pipe, which the recurrence's permutes, min/max ops and IADD3s
+// (all on the ALU pipe) leave idle.  The multiplier is a run-time register so that ptxas keeps the IMAD
+// (profiles/ubench/pipes2.cu: IMAD + PRMT 0.92 warp-instructions per clock and sub-partition, IADD3 + PRMT 0.50).
+__device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t m, uint32_t c)
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(m), "r"(c));
+    return d;
+}
+// 1 that the compiler cannot see through (gridDim.z of every launch in this library)
+__device__ __forceinline__ uint32_t opaque_one() { uint32_t d; asm volatile("mov.u32 %0, %%nctaid.z;" : "=r"(d)); return d; }
 __device__ __forceinline__ uint32_t pk2(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
 __device__ __forceinline__ uint32_t pk1(int v) { return pk2(v, v); }
 __device__ __forceinline__ int lo16(uint32_t v) { return (int)(int16_t)(v & 0xffffu); }
@@ -82,11 +104,14 @@ __device__ void warp_fill_fwd(const Opt &o, const DpTask &T, DpRes &R, uint8_t *
     int LT = e != e2 ? (q2 - q) / (e - e2) - 1 : 0;
     if (q2 + e2 + LT * e2 > q + e + LT * e) ++LT;
     const int LD = LT * (e - e2) - (q2 - q) - e2;
-#define BNDF(r) ((r) == 0 ? -qe : (r) < LT ? -e : (r) == LT ? LD : -e2)
-    const uint32_t NE1 = pk1(-e), NQE1 = pk1(-qe), NE2 = pk1(-e2), NQE2 = pk1(-qe2);
-    const uint32_t QM1 = pk1(q - 1), Q2M1 = pk1(q2 - 1);
-    // score table of one target base: byte c = score against query base c (int8)
-    const uint32_t TS_MIS = 0x01010101u * ((uint32_t)(-o.b) & 0xffu), TS_FLIP = ((uint32_t)o.a ^ (uint32_t)(-o.b)) & 0xffu;
+#define BNDF(r) (FB + ((r) == 0 ? -qe : (r) < LT ? -e : (r) == LT ? LD : -e2))
+    const int BX = qe - 1 + 0x8000, BX2 = qe2 - 1 + 0x8000;                     // offsets of x, y and of x2, y2
+    const uint32_t CA = (uint32_t)(FB - BX) * 65537u, CA2 = (uint32_t)(FB - BX2) * 65537u;      // a = x + v + CA: exact on both halves
+    const uint32_t QM1 = pk1(q - 1), Q2M1 = pk1(q2 - 1), XFLOOR = 0x7fff7fffu, DK = 0x80008000u;
+    const uint32_t X0 = pk1(BX - qe), X20 = pk1(BX2 - qe2);                     // a gap state that has just been reset (= XFLOOR)
+    // score table of one target base: byte c = score against query base c, + 2 FB (a positive int8)
+    const uint32_t TS_MIS = 0x01010101u * (uint32_t)(2 * FB - o.b), TS_FLIP = (uint32_t)(2 * FB + o.a) ^ (uint32_t)(2 * FB - o.b);
+    const uint32_t ONE = opaque_one(), MONE = 0u - ONE, TWO = ONE + ONE, K01 = 0x01010101u * ONE;
     const int stride = fill_stride(tlen);
     const int npairs = (qlen + 1) >> 1, npass = (tlen + FW - 1) / FW;
     int usum = 0;
@@ -103,7 +128,7 @@ __device__ void warp_fill_fwd(const Opt &o, const DpTask &T, DpRes &R, uint8_t *
 #pragma unroll
         for (int k = 0; k < FC; ++k) {              // top boundary sits in the hi halves (row "-1" of pair 0)
             const int r = t0 + k;
-            Uu[k] = pk2(0, BNDF(r)); Uy[k] = pk2(0, -qe); Uy2[k] = pk2(0, -qe2);
+            Uu[k] = pk2(FB, BNDF(r)); Uy[k] = X0; Uy2[k] = X20;
         }
         uint32_t inV = 0, inX = 0, inX2 = 0, Ufirst = 0;
         const bool last_pass = pass == npass - 1;
@@ -114,7 +139,7 @@ __device__ void warp_fill_fwd(const Opt &o, const DpTask &T, DpRes &R, uint8_t *
             if (lane == 0 && s < npairs) {
                 const int j = 2 * s;
                 if (pass == 0) {
-                    inV = pk2(BNDF(j), BNDF(j + 1)); inX = NQE1; inX2 = NQE2;
+                    inV = pk2(BNDF(j), BNDF(j + 1)); inX = X0; inX2 = X20;
                 } else { inV = bnd[3 * s]; inX = bnd[3 * s + 1]; inX2 = bnd[3 * s + 2]; }
             }
             uint32_t outV = 0, outX = 0, outX2 = 0;
@@ -124,9 +149,9 @@ __device__ void warp_fill_fwd(const Opt &o, const DpTask &T, DpRes &R, uint8_t *
                 // lo half <- sign-extended byte q[j] of the first table, hi half <- byte q[j+1] of the second
                 const uint32_t q0 = Q[j], q1 = j + 1 < qlen ? Q[j + 1] : 0;
                 const uint32_t inQ = q0 | (q0 | 8u) << 4 | (q1 + 4u) << 8 | (q1 + 12u) << 12;
-                uint32_t Lv = inV, Lx = inX, Lx2 = inX2, pu = 0, py = 0, py2 = 0, kV = 0, kX = 0, kX2 = 0;
+                uint32_t Lv = inV, Lx = inX, Lx2 = inX2, pu = pk1(FB), py = X0, py2 = X20, kV = 0, kX = 0, kX2 = 0;
                 uint32_t W[FC / 2 + 1];             // W[p]: flag bytes of cells (2p, j), (2p-1, j+1), (2p+1, j), (2p, j+1)
-                uint32_t eDS = 0, eDA = 0, eDB = 0, eDA2 = 0, eCX = 0, eCY = 0, eCX2 = 0, eCY2 = 0;   // even iteration, waiting for its partner
+                uint32_t eDS = 0, eDA = 0, eDB = 0, eDA2 = 0, eNX = 0, eNY = 0, eNX2 = 0, eNY2 = 0;   // even iteration, waiting for its partner
 #pragma unroll
                 for (int k = 0; k <= FC; ++k) {
                     const int kk = k < FC ? k : FC - 1, kh = k > 0 ? k - 1 : 0;
@@ -136,34 +161,39 @@ __device__ void warp_fill_fwd(const Opt &o, const DpTask &T, DpRes &R, uint8_t *
                         Lv = __byte_perm(Lv, inV, 0x7610); Lx = __byte_perm(Lx, inX, 0x7610); Lx2 = __byte_perm(Lx2, inX2, 0x7610);
                     }
                     const uint32_t S = prmt(TS[kk], TS[kh], inQ);
-                    const uint32_t A = __vadd2(Lx, Lv), A2 = __vadd2(Lx2, Lv), B = __vadd2(up_y, up_u), B2 = __vadd2(up_y2, up_u);
+                    const uint32_t A = Lx + Lv + CA, A2 = Lx2 + Lv + CA2, B = up_y + up_u + CA, B2 = up_y2 + up_u + CA2;
                     uint32_t Z = __vimax3_s16x2(S, A, B);
                     Z = __vimax3_s16x2(Z, A2, B2);
-                    const uint32_t DS = __vsub2(S, Z), DA = __vsub2(A, Z), DB = __vsub2(B, Z), DA2 = __vsub2(A2, Z), DB2 = __vsub2(B2, Z);
-                    const uint32_t nu = __vsub2(Z, Lv), nv = __vsub2(Z, up_u);
-                    const uint32_t nx = __viaddmax_s16x2(DA, NE1, NQE1), ny = __viaddmax_s16x2(DB, NE1, NQE1);
-                    const uint32_t nx2 = __viaddmax_s16x2(DA2, NE2, NQE2), ny2 = __viaddmax_s16x2(DB2, NE2, NQE2);
-                    const uint32_t cx = __vadd2(DA, QM1), cy = __vadd2(DB, QM1), cx2 = __vadd2(DA2, Q2M1), cy2 = __vadd2(DB2, Q2M1);
-                    // 8 sign bits per cell -> one byte per cell.  Two iterations are gathered together, one PRMT per flag:
-                    // bytes (k lo, k hi, k+1 lo, k+1 hi) of flag f land on bit f of the four cell bytes.
+                    // t - z + 0x8000 per half: bit 15 set exactly when t is the maximum (two-input adds: FMA pipe)
+                    const uint32_t NZ = imad(Z, MONE, DK);
+                    const uint32_t DS = imad(S, ONE, NZ), DA = imad(A, ONE, NZ), DB = imad(B, ONE, NZ), DA2 = imad(A2, ONE, NZ), DB2 = imad(B2, ONE, NZ);
+                    const uint32_t nu = imad(Lv, MONE, Z), nv = imad(up_u, MONE, Z);
+                    // max(t - z - e, -(q + e)) in the offset form: bit 15 set exactly when the gap continues
+                    const uint32_t nx = __viaddmax_u16x2(DA, QM1, XFLOOR), ny = __viaddmax_u16x2(DB, QM1, XFLOOR);
+                    const uint32_t nx2 = __viaddmax_u16x2(DA2, Q2M1, XFLOOR), ny2 = __viaddmax_u16x2(DB2, Q2M1, XFLOOR);
+                    // 8 top bits per cell -> one byte per cell (a flag is the COMPLEMENT of the top bit: "below the maximum",
+                    // "does not continue").  Two iterations are gathered together: one PRMT per flag replicates the top bits of
+                    // (k lo, k hi, k+1 lo, k+1 hi) into the bytes r_f of a word (0x00 / 0xff).  sum_f r_f 2^f = 255 T (mod 2^32),
+                    // T = the word of top-bit bytes (each 0xff byte is 256 - 1: the carries telescope), so the flag word
+                    // ~T = -1 - 255 T / 255 = (sum_f r_f 2^f) * 0x01010101 - 1: Horner steps and one multiply, all IMADs.
                     if (k == FC) {                  // last iteration (even): only its hi cell (FC-1, j+1) exists
-                        uint32_t acc = prmt(DS, DA, 0xFDB9) & 0x02020101u;
-                        acc |= prmt(DB, DA2, 0xFDB9) & 0x08080404u;
-                        acc |= prmt(cx, cy, 0xFDB9) & 0x20201010u;
-                        acc |= prmt(cx2, cy2, 0xFDB9) & 0x80804040u;
+                        uint32_t acc = ~prmt(DS, DA, 0xFDB9) & 0x02020101u;
+                        acc |= ~prmt(DB, DA2, 0xFDB9) & 0x08080404u;
+                        acc |= ~prmt(nx, ny, 0xFDB9) & 0x20201010u;
+                        acc |= ~prmt(nx2, ny2, 0xFDB9) & 0x80804040u;
                         W[FC / 2] = acc | (acc >> 16);          // byte 1
                     } else if (!(k & 1)) {
-                        eDS = DS; eDA = DA; eDB = DB; eDA2 = DA2; eCX = cx; eCY = cy; eCX2 = cx2; eCY2 = cy2;
+                        eDS = DS; eDA = DA; eDB = DB; eDA2 = DA2; eNX = nx; eNY = ny; eNX2 = nx2; eNY2 = ny2;
                     } else {
-                        uint32_t acc = prmt(eDS, DS, 0xFDB9) & 0x01010101u;
-                        acc |= prmt(eDA, DA, 0xFDB9) & 0x02020202u;
-                        acc |= prmt(eDB, DB, 0xFDB9) & 0x04040404u;
-                        acc |= prmt(eDA2, DA2, 0xFDB9) & 0x08080808u;
-                        acc |= prmt(eCX, cx, 0xFDB9) & 0x10101010u;
-                        acc |= prmt(eCY, cy, 0xFDB9) & 0x20202020u;
-                        acc |= prmt(eCX2, cx2, 0xFDB9) & 0x40404040u;
-                        acc |= prmt(eCY2, cy2, 0xFDB9) & 0x80808080u;
-                        W[k >> 1] = acc;
+                        uint32_t acc = prmt(eNY2, ny2, 0xFDB9);
+                        acc = imad(acc, TWO, prmt(eNX2, nx2, 0xFDB9));
+                        acc = imad(acc, TWO, prmt(eNY, ny, 0xFDB9));
+                        acc = imad(acc, TWO, prmt(eNX, nx, 0xFDB9));
+                        acc = imad(acc, TWO, prmt(eDA2, DA2, 0xFDB9));
+                        acc = imad(acc, TWO, prmt(eDB, DB, 0xFDB9));
+                        acc = imad(acc, TWO, prmt(eDA, DA, 0xFDB9));
+                        acc = imad(acc, TWO, prmt(eDS, DS, 0xFDB9));
+                        W[k >> 1] = imad(acc, K01, 0xffffffffu);
                     }
                     if (k >= 1) { Uu[k - 1] = nu; Uy[k - 1] = ny; Uy2[k - 1] = ny2; }      // hi halves: cell (k-1, j+1) = up input of the next row pair
                     if (k == 0) Ufirst = nu;
@@ -201,8 +231,8 @@ __device__ void warp_fill_fwd(const Opt &o, const DpTask &T, DpRes &R, uint8_t *
 #pragma unroll
             for (int k = 0; k < FC; ++k) {
                 if (t0 + k >= tlen) continue;
-                if (qlen & 1) usum += k == 0 ? lo16(Ufirst) : lo16(Uu[k - 1]);     // last real row = first row of the last pair
-                else usum += hi16(Uu[k]);
+                if (qlen & 1) usum += (k == 0 ? lo16(Ufirst) : lo16(Uu[k - 1])) - FB;     // last real row = first row of the last pair
+                else usum += hi16(Uu[k]) - FB;
             }
         }
         __syncwarp();       // bnd[] written by lane 31 is read by lane 0 in the next pass
@@ -227,7 +257,10 @@ __device__ bool warp_fill_fast(const Opt &o, const DpTask &T, DpRes &R, uint8_t 
         for (int i = lane; i < T.tlen; i += 32) n |= T.t[i] > 3;
         if (__any_sync(0xffffffffu, n)) return false;
     }
-    if (o.a > 127 || o.b > 127) return false;            // score tables are int8
+    {   // the offset representation needs every stored half-word in [0, 2 FB + a] (score table = positive int8)
+        const int qm = o.q + o.e > o.q2 + o.e2 ? o.q + o.e : o.q2 + o.e2;
+        if (o.a < 0 || o.b < 0 || 2 * FB + o.a > 127 || o.a + o.b + qm > FB) return false;
+    }
 #if TELR_FILL_FC12
     // the 12-column instance halves the passes of 257..384-column fills but doubles the hot code: it pays only where it has SMs
     // of its own (k_al_queue, role 2); sharing an instruction cache with the 8-column instance it costs 35 % (profiles/README.md)
