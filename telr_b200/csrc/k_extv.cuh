@@ -7,6 +7,9 @@
 // shared table of packed match/mismatch scores.  (An 8-column variant executes fewer instructions but its larger loop
 // body costs more in instruction-cache misses than it saves: measured 12 % slower end to end.)  In exact mode the running H row is updated in the same pass and the
 // row maximum (with the reference's tie order) is found with one integer key per cell and a single warp reduction.
+// The shared-memory state is held in the offset form of k_fill.cuh — bytes u + FB, v + FB, x + (q + e), y + (q + e),
+// x2 + (q2 + e2), y2 + (q2 + e2), all non-negative — so that the recurrence runs on 32-bit adds (IADD3 / IMAD) without packed
+// negations, and the flag gather is the Horner form described there.
 // Direction bytes use the sign-bit format:
 //   bits 0-3: "below the maximum" for (s,a,b,a2) [left-aligned gaps] or (b2,a,b,a2) [right-aligned]
 //   bits 4-7: "gap does not continue" for x,y,x2,y2
@@ -26,7 +29,7 @@ struct VecSmem { int8_t st[6][VSC]; int32_t H[VSC]; uint8_t tb[VCW / 4]; uint8_t
 __device__ __forceinline__ void vec_fill_stab(uint2 *stab, const Opt &o)
 {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-        const int s0 = (i & 3) ? -o.b : o.a, s1 = ((i >> 2) & 3) ? -o.b : o.a, s2 = ((i >> 4) & 3) ? -o.b : o.a, s3 = ((i >> 6) & 3) ? -o.b : o.a;
+        const int s0 = 2 * FB + ((i & 3) ? -o.b : o.a), s1 = 2 * FB + (((i >> 2) & 3) ? -o.b : o.a), s2 = 2 * FB + (((i >> 4) & 3) ? -o.b : o.a), s3 = 2 * FB + (((i >> 6) & 3) ? -o.b : o.a);
         stab[i] = make_uint2(((uint32_t)s0 & 0xffffu) | ((uint32_t)s1 << 16), ((uint32_t)s2 & 0xffffu) | ((uint32_t)s3 << 16));
     }
     __syncthreads();
@@ -51,6 +54,8 @@ __host__ __device__ __forceinline__ bool vec_ok(const Opt &o, int qlen, int tlen
 {
     if (qlen <= 0 || tlen <= 0 || vec_ncol(qlen, tlen, w_in) > VEC_MAX_NCOL) return false;
     // |H| must stay below 2^20 for the packed (score, rank) keys
+    const int qm = o.q + o.e > o.q2 + o.e2 ? o.q + o.e : o.q2 + o.e2;
+    if (o.a < 0 || o.b < 0 || o.a + o.b + qm > FB) return false;      // offset form: every stored byte stays in [0, 2 FB + a]
     const long long mab = o.a > o.b ? o.a : o.b, me = o.e > o.e2 ? o.e : o.e2;
     return mab * (qlen < tlen ? qlen : tlen) + o.q + o.q2 + me * ((long long)qlen + tlen) < (1 << 20) - 64;
 }
@@ -70,14 +75,16 @@ __device__ bool warp_extd2_vec(const Opt &o, const DpTask &T, DpRes &R, VecSmem 
     if (q2 + e2 + LT * e2 > q + e + LT * e) ++LT;
     const int LD = LT * (e - e2) - (q2 - q) - e2;
     const bool approx = flag & KSW_APPROX_MAX;
-    const uint32_t NE1 = pk1(-e), NQE1 = pk1(-qe), NE2 = pk1(-e2), NQE2 = pk1(-qe2);
-    const uint32_t QC1 = pk1(q - 1 + (RIGHT ? 1 : 0)), QC2 = pk1(q2 - 1 + (RIGHT ? 1 : 0));
-    int8_t *u = M.st[0], *v = M.st[1], *x = M.st[2], *y = M.st[3], *x2 = M.st[4], *y2 = M.st[5];
+    const uint32_t QC1 = pk1(q - 1 + (RIGHT ? 1 : 0)), QC2 = pk1(q2 - 1 + (RIGHT ? 1 : 0)), Q1 = pk1(q), Q2 = pk1(q2);
+    const uint32_t CA = (uint32_t)(FB - qe) * 65537u, CA2 = (uint32_t)(FB - qe2) * 65537u, DK = 0x80008000u;
+    const uint32_t ONE = opaque_one(), MONE = 0u - ONE, TWO = ONE + ONE, FOUR = TWO + TWO, SIXTEEN = FOUR * FOUR, K01 = 0x01010101u * ONE;
+    uint8_t *u = reinterpret_cast<uint8_t *>(M.st[0]), *v = reinterpret_cast<uint8_t *>(M.st[1]), *x = reinterpret_cast<uint8_t *>(M.st[2]);
+    uint8_t *y = reinterpret_cast<uint8_t *>(M.st[3]), *x2 = reinterpret_cast<uint8_t *>(M.st[4]), *y2 = reinterpret_cast<uint8_t *>(M.st[5]);
     int32_t *H = M.H;
     // seed roles: lanes 0..5 write one array each when a column enters the band; lanes 0..2 write the left neighbour of st
-    int8_t *const enter_arr = M.st[lane < 6 ? lane : 0];
-    const int enter_val = lane < 4 ? -qe : -qe2;
-    int8_t *const left_arr = lane == 0 ? x : lane == 1 ? x2 : v;
+    uint8_t *const enter_arr = reinterpret_cast<uint8_t *>(M.st[lane < 6 ? lane : 0]);
+    const int enter_val = lane < 2 ? FB - qe : 0;                // u, v = -q-e; x, y = -q-e and x2, y2 = -q2-e2 are 0 in the offset form
+    uint8_t *const left_arr = lane == 0 ? x : lane == 1 ? x2 : v;
     int pst = -1, pen = -1, t_loaded = 0, q_loaded = 0;
     int32_t ez_max = 0, ez_max_t = -1, ez_max_q = -1, ez_mqe = KSW_NEG_INF, ez_mqe_t = -1, ez_mte = KSW_NEG_INF, ez_mte_q = -1;
     int32_t ez_score = KSW_NEG_INF, zdropped = 0, H0 = 0, last_H0_t = 0;
@@ -122,10 +129,10 @@ __device__ bool warp_extd2_vec(const Opt &o, const DpTask &T, DpRes &R, VecSmem 
         if (bail) break;
         // ---- seeds: entering column, top boundary, left neighbour of the first cell ----
         const int bnd = r == 0 ? -q - e : r < LT ? -e : r == LT ? LD : -e2;
-        if (en > pen && lane < 6) enter_arr[vwr(en)] = (int8_t)enter_val;           // u,v,x,y = -q-e; x2,y2 = -q2-e2
-        if (en == r && lane == 0) u[vwr(r)] = (int8_t)bnd;                            // (en == r implies en > pen: y, y2 are already seeded)
+        if (en > pen && lane < 6) enter_arr[vwr(en)] = (uint8_t)enter_val;          // u,v,x,y = -q-e; x2,y2 = -q2-e2
+        if (en == r && lane == 0) u[vwr(r)] = (uint8_t)(bnd + FB);                    // (en == r implies en > pen: y, y2 are already seeded)
         if ((st == 0 || !(st - 1 >= pst && st - 1 <= pen)) && lane < 3)
-            left_arr[vwr(st - 1)] = (int8_t)(lane == 0 ? -qe : lane == 1 ? -qe2 : st == 0 ? bnd : -qe);
+            left_arr[vwr(st - 1)] = (uint8_t)(lane < 2 ? 0 : FB + (st == 0 ? bnd : -qe));
         int32_t Hp = 0;
         if (!approx && r > 0) Hp = H[vwr(en > 0 ? en - 1 : 0)];                       // last row's H next to (or at) the entering end
         __syncwarp();
@@ -159,30 +166,29 @@ __device__ bool warp_extd2_vec(const Opt &o, const DpTask &T, DpRes &R, VecSmem 
                 uint32_t nU[2], nV[2], nX[2], nY[2], nX2[2], nY2[2], fO[2], fA[2], fB[2], fA2[2], fX[2], fY[2], fX2[2], fY2[2];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const uint32_t sxl = h ? 0xB3A2 : 0x9180;
-                    const uint32_t up_u = prmt(Wu, Wu, sxl), up_y = prmt(Wy, Wy, sxl), up_y2 = prmt(Wy2, Wy2, sxl);
-                    const uint32_t Lv = prmt(Lv4, Lv4, sxl), Lx = prmt(Lx4, Lx4, sxl), Lx2 = prmt(Lx24, Lx24, sxl);
+                    const uint32_t sxl = h ? 0x4342 : 0x4140;          // bytes (0, 1) or (2, 3), zero-extended to the two halves
+                    const uint32_t up_u = prmt(Wu, 0u, sxl), up_y = prmt(Wy, 0u, sxl), up_y2 = prmt(Wy2, 0u, sxl);
+                    const uint32_t Lv = prmt(Lv4, 0u, sxl), Lx = prmt(Lx4, 0u, sxl), Lx2 = prmt(Lx24, 0u, sxl);
                     const uint32_t S = h ? SS.y : SS.x;
-                    const uint32_t A = __vadd2(Lx, Lv), A2 = __vadd2(Lx2, Lv), B = __vadd2(up_y, up_u), B2 = __vadd2(up_y2, up_u);
+                    const uint32_t A = Lx + Lv + CA, A2 = Lx2 + Lv + CA2, B = up_y + up_u + CA, B2 = up_y2 + up_u + CA2;
                     uint32_t Z = __vimax3_s16x2(S, A, B);
                     Z = __vimax3_s16x2(Z, A2, B2);
-                    const uint32_t DA = __vsub2(A, Z), DB = __vsub2(B, Z), DA2 = __vsub2(A2, Z), DB2 = __vsub2(B2, Z);
-                    fO[h] = __vsub2(RIGHT ? B2 : S, Z);          // the one candidate the two tie-break orders do not share
-                    nU[h] = __vsub2(Z, Lv); nV[h] = __vsub2(Z, up_u);
-                    nX[h] = __viaddmax_s16x2(DA, NE1, NQE1); nY[h] = __viaddmax_s16x2(DB, NE1, NQE1);
-                    nX2[h] = __viaddmax_s16x2(DA2, NE2, NQE2); nY2[h] = __viaddmax_s16x2(DB2, NE2, NQE2);
+                    const uint32_t NZ = FSUB(DK, Z);                   // t + NZ = t - z + 0x8000 per half: top bit set when t is the maximum
+                    const uint32_t DA = FADD(A, NZ), DB = FADD(B, NZ), DA2 = FADD(A2, NZ), DB2 = FADD(B2, NZ);
+                    fO[h] = FADD(RIGHT ? B2 : S, NZ);          // the one candidate the two tie-break orders do not share
+                    nU[h] = FSUB(Z, Lv); nV[h] = FSUB(Z, up_u);
+                    // 0x8000 + max(t - z + q, 0): the low byte is the new gap state in the offset form
+                    nX[h] = __viaddmax_u16x2(DA, Q1, DK); nY[h] = __viaddmax_u16x2(DB, Q1, DK);
+                    nX2[h] = __viaddmax_u16x2(DA2, Q2, DK); nY2[h] = __viaddmax_u16x2(DB2, Q2, DK);
                     fA[h] = DA; fB[h] = DB; fA2[h] = DA2;
-                    fX[h] = __vadd2(DA, QC1); fY[h] = __vadd2(DB, QC1); fX2[h] = __vadd2(DA2, QC2); fY2[h] = __vadd2(DB2, QC2);
+                    fX[h] = FADD(DA, QC1); fY[h] = FADD(DB, QC1); fX2[h] = FADD(DA2, QC2); fY2[h] = FADD(DB2, QC2);   // top bit set when the gap continues
                 }
-                // 8 sign bits per cell: one PRMT per flag gathers the four cells of the group (bytes = columns c0..c0+3)
-                uint32_t dw = prmt(fO[0], fO[1], 0xFDB9) & 0x01010101u;
-                dw |= prmt(fA[0], fA[1], 0xFDB9) & 0x02020202u;
-                dw |= prmt(fB[0], fB[1], 0xFDB9) & 0x04040404u;
-                dw |= prmt(fA2[0], fA2[1], 0xFDB9) & 0x08080808u;
-                dw |= prmt(fX[0], fX[1], 0xFDB9) & 0x10101010u;
-                dw |= prmt(fY[0], fY[1], 0xFDB9) & 0x20202020u;
-                dw |= prmt(fX2[0], fX2[1], 0xFDB9) & 0x40404040u;
-                dw |= prmt(fY2[0], fY2[1], 0xFDB9) & 0x80808080u;
+                // 8 top bits per cell, complemented: one PRMT per flag gathers the four cells of the group (bytes = columns c0..c0+3),
+                // a tree of multiply-adds and one multiply put flag f on bit f (k_fill.cuh)
+                uint32_t dw = flag_sum(prmt(fO[0], fO[1], 0xFDB9), prmt(fA[0], fA[1], 0xFDB9), prmt(fB[0], fB[1], 0xFDB9), prmt(fA2[0], fA2[1], 0xFDB9),
+                                       prmt(fX[0], fX[1], 0xFDB9), prmt(fY[0], fY[1], 0xFDB9), prmt(fX2[0], fX2[1], 0xFDB9), prmt(fY2[0], fY2[1], 0xFDB9),
+                                       TWO, FOUR, SIXTEEN);
+                dw = imad(dw, K01, 0xffffffffu);
                 // Whole words are written back: cells outside [st, en] hold garbage, which is never read (a column is
                 // re-seeded when it enters the band, and the left neighbour of st is either last row's cell or a constant).
 #define PACK8(a) __byte_perm((a)[0], (a)[1], 0x6420)
@@ -202,7 +208,7 @@ __device__ bool warp_extd2_vec(const Opt &o, const DpTask &T, DpRes &R, VecSmem 
                     const int d = c0 - st;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const int32_t vk = (k & 1) ? (int32_t)nV[k >> 1] >> 16 : (int32_t)(int16_t)(nV[k >> 1] & 0xffffu);
+                        const int32_t vk = (int32_t)((k & 1) ? nV[k >> 1] >> 16 : nV[k >> 1] & 0xffffu) - FB;
                         const int rel = d + k;
                         if ((unsigned)rel < n_upd) hv[k] += vk;
                         // rank code 2046 - cls * 256 - idx with cls = (k - st) & 3 and idx = g + ((k - st) >> 2): kc[k] is uniform over the row
@@ -217,7 +223,7 @@ __device__ bool warp_extd2_vec(const Opt &o, const DpTask &T, DpRes &R, VecSmem 
         if (!approx) {
             int32_t max_H, max_t, Hen, Hst;
             if (r > 0) {
-                Hen = Hp + (en > 0 ? (int32_t)u[vwr(en)] : (int32_t)v[vwr(0)]);
+                Hen = Hp + (en > 0 ? (int32_t)u[vwr(en)] : (int32_t)v[vwr(0)]) - FB;
                 if (lane < 3 && en1 + lane < en) {                    // the scalar tail of the reference's row scan
                     const int32_t key = H[vwr(en1 + lane)] * 2048 + (2046 - 1024 - lane);
                     if (key > kmax) kmax = key;
@@ -234,7 +240,7 @@ __device__ bool warp_extd2_vec(const Opt &o, const DpTask &T, DpRes &R, VecSmem 
                 Hst = st == en ? Hen : H[vwr(st)];
                 if (lane == 0) H[vwr(en)] = Hen;
             } else {
-                Hen = Hst = (int32_t)v[0] - qe;
+                Hen = Hst = (int32_t)v[0] - FB - qe;
                 if (lane == 0) H[0] = Hen;
                 max_H = Hen, max_t = 0;
             }
@@ -252,11 +258,11 @@ __device__ bool warp_extd2_vec(const Opt &o, const DpTask &T, DpRes &R, VecSmem 
         } else {
             if (r > 0) {
                 if (last_H0_t >= st && last_H0_t <= en && last_H0_t + 1 >= st && last_H0_t + 1 <= en) {
-                    int d0 = v[vwr(last_H0_t)], d1 = u[vwr(last_H0_t + 1)];
+                    int d0 = (int)v[vwr(last_H0_t)] - FB, d1 = (int)u[vwr(last_H0_t + 1)] - FB;
                     if (d0 > d1) H0 += d0; else H0 += d1, ++last_H0_t;
-                } else if (last_H0_t >= st && last_H0_t <= en) H0 += v[vwr(last_H0_t)];
-                else ++last_H0_t, H0 += u[vwr(last_H0_t)];
-            } else H0 = (int32_t)v[0] - qe, last_H0_t = 0;
+                } else if (last_H0_t >= st && last_H0_t <= en) H0 += (int)v[vwr(last_H0_t)] - FB;
+                else ++last_H0_t, H0 += (int)u[vwr(last_H0_t)] - FB;
+            } else H0 = (int32_t)v[0] - FB - qe, last_H0_t = 0;
             if (r == nr - 1 && en == tlen - 1) ez_score = H0;
         }
         pst = st, pen = en;

@@ -32,6 +32,9 @@ namespace telr {
 #define TELR_FILL_FC12 1
 #endif
 constexpr int FC_MAX = 12;            // columns per lane: 8 (256-column passes) or 12 (384-column passes)
+#ifndef TELR_FILL_CADD
+#define TELR_FILL_CADD 1              // 1: two-input adds left to the compiler's pipe choice (mostly IMAD.IADD); 0: forced IMADs (1 % slower)
+#endif
 constexpr int FB = 60;                // offset of the stored differences (see "Number representation" above)
 
 // prmt.b32 in default mode: selector nibble bit 3 replicates the sign of the selected byte (__byte_perm drops that bit)
@@ -52,6 +55,20 @@ __device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t m, uint32_t c)
 }
 // 1 that the compiler cannot see through (gridDim.z of every launch in this library)
 __device__ __forceinline__ uint32_t opaque_one() { uint32_t d; asm volatile("mov.u32 %0, %%nctaid.z;" : "=r"(d)); return d; }
+// sum_f r[f] 2^f as a depth-3 tree of IMADs (a Horner chain is 7 dependent operations)
+__device__ __forceinline__ uint32_t flag_sum(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, uint32_t r4, uint32_t r5, uint32_t r6, uint32_t r7,
+                                             uint32_t TWO, uint32_t FOUR, uint32_t SIXTEEN)
+{
+    const uint32_t a = imad(r1, TWO, r0), b = imad(r3, TWO, r2), c = imad(r5, TWO, r4), d = imad(r7, TWO, r6);
+    return imad(imad(d, FOUR, c), SIXTEEN, imad(b, FOUR, a));
+}
+#if TELR_FILL_CADD
+#define FADD(a, b) ((a) + (b))
+#define FSUB(a, b) ((a) - (b))
+#else
+#define FADD(a, b) imad((a), ONE, (b))
+#define FSUB(a, b) imad((b), MONE, (a))
+#endif
 __device__ __forceinline__ uint32_t pk2(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
 __device__ __forceinline__ uint32_t pk1(int v) { return pk2(v, v); }
 __device__ __forceinline__ int lo16(uint32_t v) { return (int)(int16_t)(v & 0xffffu); }
@@ -111,7 +128,7 @@ __device__ void warp_fill_fwd(const Opt &o, const DpTask &T, DpRes &R, uint8_t *
     const uint32_t X0 = pk1(BX - qe), X20 = pk1(BX2 - qe2);                     // a gap state that has just been reset (= XFLOOR)
     // score table of one target base: byte c = score against query base c, + 2 FB (a positive int8)
     const uint32_t TS_MIS = 0x01010101u * (uint32_t)(2 * FB - o.b), TS_FLIP = (uint32_t)(2 * FB + o.a) ^ (uint32_t)(2 * FB - o.b);
-    const uint32_t ONE = opaque_one(), MONE = 0u - ONE, TWO = ONE + ONE, K01 = 0x01010101u * ONE;
+    const uint32_t ONE = opaque_one(), MONE = 0u - ONE, TWO = ONE + ONE, FOUR = TWO + TWO, SIXTEEN = FOUR * FOUR, K01 = 0x01010101u * ONE;
     const int stride = fill_stride(tlen);
     const int npairs = (qlen + 1) >> 1, npass = (tlen + FW - 1) / FW;
     int usum = 0;
@@ -131,6 +148,8 @@ __device__ void warp_fill_fwd(const Opt &o, const DpTask &T, DpRes &R, uint8_t *
             Uu[k] = pk2(FB, BNDF(r)); Uy[k] = X0; Uy2[k] = X20;
         }
         uint32_t inV = 0, inX = 0, inX2 = 0, Ufirst = 0;
+        // query bases of the lane's next row pair (q[j] | q[j+1] << 8), loaded one step ahead of their use
+        const uint32_t BND_TAIL = pk1(FB - e2);      // boundary differences beyond row LT
         const bool last_pass = pass == npass - 1;
         const int nlive = tlen - pass * FW >= FW ? 32 : (tlen - pass * FW + FC - 1) / FC;      // lanes that own columns in this pass
         for (int s = 0; s < npairs + nlive - 1; ++s) {
@@ -139,7 +158,7 @@ __device__ void warp_fill_fwd(const Opt &o, const DpTask &T, DpRes &R, uint8_t *
             if (lane == 0 && s < npairs) {
                 const int j = 2 * s;
                 if (pass == 0) {
-                    inV = pk2(BNDF(j), BNDF(j + 1)); inX = X0; inX2 = X20;
+                    inV = j > LT ? BND_TAIL : pk2(BNDF(j), BNDF(j + 1)); inX = X0; inX2 = X20;
                 } else { inV = bnd[3 * s]; inX = bnd[3 * s + 1]; inX2 = bnd[3 * s + 2]; }
             }
             uint32_t outV = 0, outX = 0, outX2 = 0;
@@ -165,9 +184,9 @@ __device__ void warp_fill_fwd(const Opt &o, const DpTask &T, DpRes &R, uint8_t *
                     uint32_t Z = __vimax3_s16x2(S, A, B);
                     Z = __vimax3_s16x2(Z, A2, B2);
                     // t - z + 0x8000 per half: bit 15 set exactly when t is the maximum (two-input adds: FMA pipe)
-                    const uint32_t NZ = imad(Z, MONE, DK);
-                    const uint32_t DS = imad(S, ONE, NZ), DA = imad(A, ONE, NZ), DB = imad(B, ONE, NZ), DA2 = imad(A2, ONE, NZ), DB2 = imad(B2, ONE, NZ);
-                    const uint32_t nu = imad(Lv, MONE, Z), nv = imad(up_u, MONE, Z);
+                    const uint32_t NZ = FSUB(DK, Z);
+                    const uint32_t DS = FADD(S, NZ), DA = FADD(A, NZ), DB = FADD(B, NZ), DA2 = FADD(A2, NZ), DB2 = FADD(B2, NZ);
+                    const uint32_t nu = FSUB(Z, Lv), nv = FSUB(Z, up_u);
                     // max(t - z - e, -(q + e)) in the offset form: bit 15 set exactly when the gap continues
                     const uint32_t nx = __viaddmax_u16x2(DA, QM1, XFLOOR), ny = __viaddmax_u16x2(DB, QM1, XFLOOR);
                     const uint32_t nx2 = __viaddmax_u16x2(DA2, Q2M1, XFLOOR), ny2 = __viaddmax_u16x2(DB2, Q2M1, XFLOOR);
@@ -175,7 +194,7 @@ __device__ void warp_fill_fwd(const Opt &o, const DpTask &T, DpRes &R, uint8_t *
                     // "does not continue").  Two iterations are gathered together: one PRMT per flag replicates the top bits of
                     // (k lo, k hi, k+1 lo, k+1 hi) into the bytes r_f of a word (0x00 / 0xff).  sum_f r_f 2^f = 255 T (mod 2^32),
                     // T = the word of top-bit bytes (each 0xff byte is 256 - 1: the carries telescope), so the flag word
-                    // ~T = -1 - 255 T / 255 = (sum_f r_f 2^f) * 0x01010101 - 1: Horner steps and one multiply, all IMADs.
+                    // ~T = -1 - 255 T / 255 = (sum_f r_f 2^f) * 0x01010101 - 1: a tree of multiply-adds and one multiply, all IMADs.
                     if (k == FC) {                  // last iteration (even): only its hi cell (FC-1, j+1) exists
                         uint32_t acc = ~prmt(DS, DA, 0xFDB9) & 0x02020101u;
                         acc |= ~prmt(DB, DA2, 0xFDB9) & 0x08080404u;
@@ -185,14 +204,9 @@ __device__ void warp_fill_fwd(const Opt &o, const DpTask &T, DpRes &R, uint8_t *
                     } else if (!(k & 1)) {
                         eDS = DS; eDA = DA; eDB = DB; eDA2 = DA2; eNX = nx; eNY = ny; eNX2 = nx2; eNY2 = ny2;
                     } else {
-                        uint32_t acc = prmt(eNY2, ny2, 0xFDB9);
-                        acc = imad(acc, TWO, prmt(eNX2, nx2, 0xFDB9));
-                        acc = imad(acc, TWO, prmt(eNY, ny, 0xFDB9));
-                        acc = imad(acc, TWO, prmt(eNX, nx, 0xFDB9));
-                        acc = imad(acc, TWO, prmt(eDA2, DA2, 0xFDB9));
-                        acc = imad(acc, TWO, prmt(eDB, DB, 0xFDB9));
-                        acc = imad(acc, TWO, prmt(eDA, DA, 0xFDB9));
-                        acc = imad(acc, TWO, prmt(eDS, DS, 0xFDB9));
+                        const uint32_t acc = flag_sum(prmt(eDS, DS, 0xFDB9), prmt(eDA, DA, 0xFDB9), prmt(eDB, DB, 0xFDB9), prmt(eDA2, DA2, 0xFDB9),
+                                                      prmt(eNX, nx, 0xFDB9), prmt(eNY, ny, 0xFDB9), prmt(eNX2, nx2, 0xFDB9), prmt(eNY2, ny2, 0xFDB9),
+                                                      TWO, FOUR, SIXTEEN);
                         W[k >> 1] = imad(acc, K01, 0xffffffffu);
                     }
                     if (k >= 1) { Uu[k - 1] = nu; Uy[k - 1] = ny; Uy2[k - 1] = ny2; }      // hi halves: cell (k-1, j+1) = up input of the next row pair
@@ -293,13 +307,25 @@ __device__ void fill_traceback(const DpTask &T, DpRes &R, const uint8_t *dir, ui
     while (i >= 0 && j >= 0) {
         const int c0 = (i - (TBW - 8)) > 0 ? ((i - (TBW - 8)) & ~7) : 0;      // window columns [c0, c0+64), rows [jtop, j0]
         const int j0 = j, jtop = j - (TBR - 1) > 0 ? j - (TBR - 1) : 0;
-        for (int rr = lane; rr < TBR; rr += 32) {
-            const int row = j0 - rr;
-            if (row >= 0) {
+        {   // Every load first, then the stores: through generic pointers the compiler must assume that a store to the window may
+            // alias the next load, and would wait for each load in turn (16 dependent L2 round trips per window and lane).
+            static_assert(TBR <= 64, "two window rows per lane");
+            uint2 t[2][TBW / 8];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int rr = lane + 32 * h, row = j0 - rr;
                 const uint8_t *src = dir + (int64_t)row * stride + c0;
 #pragma unroll
                 for (int k = 0; k < TBW / 8; ++k)
-                    if (c0 + 8 * k < stride) tb.w[rr][k] = *reinterpret_cast<const uint2 *>(src + 8 * k);
+                    t[h][k] = rr < TBR && row >= 0 && c0 + 8 * k < stride ? *reinterpret_cast<const uint2 *>(src + 8 * k) : make_uint2(0u, 0u);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int rr = lane + 32 * h;
+                if (rr < TBR) {
+#pragma unroll
+                    for (int k = 0; k < TBW / 8; ++k) tb.w[rr][k] = t[h][k];
+                }
             }
         }
         __syncwarp();
