@@ -65,11 +65,12 @@ struct telr_af_ctx {
     DevBuf b_order, b_wflag, b_woff;      // LPT order of the chunk's problems, work-list filter
     DevBuf b_tfirst, b_tcnt, b_toff, b_tmpx, b_tmpy;     // tile sketch: first tile per sequence, per-tile counts/offsets, per-tile slots
     int sketch_tiles = 1;
-    // TELR_AL_QUEUE=1 selects the role-specialised alignment kernel k_al_queue (ext_per8 / wide_per8: eighths of the SMs that start in the
-    // extension role / the 12-column gap-fill role).  Measured (profiles/README.md, round 2): it removes the instruction-cache penalty of extra
-    // loop bodies as designed, but end to end it is within +-1.5 % of k_al_fused on map-ont and 18 % slower on map-pb / map-hifi, so the
-    // fused kernel stays the default.
-    int al_queue = 0, ext_per8 = 2, wide_per8 = 2;
+    // The alignment stage has two kernels: k_al_fused (one warp owns one problem from start to end) and the role-specialised k_al_queue
+    // (SM roles + device-wide task rings; ext_per8 / wide_per8: eighths of the SMs that start in the extension role / the 12-column gap-fill
+    // role).  Measured with the offset-form DP loops (profiles/README.md, round 2): k_al_queue is 5.5 % faster on map-ont (gap fills dominate,
+    // one loop per SM fits the instruction cache) and 15-25 % slower on map-pb / map-hifi (extensions dominate, the rings add latency), so
+    // the default (-1) picks it for map-ont only.  TELR_AL_QUEUE=0/1 forces one of them.
+    int al_queue = -1, ext_per8 = 2, wide_per8 = 2;
     int opt_bw = 0, opt_bw_long = 0;     // telr_af_set_option overrides (0 = preset value)
     DevBuf b_qring, b_qstate;
     int al_blocks = AL_BLOCKS_PER_SM;    // resident k_al_fused CTAs per SM this context asks for (fewer leaves room for a second context's kernels)
@@ -530,7 +531,7 @@ static int run_chunk(telr_af_ctx *ctx, const Opt &o, const telr_af_batch *db /* 
         CK(cudaMemsetAsync(ctx->b_rc.p, 0, 1024, st));
         { ++ctx->launches; k_al_offsets<<<tb, 128, 0, st>>>(aa, ctx->b_aloff.as<int64_t>()); }
         { ++ctx->launches; k_al_init<<<tb, 128, 0, st>>>(aa); }
-        if (ctx->al_queue) {
+        if (ctx->al_queue < 0 ? db->preset == TELR_PRESET_MAP_ONT : ctx->al_queue > 0) {
             aa.q_cap = n_work + 1; aa.ext_per8 = ctx->ext_per8; aa.wide_per8 = ctx->wide_per8;
             ENS(ctx->b_qring, (size_t)AQ_ROLES * aa.q_cap * 4); ENS(ctx->b_qstate, (AQ_SLOTS + AQ_MAX_SM) * 4);
             CK(cudaMemsetAsync(ctx->b_qring.p, 0, (size_t)AQ_ROLES * aa.q_cap * 4, st));
@@ -1070,7 +1071,7 @@ extern "C" int telr_af_dp(telr_af_ctx *ctx, int32_t preset, int32_t n_tasks, con
     int maxQ = 0, maxT = 0;
     for (int i = 0; i < n_tasks; ++i) { maxQ = std::max(maxQ, tasks[i].qlen); maxT = std::max(maxT, tasks[i].tlen); }
     A.maxQ = (maxQ + 64) & ~15; A.maxT = (maxT + 64) & ~15; A.dir_cap = ctx->dir_cap;
-    A.use_fast = ctx->use_fast ? (ctx->al_queue && ctx->wide_per8 > 0 ? 2 : 1) : 0; A.use_vec = ctx->use_vec;
+    A.use_fast = ctx->use_fast ? (ctx->al_queue > 0 && ctx->wide_per8 > 0 ? 2 : 1) : 0; A.use_vec = ctx->use_vec;
     A.stride = ((size_t)A.maxT * (6 + 4 + 24) + (size_t)(A.maxQ + A.maxT) * 4 + (size_t)A.maxQ * 6 + 512 + (size_t)A.dir_cap + 255) & ~(size_t)255;
     const int grid = std::max(1, std::min((n_tasks + AL_WARPS - 1) / AL_WARPS, ctx->sm_count * AL_BLOCKS_PER_SM));
     ENS(ctx->b_alws, A.stride * (size_t)grid * AL_WARPS);

@@ -264,11 +264,13 @@ def test_full_pipeline_matches_oracle(ctx, cfg, n, kw):
     assert r.c.dp_cells == ro.c.dp_cells and r.c.n_anchors == ro.c.n_anchors
 
 
-@pytest.mark.parametrize("cfg,n,env", [("ont_3k_50x", 8, {"TELR_AL_QUEUE": "1"}), ("clr_3k_40x", 5, {"TELR_AL_QUEUE": "1", "TELR_AL_EXT8": "5", "TELR_AL_WIDE8": "0"}),
+@pytest.mark.parametrize("cfg,n,env", [("ont_3k_50x", 8, {"TELR_AL_QUEUE": "0"}), ("ont_3k_50x", 8, {"TELR_AL_QUEUE": "1", "TELR_AL_EXT8": "3", "TELR_AL_WIDE8": "1"}),
+                                       ("clr_3k_40x", 5, {"TELR_AL_QUEUE": "1", "TELR_AL_EXT8": "5", "TELR_AL_WIDE8": "0"}),
                                        ("hifi_3k_40x", 5, {"TELR_AL_QUEUE": "1", "TELR_AL_EXT8": "0", "TELR_AL_WIDE8": "4"})])
-def test_role_specialised_alignment_kernel_matches_oracle(built, monkeypatch, cfg, n, env):
-    """k_al_queue (SM roles + device-wide task rings, optional: TELR_AL_QUEUE=1) gives the results of the default fused kernel:
-    every problem migrates between warps through global memory, the 12-column fill instance runs in its own role."""
+def test_both_alignment_kernels_match_oracle(built, monkeypatch, cfg, n, env):
+    """The alignment stage has two kernels and a per-preset default (k_al_queue — SM roles + device-wide task rings, every problem
+    migrating between warps through global memory, the 12-column fill instance in its own role — for map-ont, k_al_fused for map-pb and
+    map-hifi).  The rest of the suite runs the defaults; this test forces the other kernel of each preset and non-default role splits."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     b = synth.generate(cfg, 20, n)
