@@ -40,7 +40,7 @@ WORKLOAD = os.environ.get("TELR_BENCH_CONFIG", "ont_30k_30x")     # BASELINE.jso
 METRIC = "candidate loci/sec (stage-4 AF)"                         # GCUPS of the base-level DP is reported in `gcups` / `roofline`
 DTYPE = "int16x2 (integer DP), fp32 chain penalty, fp64 AF"
 OPS_PER_CELL = 30.0        # integer lane-ops per DP cell of the two-piece affine recurrence with traceback
-DRAM_BYTES_PER_CELL = float(os.environ.get("TELR_DRAM_B_PER_CELL", "1.33"))   # dram bytes of the DP kernels / DP cells, ncu --set full capture (profiles/)
+DRAM_BYTES_PER_CELL = float(os.environ.get("TELR_DRAM_B_PER_CELL", "1.47"))   # dram bytes of the DP kernels / DP cells, ncu --set full capture (profiles/)
 BUDGET_S = float(os.environ.get("TELR_BENCH_BUDGET_S", "420"))    # the e2e legs shrink their step count to keep the whole run inside this
 
 
