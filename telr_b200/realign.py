@@ -9,7 +9,8 @@
 
 Record layout follows minimap2 format.c (mm_write_sam3 / mm_write_paf3): FLAG 0x10 / 0x100 / 0x800, POS = rs + 1, soft clips on
 the primary line and hard clips on supplementary and secondary lines, SEQ reverse-complemented for reverse hits, `*` for
-secondary lines, tags NM ms AS nn tp cm s1 s2 de.  Not written: rl:i, SA:Z (stated in DESIGN.md).
+secondary lines, tags NM ms AS nn tp cm s1 s2 de, and SA:Z on the non-secondary lines of a read that has several of them
+(minimap2's abbreviated form: rname,pos,strand,clip/M/I|D/clip,mapq,NM;).  Not written: rl:i (stated in DESIGN.md).
 """
 from __future__ import annotations
 
@@ -62,7 +63,20 @@ def _aux(a, cig, tp) -> bytes:
     return out + b"def" + struct.pack("<f", _event_de(a, cig))
 
 
-def strand_records(batch: Batch, result, locus: int, strand: int, read_names):
+def _sa_entry(a, qlen: int, ref_name: str) -> str:
+    """One SA:Z element the way format.c mm_write_sam3 abbreviates it: clips as S, one M run, the length difference as I or D."""
+    qs, qe, rs, re_, rev = int(a["qs"]), int(a["qe"]), int(a["rs"]), int(a["re"]), bool(a["rev"])
+    l_i = l_d = 0
+    if qe - qs < re_ - rs:
+        l_m, l_d = qe - qs, (re_ - rs) - (qe - qs)
+    else:
+        l_m, l_i = re_ - rs, (qe - qs) - (re_ - rs)
+    c5, c3 = (qlen - qe, qs) if rev else (qs, qlen - qe)
+    cg = "".join(f"{n}{op}" for n, op in ((c5, "S"), (l_m, "M"), (l_i, "I"), (l_d, "D"), (c3, "S")) if n)
+    return f"{ref_name},{rs + 1},{'-' if rev else '+'},{cg},{int(a['mapq'])},{int(a['blen']) - int(a['mlen']) + int(a['n_ambi'])};"
+
+
+def strand_records(batch: Batch, result, locus: int, strand: int, read_names, ref_name: str = "ctg1"):
     """SAM records (dicts) of the reads of one locus against one contig strand, in minimap2's output order."""
     rb, re_ = int(batch.locus_read_begin[locus]), int(batch.locus_read_begin[locus + 1])
     al = result.alns
@@ -80,6 +94,7 @@ def strand_records(batch: Batch, result, locus: int, strand: int, read_names):
             recs.append(dict(qname=name, flag=4, tid=-1, pos=-1, mapq=0, cigar=np.zeros(0, np.uint32), seq=fw, aux=b""))
             continue
         rc = None
+        chimeric = [i for i in by_read[r] if not int(al["flag"][i]) & 0x100]       # primary + supplementary lines (parent == id)
         for i in by_read[r]:
             a = al[i]
             cig = result.cigar_of(i)
@@ -93,7 +108,10 @@ def strand_records(batch: Batch, result, locus: int, strand: int, read_names):
                 seq = s[c5: len(s) - c3]                    # supplementary: hard-clipped
             else:
                 seq = s
-            recs.append(dict(qname=name, flag=flag, tid=0, pos=pos, mapq=mapq, cigar=words, seq=seq, aux=_aux(a, cig, tp)))
+            aux = _aux(a, cig, tp)
+            if len(chimeric) > 1 and not flag & 0x100:
+                aux += b"SAZ" + "".join(_sa_entry(al[k], qlen, ref_name) for k in chimeric if k != i).encode() + b"\0"
+            recs.append(dict(qname=name, flag=flag, tid=0, pos=pos, mapq=mapq, cigar=words, seq=seq, aux=aux))
     return recs
 
 
@@ -127,7 +145,7 @@ def write_realign_bams(batch: Batch, result, read_names, prefixes, contig_names=
         cname = contig_names[l] if contig_names else "ctg1"
         for strand, sfx in ((0, ""), (1, ".revcomp")):
             p = prefixes[l] + sfx + ".realign.sort.bam"
-            write_bam(p, cname, L, strand_records(batch, result, l, strand, read_names), level,
+            write_bam(p, cname, L, strand_records(batch, result, l, strand, read_names, cname), level,
                       "@PG\tID:telr_b200\tPN:telr_b200\tCL:minimap2 -a -x %s\n" % {0: "map-ont", 1: "map-pb", 2: "map-hifi"}.get(batch.preset, "?"))
             paths.append(p)
     return paths
@@ -251,7 +269,7 @@ def align_to_bam(contig_name: str, contig: bytes, reads, preset: str, bam_path: 
         ctx.set_option("bw", 0)
         if own:
             ctx.close()
-    recs = strand_records(b, r, 0, 0, names)
+    recs = strand_records(b, r, 0, 0, names, contig_name)
     write_bam(bam_path, contig_name, len(contig), recs, header_extra="@PG\tID:telr_b200\tPN:telr_b200\tCL:minimap2 -ax %s%s\n" % (preset, " -r%d" % bw if bw else ""))
     return len(recs)
 

@@ -429,6 +429,23 @@ def test_realign_bam_records_reproduce_the_depth(built, tmp_path):
                     assert ((op != 5).all() if not r["flag"] & 0x800 else (op != 4).all())
                 assert {"NM", "ms", "AS", "nn", "tp", "cm", "s1", "de"} <= set(r["tags"]) and 0 <= r["mapq"] <= 60
                 assert r["tags"]["tp"] == ("S" if r["flag"] & 0x100 else r["tags"]["tp"]) and ("s2" in r["tags"]) == (not r["flag"] & 0x100)
+            # SA:Z: every non-secondary line of a read with several of them lists the others (minimap2's abbreviated CIGAR)
+            by_name = {}
+            for r in mapped:
+                if not r["flag"] & 0x100:
+                    by_name.setdefault(r["qname"], []).append(r)
+            for name, rs_ in by_name.items():
+                for r in rs_:
+                    assert ("SA" in r["tags"]) == (len(rs_) > 1)
+                    if len(rs_) > 1:
+                        ents = [e.split(",") for e in r["tags"]["SA"].rstrip(";").split(";")]
+                        others = [o for o in rs_ if o is not r]
+                        assert sorted((int(e[1]) - 1, e[2], int(e[4]), int(e[5])) for e in ents) == \
+                            sorted((o["pos"], "-" if o["flag"] & 0x10 else "+", o["mapq"], o["tags"]["NM"]) for o in others)
+                        assert all(e[0] == "ctg1" for e in ents)
+                        for e in ents:     # clips + M + I of the abbreviated CIGAR = read length
+                            parts = re.findall(r"(\d+)([SMID])", e[3])
+                            assert sum(int(n) for n, op in parts if op in "SMI") == int(b.read_len[int(name[4:])])
             # primary SEQ is the read (reverse-complemented for reverse hits)
             prim = next(r for r in mapped if not r["flag"] & 0x900)
             rd = int(prim["qname"][4:])
