@@ -7,21 +7,24 @@
 // Inside a lane-step the two rows are swept left to right with the second row one column behind the first, so the
 // two cells handled together are independent and sit in the two 16-bit halves of every register:
 //     lo half: cell (column k,   row j)      hi half: cell (column k-1, row j+1)
-// The difference recurrence (u,v,x,y,x2,y2) then runs on packed 16x2 integer SIMD ops.  Direction information is
-// 8 sign bits per cell (which of s,a,b,a2 is below the maximum; which gap states do not continue) gathered with
-// four PRMTs in sign-replicate mode; one 8-byte store per row per lane writes them row-major.
+// Direction information is 8 bits per cell (which of s,a,b,a2 is below the maximum; which gap states do not continue);
+// one 8-byte store per row per lane writes them row-major.
 // Left-to-right values (v,x,x2) travel between lanes by shuffle, between 256-column passes through a small
 // per-warp boundary array.  No tensor cores: this is not a dense contraction.
 //
-// Number representation (round 2).  sm_100a has no packed 16x2 subtract (`__vsub2` = LOP3 + 2 x VIADD.16x2), and the recurrence
-// subtracts seven times per cell pair.  Every stored half-word therefore carries an offset that keeps it NON-NEGATIVE, so that a
-// plain 32-bit IADD3 (three inputs, free negation) acts on the two halves independently — no borrow ever crosses bit 16:
+// Number representation (round 2, "offset form").  The measured issue budget of an SM sub-partition is 0.5 instructions per clock on
+// the ALU pipe (PRMT, LOP3, packed min/max, IADD3) and 0.5 on the FMA pipe (IMAD, IMAD.IADD), ~0.95 together
+// (profiles/ubench/pipes2.cu); sm_100a has no packed 16x2 subtract (`__vsub2` = LOP3 + 2 x VIADD.16x2) and the recurrence subtracts
+// seven times per cell pair.  Every stored half-word therefore carries an offset that keeps it NON-NEGATIVE, so that plain 32-bit
+// adds and subtracts act on the two halves independently — no borrow ever crosses bit 16:
 //     u, v         + FB                      (FB = 60; the differences are bounded by the gap costs)
 //     s, z, a, b.. + 2 FB                    (the score table holds s + 2 FB as a positive int8)
 //     x, y         + (q + e - 1) + 0x8000,   x2, y2 + (q2 + e2 - 1) + 0x8000
 // With that offset a gap state equals 0x7fff exactly when it was reset to -(q + e) and has bit 15 set exactly when it continues:
 // the continuation flag is the stored value's top bit (no compare), and "t - z + 0x8000" has bit 15 set exactly when t is the
-// maximum.  33 -> 29 arithmetic/permute operations per cell pair, none of them a negation.
+// maximum.  The flag bytes are gathered by one top-bit-replicating PRMT per flag and a tree of multiply-adds (see the cell loop).
+// Per cell pair: 4 IADD3 + 2 VIMNMX3.S16x2 + 4 VIADDMNMX.U16x2 + 8 PRMT on the ALU pipe, 12 IMAD / IMAD.IADD on the FMA pipe
+// (21 ALU-pipe operations + 18 VIADD.16x2 in round 1).  tests/test_offset_form.py replays this arithmetic on the host.
 #pragma once
 #include <cuda_runtime.h>
 #include "mm_align.cuh"
